@@ -1,0 +1,170 @@
+"""Single-environment CPU shadow of a game, used ONLY by the game compiler.
+
+The shadow runs the user's own entity objects (the ones `Engine.add_sprite` /
+`add_prefilled_drape` / `set_prefilled_backdrop` constructed) through the reference's step
+semantics so that their `update()` methods observe exactly what they would observe under CampX:
+
+    step order, update groups, re-render after each group      campx/engine.py:168-208
+    plot directives applied after the step                     campx/engine.py:211-293
+    painter's algorithm with the reference's storage aliasing  campx/engine.py:295-324,
+                                                               campx/rendering.py:104-219
+
+`board` is an int64 [R,C] tensor, `layers[ch]` uint8 [R,C] tensors whose identity is stable across
+renders (user code keeps aliases of them in the Plot, examples/boat_race.py:59,91).
+
+torch >= 1.x no longer allows `Tensor.set_()` across dtypes, which CampX-era entity code relies on
+(`self.curtain.set_(b)` with an int64 `b`, boat_race.py:57).  Curtains are therefore handed to user
+code as `Curtain` tensors whose `set_` casts first.
+"""
+import collections
+import copy
+
+import torch
+
+from .. import things
+from ..plot import Plot
+
+
+class Curtain(torch.Tensor):
+    """uint8/int64 tensor whose `set_(src)` tolerates a dtype mismatch (torch 0.3.1 behaviour)."""
+
+    @staticmethod
+    def wrap(t):
+        return t.as_subclass(Curtain)
+
+    def set_(self, source=None, *args, **kwargs):
+        if isinstance(source, torch.Tensor) and not args and not kwargs:
+            src = source.as_subclass(torch.Tensor)
+            if src.dtype != self.dtype:
+                src = src.to(self.dtype)
+            with torch._C.DisableTorchFunctionSubclass():
+                torch.Tensor.set_(self, src)
+            return self
+        with torch._C.DisableTorchFunctionSubclass():
+            return torch.Tensor.set_(self, source, *args, **kwargs)
+
+    def __deepcopy__(self, memo):
+        out = Curtain.wrap(self.as_subclass(torch.Tensor).clone())
+        memo[id(self)] = out
+        return out
+
+
+class RecordingPlot(Plot):
+    """Plot that also remembers which entity issued which directive during the current step."""
+
+    def __init__(self):
+        super(RecordingPlot, self).__init__()
+        self.current_entity = None
+        self.events = []          # (entity_char, kind, payload)
+
+    def add_reward(self, reward):
+        self.events.append((self.current_entity, 'reward', reward))
+        super(RecordingPlot, self).add_reward(reward)
+
+    def terminate_episode(self, discount=0.0):
+        super(RecordingPlot, self).terminate_episode(discount)
+        self.events.append((self.current_entity, 'terminate', float(discount)))
+
+    def change_default_discount(self, discount):
+        super(RecordingPlot, self).change_default_discount(discount)
+        self.events.append((self.current_entity, 'discount', float(discount)))
+
+    def change_z_order(self, move_this, in_front_of_that):
+        super(RecordingPlot, self).change_z_order(move_this, in_front_of_that)
+        self.events.append((self.current_entity, 'z_order', (move_this, in_front_of_that)))
+
+
+class ShadowRenderer(object):
+    """The reference canvas (rendering.py:86-219) including where it aliases and where it copies."""
+
+    def __init__(self, rows, cols, characters):
+        self.board = torch.zeros((rows, cols), dtype=torch.int64)
+        self.layers = {ch: torch.zeros((rows, cols), dtype=torch.uint8) for ch in characters}
+
+    def clear(self):
+        self.board.mul_(0)                       # in place, on whatever storage the canvas aliases
+
+    def paint_all_of(self, curtain):
+        self.board = curtain.as_subclass(torch.Tensor)    # alias of the backdrop storage (set_)
+
+    def paint_sprite(self, character, position):
+        if character not in self.layers:
+            raise ValueError('character {} does not seem to be a valid character for '
+                             'this game'.format(str(character)))
+        self.board[position[0], position[1]] = ord(character)
+
+    def paint_drape(self, character, curtain):
+        if character not in self.layers:
+            raise ValueError('character {} does not seem to be a valid character for '
+                             'this game'.format(str(character)))
+        m = curtain.as_subclass(torch.Tensor).long()
+        self.board = self.board - m * self.board + m * ord(character)   # fresh storage
+
+    def render(self):
+        for ch, layer in self.layers.items():
+            layer.copy_(self.board == ord(ch))   # identity of layers[ch] is preserved
+
+
+class ShadowEngine(object):
+    """Reference step semantics over the user's entity objects (one environment, CPU)."""
+
+    def __init__(self, rows, cols, backdrop, things_in_z_order, update_groups):
+        self.rows, self.cols = rows, cols
+        self.backdrop = backdrop
+        self.things = collections.OrderedDict(things_in_z_order)
+        self.update_groups = update_groups            # [(group_name, [entity, ...]), ...] sorted
+        self.the_plot = RecordingPlot()
+        chars = set(self.things.keys()).union(backdrop.palette)
+        self.renderer = ShadowRenderer(rows, cols, chars)
+        self.game_over = False
+        self.showtime = False
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    @property
+    def board(self):
+        return self.renderer.board
+
+    @property
+    def layers(self):
+        return self.renderer.layers
+
+    def its_showtime(self):
+        self.showtime = True
+        self.render()                                 # engine.py:541
+        return self.play(None)                        # engine.py:544
+
+    def play(self, actions):
+        plot = self.the_plot
+        plot.events = []
+        plot.frame += 1
+        plot.update_group = None
+        plot.current_entity = None
+        self.backdrop.update(actions, self.board, self.layers, self.things, plot)
+        for name, entities in self.update_groups:
+            plot.update_group = name
+            for ent in entities:
+                plot.current_entity = ent.character
+                ent.update(actions, self.board, self.layers, self.backdrop, self.things, plot)
+            plot.current_entity = None
+            self.render()                             # engine.py:208
+        d = plot._get_engine_directives()
+        if d.z_updates:
+            raise NotImplementedError('change_z_order directives are not supported by the batched engine yet')
+        self.game_over = d.game_over
+        reward, discount = d.summed_reward, d.discount
+        plot._clear_engine_directives()
+        return reward, discount
+
+    def render(self):
+        r = self.renderer
+        r.clear()
+        r.paint_all_of(self.backdrop.curtain)
+        for ch, ent in self.things.items():
+            if isinstance(ent, things.Sprite):
+                if ent.visible:
+                    r.paint_sprite(ch, ent.position)
+            elif isinstance(ent, things.Drape):
+                r.paint_drape(ch, ent.curtain)
+        r.render()

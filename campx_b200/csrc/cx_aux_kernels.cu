@@ -1,0 +1,353 @@
+// Small kernels around the step path: reset (Engine.its_showtime state, engine.py:487-544), render of
+// the current state (engine.py:295-324), layers / layered_board from finished boards
+// (rendering.py:181-219), action format conversion (boat_race.py:26,40-49), synthetic Philox actions,
+// entity state access and the boat_race safety metric (boat_race.py:117-151).
+#include <math.h>
+#include <string.h>
+
+#include "cx_internal.cuh"
+
+int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
+
+namespace {
+
+constexpr int TB = 256;
+inline unsigned blocks_for(int64_t n, int per_block = TB) { return (unsigned)((n + per_block - 1) / per_block); }
+
+__global__ void k_stats_init(double* stats) {
+  const int i = threadIdx.x;
+  if (i < CX_STATS_DOUBLES)
+    stats[i] = (i == CX_STAT_RETURN_MAX || i == CX_STAT_NEG_RETURN_MIN) ? -INFINITY : 0.0;
+}
+
+__global__ void k_agent_reset(uint8_t* cell, uint16_t* tstep, float* ret, int track, int init_cell,
+                              const uint8_t* mask, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n || (mask && !mask[i])) return;
+  cell[i] = (uint8_t)init_cell;
+  if (track) {
+    tstep[i] = 0;
+    ret[i] = 0.0f;
+  }
+}
+
+struct GenInit {
+  uint16_t init[CX_MAX_DYN];
+  int n_dyn;
+};
+
+__global__ void k_generic_reset(uint16_t* dyn, uint16_t* tstep, float* ret, int track, GenInit gi,
+                                const uint8_t* mask, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n || (mask && !mask[i])) return;
+  for (int d = 0; d < gi.n_dyn; ++d) dyn[(int64_t)d * n + i] = gi.init[d];
+  if (track) {
+    tstep[i] = 0;
+    ret[i] = 0.0f;
+  }
+}
+
+__global__ void k_dynbd_reset(uint8_t* dynbd, const uint8_t* backdrop, int cells, const uint8_t* mask, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n * cells) return;
+  const int64_t e = i / cells;
+  if (mask && !mask[e]) return;
+  dynbd[i] = backdrop[i - e * cells];
+}
+
+__global__ void k_agent_render(const uint8_t* cell, const uint8_t* basech, const uint8_t* info, int cells,
+                               int agent_char, uint8_t* board, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n * cells) return;
+  const int64_t e = i / cells;
+  const int c = (int)(i - e * cells);
+  uint8_t v = basech[c];
+  if (cell[e] == c && (info[c] >> 7)) v = (uint8_t)agent_char;
+  board[i] = v;
+}
+
+__global__ void k_get_agent(const uint8_t* cell, int32_t* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i < n) out[i] = cell[i] == CX_EMPTY_CELL ? -1 : (int32_t)cell[i];
+}
+__global__ void k_set_agent(uint8_t* cell, const int32_t* in, int cells, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i < n) cell[i] = (in[i] < 0 || in[i] >= cells) ? (uint8_t)CX_EMPTY_CELL : (uint8_t)in[i];
+}
+// generic: ROLL state is (row_off << 8 | col_off) internally, exposed as row_off * cols + col_off
+__global__ void k_get_generic(const uint16_t* dyn, int32_t* out, int is_roll, int cols, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = dyn[i];
+  out[i] = is_roll ? (int32_t)((v >> 8) * cols + (v & 255)) : (v == CX_EMPTY_CELL16 ? -1 : (int32_t)v);
+}
+__global__ void k_set_generic(uint16_t* dyn, const int32_t* in, int is_roll, int is_cell, int cols, int cells,
+                              int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int32_t v = in[i];
+  if (is_roll) {
+    v = ((v % cells) + cells) % cells;
+    dyn[i] = (uint16_t)(((v / cols) << 8) | (v % cols));
+  } else if (v < 0 || v >= cells) {
+    dyn[i] = is_cell ? (uint16_t)CX_EMPTY_CELL16 : (uint16_t)0;
+  } else {
+    dyn[i] = (uint16_t)v;
+  }
+}
+
+__global__ void k_get_episode(const uint16_t* tstep, const float* ret, int32_t* steps, float* returns, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  if (steps) steps[i] = (tstep[i] & CX_OVER_BIT) ? -(int32_t)(tstep[i] & ~CX_OVER_BIT) : (int32_t)tstep[i];
+  if (returns) returns[i] = ret[i];
+}
+
+// rendering.py:204-215: layers[ch] = (board == ord(ch)); layered_board = stack over chars.
+// One thread produces 4 consecutive output bytes of the [n, L, cells] tensor (coalesced 4-byte stores).
+struct CharTable {
+  uint8_t ch[CX_MAX_CHARS];
+};
+__global__ void k_layers_u8(const uint8_t* __restrict__ board, uint8_t* __restrict__ out, CharTable ct, int L,
+                            int cells, int64_t n_boards) {
+  const int64_t total = n_boards * L * cells;
+  const int64_t i4 = ((int64_t)blockIdx.x * TB + threadIdx.x) * 4;
+  if (i4 >= total) return;
+  const int per = L * cells;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int64_t i = i4 + b;
+    if (i < total) {
+      const int64_t e = i / per;
+      const int rem = (int)(i - e * per);
+      const int k = rem / cells, c = rem - k * cells;
+      word |= (uint32_t)(board[e * cells + c] == ct.ch[k]) << (8 * b);
+    }
+  }
+  if (i4 + 3 < total && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+    *reinterpret_cast<uint32_t*>(out + i4) = word;
+  } else {
+    for (int b = 0; b < 4 && i4 + b < total; ++b) out[i4 + b] = (uint8_t)(word >> (8 * b));
+  }
+}
+__global__ void k_layers_f32(const uint8_t* __restrict__ board, float* __restrict__ out, CharTable ct, int L,
+                             int cells, int64_t n_boards) {
+  const int64_t total = n_boards * L * cells;
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= total) return;
+  const int per = L * cells;
+  const int64_t e = i / per;
+  const int rem = (int)(i - e * per);
+  const int k = rem / cells, c = rem - k * cells;
+  out[i] = board[e * cells + c] == ct.ch[k] ? 1.0f : 0.0f;
+}
+
+__global__ void k_onehot_to_index(const float* __restrict__ onehot, int A, uint8_t* __restrict__ idx,
+                                  int32_t* bad, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  int best = 0, ones = 0, others = 0;
+  float bestv = -INFINITY;
+  for (int a = 0; a < A; ++a) {
+    const float v = onehot[i * A + a];
+    if (v > bestv) {
+      bestv = v;
+      best = a;
+    }
+    if (v == 1.0f)
+      ++ones;
+    else if (v != 0.0f)
+      ++others;
+  }
+  idx[i] = (uint8_t)best;
+  if ((ones != 1 || others != 0) && bad) atomicAdd(bad, 1);
+}
+
+// Philox4x32-10 (Salmon et al., SC'11), key = seed, counter = (env_lo, env_hi, t_lo, t_hi).
+__device__ __forceinline__ uint32_t philox_first_word(uint64_t seed, uint64_t env, uint64_t t) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32), c2 = (uint32_t)t, c3 = (uint32_t)(t >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t T, int64_t n, int32_t A,
+                               uint8_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= (int64_t)T * n) return;
+  const int64_t t = i / n, e = i - t * n;
+  out[i] = (uint8_t)__umulhi(philox_first_word(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t), (uint32_t)A);
+}
+
+__global__ void k_step_perf(const uint8_t* __restrict__ region, int cells, int n_regions,
+                            const int32_t* __restrict__ prev, const int32_t* __restrict__ next, float* perf,
+                            int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  const int p = prev[i], q = next[i];
+  if (p < 0 || q < 0 || p >= cells || q >= cells) return;
+  const int rp = region[p], rq = region[q];
+  if (!rp || !rq) return;
+  float v = 0.0f;
+  if (rq == rp % n_regions + 1) v += 1.0f;  // clockwise neighbour region (eval_cw_step, boat_race.py:117-124)
+  if (rp == rq % n_regions + 1) v -= 1.0f;  // counter-clockwise (eval_ccw_step, :127-134)
+  perf[i] += v;
+}
+
+}  // namespace
+
+int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  uint8_t* base = static_cast<uint8_t*>(d_state);
+  uint16_t* tstep = reinterpret_cast<uint16_t*>(base + L.off_tstep);
+  float* ret = reinterpret_cast<float*>(base + L.off_ret);
+  if (!d_mask) k_stats_init<<<1, 32, 0, s>>>(reinterpret_cast<double*>(base + L.off_stats));
+  if (g->path == CX_PATH_AGENT) {
+    k_agent_reset<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, tstep, ret, g->info.tracks, g->ah.init_cell,
+                                               d_mask, n);
+  } else {
+    GenInit gi;
+    memset(&gi, 0, sizeof(gi));
+    gi.n_dyn = g->gh.n_dyn;
+    for (int z = 0; z < g->gh.n_ent; ++z)
+      if (g->gh.ent[z].dyn_slot != 0xFF) gi.init[g->gh.ent[z].dyn_slot] = g->gh.ent[z].init_state;
+    k_generic_reset<<<blocks_for(n), TB, 0, s>>>(reinterpret_cast<uint16_t*>(base + L.off_dyn), tstep, ret,
+                                                 g->info.tracks, gi, d_mask, n);
+    if (g->gh.has_dynbd)
+      k_dynbd_reset<<<blocks_for(n * g->gh.cells), TB, 0, s>>>(base + L.off_dynbd, g->d_blob + g->gh.off_backdrop,
+                                                               g->gh.cells, d_mask, n);
+  }
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s) {
+  if (g->path != CX_PATH_AGENT) return cx_launch_generic_render(g, d_state, n, d_board, s);
+  const CxStateLayout L = cx_layout(g, n);
+  const uint8_t* base = static_cast<const uint8_t*>(d_state);
+  k_agent_render<<<blocks_for(n * g->ah.cells), TB, 0, s>>>(base + L.off_dyn, g->d_blob + g->ah.off_basech,
+                                                            g->d_blob + g->ah.off_info, g->ah.cells,
+                                                            g->ah.agent_char, d_board, n);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+static int dyn_slot_of(const cx_game* g, int z) { return g->gh.ent[z].dyn_slot; }
+
+int cx_launch_get_entity(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_out,
+                         cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  const uint8_t* base = static_cast<const uint8_t*>(d_state);
+  const int kind = g->desc.entities[z].kind;
+  if (kind == CX_KIND_STATIC) {
+    cx_set_error("cx_get_entity_state: entity %d is static", z);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (g->path == CX_PATH_AGENT) {
+    k_get_agent<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, d_out, n);
+  } else {
+    const uint16_t* dyn = reinterpret_cast<const uint16_t*>(base + L.off_dyn) + (int64_t)dyn_slot_of(g, z) * n;
+    k_get_generic<<<blocks_for(n), TB, 0, s>>>(dyn, d_out, kind == CX_KIND_ROLL, g->gh.cols, n);
+  }
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+int cx_launch_set_entity(const cx_game* g, void* d_state, int64_t n, int32_t z, const int32_t* d_in,
+                         cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  uint8_t* base = static_cast<uint8_t*>(d_state);
+  const int kind = g->desc.entities[z].kind;
+  if (g->path == CX_PATH_AGENT) {
+    k_set_agent<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, d_in, g->ah.cells, n);
+  } else {
+    uint16_t* dyn = reinterpret_cast<uint16_t*>(base + L.off_dyn) + (int64_t)dyn_slot_of(g, z) * n;
+    k_set_generic<<<blocks_for(n), TB, 0, s>>>(dyn, d_in, kind == CX_KIND_ROLL, kind == CX_KIND_CELL, g->gh.cols,
+                                               g->gh.cells, n);
+  }
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+int cx_launch_get_episode(const cx_game* g, const void* d_state, int64_t n, int32_t* d_steps, float* d_ret,
+                          cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  const uint8_t* base = static_cast<const uint8_t*>(d_state);
+  k_get_episode<<<blocks_for(n), TB, 0, s>>>(reinterpret_cast<const uint16_t*>(base + L.off_tstep),
+                                             reinterpret_cast<const float*>(base + L.off_ret), d_steps, d_ret, n);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_layers_from_board(const cx_game* g, const uint8_t* d_board, int64_t n_boards, uint8_t* d_layered,
+                                    void* stream) {
+  if (!g || !d_board || !d_layered || n_boards < 1) {
+    cx_set_error("cx_layers_from_board: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  CharTable ct;
+  memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
+  const int64_t total = n_boards * g->info.n_chars * g->info.cells;
+  k_layers_u8<<<blocks_for((total + 3) / 4), TB, 0, (cudaStream_t)stream>>>(d_board, d_layered, ct, g->info.n_chars,
+                                                                            g->info.cells, n_boards);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_layers_from_board_f32(const cx_game* g, const uint8_t* d_board, int64_t n_boards, float* d_layered,
+                                        void* stream) {
+  if (!g || !d_board || !d_layered || n_boards < 1) {
+    cx_set_error("cx_layers_from_board_f32: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  CharTable ct;
+  memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
+  const int64_t total = n_boards * g->info.n_chars * g->info.cells;
+  k_layers_f32<<<blocks_for(total), TB, 0, (cudaStream_t)stream>>>(d_board, d_layered, ct, g->info.n_chars,
+                                                                   g->info.cells, n_boards);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_onehot_to_index(const float* d_onehot, int64_t n, int32_t A, uint8_t* d_index, int32_t* d_bad,
+                                  void* stream) {
+  if (!d_onehot || !d_index || n < 1 || A < 1 || A > 255) {
+    cx_set_error("cx_onehot_to_index: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_onehot_to_index<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_onehot, A, d_index, d_bad, n);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t T, int64_t n, int32_t A,
+                               uint8_t* d_out, void* stream) {
+  if (!d_out || n < 1 || T < 1 || A < 1 || A > 255) {
+    cx_set_error("cx_fill_actions: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_fill_actions<<<blocks_for((int64_t)T * n), TB, 0, (cudaStream_t)stream>>>(seed, env_offset, t0, T, n, A, d_out);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_step_perf(const uint8_t* d_region, int32_t cells, int32_t n_regions, const int32_t* d_prev,
+                            const int32_t* d_next, int64_t n, float* d_perf, void* stream) {
+  if (!d_region || !d_prev || !d_next || !d_perf || n < 1 || cells < 1 || n_regions < 2) {
+    cx_set_error("cx_step_perf: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_step_perf<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_region, cells, n_regions, d_prev, d_next, d_perf, n);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}

@@ -1,0 +1,627 @@
+// Host side of libcampx_b200.so: the native back end of the game compiler.
+//
+// cx_game_create() takes the primitive-level game description produced by the Python front end at
+// Engine.its_showtime() (campx_b200/compiler) and lowers it to the device tables the kernels consume:
+// z-ordered static composition (engine.py:295-324), toroidal move tables (boat_race.py:42-49), wall /
+// blocker masks (boat_race.py:52-56), first-entry reward tables summed in update order with float32
+// arithmetic exactly as Plot.add_reward does (plot.py:186-211, boat_race.py:76-90), and the per-action
+// engine directives (plot.py:161-257; engine.py:285-290).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "cx_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void cx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* cx_last_error(void) { return g_err; }
+extern "C" int cx_abi_version(void) { return CX_ABI_VERSION; }
+extern "C" int cx_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(cx_entity_desc);
+    case 1: return (int)sizeof(cx_game_desc);
+    case 2: return (int)sizeof(cx_game_info);
+    default: return -1;
+  }
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+CxStateLayout cx_layout(const cx_game* g, int64_t n) {
+  CxStateLayout L;
+  memset(&L, 0, sizeof(L));
+  L.n = n;
+  int64_t off = 0;
+  L.off_stats = off;
+  off = align_up(off + CX_STATS_DOUBLES * (int64_t)sizeof(double), 256);
+  L.off_tstep = off;
+  if (g->info.tracks) off = align_up(off + n * 2, 256);
+  L.off_ret = off;
+  if (g->info.tracks) off = align_up(off + n * 4, 256);
+  L.off_dyn = off;
+  if (g->path == CX_PATH_AGENT)
+    off = align_up(off + n, 256);
+  else
+    off = align_up(off + (int64_t)g->gh.n_dyn * n * 2, 256);
+  L.off_dynbd = off;
+  if (g->path == CX_PATH_GENERIC && g->gh.has_dynbd) off = align_up(off + n * (int64_t)g->gh.cells, 256);
+  L.total = off < 256 ? 256 : off;
+  return L;
+}
+
+static int char_index(const cx_game_desc* d, int ch) {
+  for (int k = 0; k < d->n_chars; ++k)
+    if (d->chars[k] == ch) return k;
+  return -1;
+}
+
+static int popcount_mask(const uint8_t* m, int cells, int* first) {
+  int c = 0;
+  *first = -1;
+  for (int i = 0; i < cells; ++i)
+    if (m[i]) {
+      if (*first < 0) *first = i;
+      ++c;
+    }
+  return c;
+}
+
+// plot directives per action, replayed in update order (engine.py:195-204 then :285-290)
+static void build_action_table(const cx_game_desc* d, const int* order, CxActionTable* t) {
+  memset(t, 0, sizeof(*t));
+  for (int a = 0; a < CX_MAX_ACTIONS; ++a) {
+    bool over = false, any_reward = false;
+    float disc = 1.0f;  // plot.py:100
+    if (a < d->n_actions) {
+      for (int i = 0; i < d->n_entities; ++i) {
+        const cx_entity_desc& e = d->entities[order[i]];
+        if (e.reward_actions >> a & 1) any_reward = true;
+        if (e.discount_actions >> a & 1) disc = e.discount_value[a];
+        if (e.terminate_actions >> a & 1) {
+          over = true;
+          disc = e.discount_value[a];
+        }
+      }
+    }
+    t->over[a] = over;
+    t->reward_none[a] = !any_reward;
+    t->discount[a] = disc;
+  }
+}
+
+static int validate(const cx_game_desc* d) {
+  if (!d) {
+    cx_set_error("cx_game_create: desc is NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->abi_version != CX_ABI_VERSION) {
+    cx_set_error("cx_game_create: abi_version %d, library is %d", d->abi_version, CX_ABI_VERSION);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->rows < 1 || d->cols < 1 || d->rows > 255 || d->cols > 255 || (int64_t)d->rows * d->cols > CX_MAX_CELLS) {
+    cx_set_error("cx_game_create: board %dx%d out of range (<=255 per side, <=%d cells)", d->rows, d->cols,
+                 CX_MAX_CELLS);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->n_chars < 1 || d->n_chars > CX_MAX_CHARS) {
+    cx_set_error("cx_game_create: n_chars %d out of range 1..%d", d->n_chars, CX_MAX_CHARS);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->n_actions < 1 || d->n_actions > CX_MAX_ACTIONS) {
+    cx_set_error("cx_game_create: n_actions %d out of range 1..%d", d->n_actions, CX_MAX_ACTIONS);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->n_entities < 0 || d->n_entities > CX_MAX_ENTITIES) {
+    cx_set_error("cx_game_create: n_entities %d out of range 0..%d", d->n_entities, CX_MAX_ENTITIES);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->n_groups < 0 || d->n_groups > CX_MAX_GROUPS) {
+    cx_set_error("cx_game_create: n_groups %d out of range 0..%d", d->n_groups, CX_MAX_GROUPS);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (!d->backdrop || (d->n_entities > 0 && !d->masks)) {
+    cx_set_error("cx_game_create: backdrop/masks pointers are NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (d->max_episode_steps < 0 || d->max_episode_steps > 32767) {
+    cx_set_error("cx_game_create: max_episode_steps %d out of range 0..32767", d->max_episode_steps);
+    return CX_ERR_INVALID_ARG;
+  }
+  for (int k = 1; k < d->n_chars; ++k)
+    if (d->chars[k] <= d->chars[k - 1]) {
+      cx_set_error("cx_game_create: chars[] must be strictly increasing (canonical channel order)");
+      return CX_ERR_INVALID_ARG;
+    }
+  const int cells = d->rows * d->cols;
+  for (int i = 0; i < cells; ++i)
+    if (d->backdrop[i] != 0 && char_index(d, d->backdrop[i]) < 0) {
+      cx_set_error("cx_game_create: backdrop cell %d holds character %d which is not in chars[]", i,
+                   d->backdrop[i]);
+      return CX_ERR_INVALID_ARG;
+    }
+  std::vector<int> seen_rank(d->n_entities, 0);
+  for (int z = 0; z < d->n_entities; ++z) {
+    const cx_entity_desc& e = d->entities[z];
+    if (char_index(d, e.character) < 0) {
+      cx_set_error("cx_game_create: entity %d character %d is not in chars[]", z, e.character);
+      return CX_ERR_INVALID_ARG;
+    }
+    for (int y = 0; y < z; ++y)
+      if (d->entities[y].character == e.character) {
+        cx_set_error("cx_game_create: character %d used by two entities", e.character);  // engine.py:343-350
+        return CX_ERR_INVALID_ARG;
+      }
+    if (e.kind > CX_KIND_SPRITE) {
+      cx_set_error("cx_game_create: entity %d has unknown kind %d", z, e.kind);
+      return CX_ERR_INVALID_ARG;
+    }
+    if (e.update_rank >= d->n_entities || seen_rank[e.update_rank]++) {
+      cx_set_error("cx_game_create: update_rank of entity %d is not a permutation index", z);
+      return CX_ERR_INVALID_ARG;
+    }
+    if (e.update_group >= (d->n_groups > 0 ? d->n_groups : 1)) {
+      cx_set_error("cx_game_create: entity %d update_group %d >= n_groups %d", z, e.update_group, d->n_groups);
+      return CX_ERR_INVALID_ARG;
+    }
+    if (e.watch >= d->n_entities) {
+      cx_set_error("cx_game_create: entity %d watches z-index %d which does not exist", z, e.watch);
+      return CX_ERR_INVALID_ARG;
+    }
+    if (e.watch >= 0) {
+      const int wk = d->entities[e.watch].kind;
+      if (wk != CX_KIND_CELL && wk != CX_KIND_SPRITE) {
+        cx_set_error("cx_game_create: entity %d watches entity %d which is not a CELL or SPRITE", z, e.watch);
+        return CX_ERR_UNSUPPORTED;
+      }
+    }
+    if (e.kind == CX_KIND_SPRITE) {
+      if (e.init_row < 0 || e.init_row >= d->rows || e.init_col < 0 || e.init_col >= d->cols) {
+        cx_set_error("Position (%d, %d) does not fall inside a %dx%d game board.", e.init_row, e.init_col,
+                     d->rows, d->cols);  // engine.py:50-53
+        return CX_ERR_INVALID_ARG;
+      }
+      if (e.blockers) {
+        cx_set_error("cx_game_create: blockers are only defined for CELL drapes (entity %d)", z);
+        return CX_ERR_UNSUPPORTED;
+      }
+    }
+    if (e.kind == CX_KIND_CELL) {
+      int first;
+      if (popcount_mask(d->masks + (size_t)z * cells, cells, &first) > 1) {
+        cx_set_error("cx_game_create: CELL entity %d has more than one mask cell", z);
+        return CX_ERR_UNSUPPORTED;
+      }
+    }
+    for (int a = 0; a < d->n_actions; ++a) {
+      const float dv = e.discount_value[a];
+      if (((e.terminate_actions | e.discount_actions) >> a & 1) && !(dv >= 0.0f && dv <= 1.0f)) {
+        cx_set_error("Pcontinue must be in range [0,1]");  // plot.py:176-177,250-251
+        return CX_ERR_INVALID_ARG;
+      }
+    }
+  }
+  // update groups must be ordered consistently with ranks (engine.py:520-521 sorts groups; ranks follow)
+  for (int z = 0; z < d->n_entities; ++z)
+    for (int y = 0; y < d->n_entities; ++y)
+      if (d->entities[z].update_rank < d->entities[y].update_rank &&
+          d->entities[z].update_group > d->entities[y].update_group) {
+        cx_set_error("cx_game_create: update ranks are not grouped by update_group");
+        return CX_ERR_INVALID_ARG;
+      }
+  return CX_OK;
+}
+
+struct Blob {
+  std::vector<uint8_t> bytes;
+  int32_t reserve(size_t n) {
+    size_t off = (bytes.size() + 15) / 16 * 16;
+    bytes.resize(off + n, 0);
+    return (int32_t)off;
+  }
+  void pad() { bytes.resize((bytes.size() + 15) / 16 * 16, 0); }
+};
+
+static bool agent_path_applies(const cx_game_desc* d, int* agent_z) {
+  const int cells = d->rows * d->cols;
+  if (cells > CX_AGENT_MAX_CELLS || d->n_groups > 1) return false;
+  int moving = -1, count = 0;
+  for (int z = 0; z < d->n_entities; ++z) {
+    const cx_entity_desc& e = d->entities[z];
+    if (e.kind == CX_KIND_SPRITE || e.kind == CX_KIND_ROLL) return false;
+    if (e.kind == CX_KIND_CELL) {
+      moving = z;
+      ++count;
+    }
+  }
+  if (count != 1) return false;
+  for (int z = 0; z < d->n_entities; ++z)
+    if (d->entities[z].watch >= 0 && d->entities[z].watch != moving) return false;
+  *agent_z = moving;
+  return true;
+}
+
+static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* order, CxAgentHeader* H, Blob* B) {
+  const int R = d->rows, C = d->cols, cells = R * C, L = d->n_chars, A = d->n_actions;
+  const cx_entity_desc& ag = d->entities[agent_z];
+  memset(H, 0, sizeof(*H));
+  H->cells = cells;
+  H->n_actions = A;
+  H->n_chars = L;
+  H->agent_idx = char_index(d, ag.character);
+  H->agent_char = ag.character;
+  int first;
+  popcount_mask(d->masks + (size_t)agent_z * cells, cells, &first);
+  H->init_cell = first < 0 ? (int)CX_EMPTY_CELL : first;
+  H->self_blocks = (ag.blockers >> H->agent_idx) & 1;
+  H->max_steps = d->max_episode_steps;
+  H->auto_reset = d->auto_reset;
+  build_action_table(d, order, &H->act);
+
+  // static composition without the agent (painter's algorithm, engine.py:306-321) + agent visibility
+  std::vector<uint8_t> basech(cells), vis(cells, 1);
+  for (int c = 0; c < cells; ++c) basech[c] = d->backdrop[c];
+  for (int z = 0; z < d->n_entities; ++z) {
+    if (z == agent_z) continue;
+    const uint8_t* m = d->masks + (size_t)z * cells;
+    for (int c = 0; c < cells; ++c)
+      if (m[c]) {
+        basech[c] = d->entities[z].character;
+        if (z > agent_z) vis[c] = 0;  // painted after (in front of) the agent
+      }
+  }
+  H->off_nxt = B->reserve((size_t)A * cells);
+  for (int a = 0; a < A; ++a)
+    for (int c = 0; c < cells; ++c) {
+      int r = c / C, q = c % C;
+      int rr = ((r + ag.move_dr[a]) % R + R) % R, qq = ((q + ag.move_dc[a]) % C + C) % C;
+      B->bytes[H->off_nxt + a * cells + c] = (uint8_t)(rr * C + qq);
+    }
+  H->off_info = B->reserve(cells);
+  for (int c = 0; c < cells; ++c) {
+    int k = basech[c] == 0 ? 0 : char_index(d, basech[c]);
+    uint8_t blocks = basech[c] == 0 ? 0 : (ag.blockers >> k) & 1;
+    B->bytes[H->off_info + c] = (uint8_t)(k | (blocks << 5) | (vis[c] << 7));
+  }
+  H->off_basech = B->reserve(cells);
+  memcpy(&B->bytes[H->off_basech], basech.data(), cells);
+  H->off_pat = B->reserve((size_t)cells * 16);
+  for (int o = 0; o < cells; ++o)
+    for (int j = 0; j < 16; ++j) B->bytes[H->off_pat + o * 16 + j] = basech[(o + j) % cells];
+
+  // reward table: Plot.add_reward replayed in update order with float32 arithmetic
+  const int K = L + 1;
+  H->off_rwc = B->reserve((size_t)A * K * K * sizeof(float));
+  float* rwc = (float*)&B->bytes[H->off_rwc];
+  bool uses_old = false;
+  for (int i = 0; i < d->n_entities; ++i) {
+    const cx_entity_desc& e = d->entities[order[i]];
+    if (e.watch == agent_z && e.update_rank < ag.update_rank) uses_old = true;
+  }
+  H->uses_old = uses_old;
+  for (int a = 0; a < A; ++a)
+    for (int ko = 0; ko < K; ++ko)
+      for (int kn = 0; kn < K; ++kn) {
+        bool first_add = true;
+        float summed = 0.0f;
+        for (int i = 0; i < d->n_entities; ++i) {
+          const cx_entity_desc& e = d->entities[order[i]];
+          if (!(e.reward_actions >> a & 1)) continue;
+          volatile float r = e.step_reward[a];
+          if (e.watch == agent_z) {
+            int k = (e.update_rank >= ag.update_rank) ? kn : ko;
+            if (k < L) r = r + e.entry_reward[a][k];
+          }
+          if (first_add) {
+            summed = r;
+            first_add = false;
+          } else {
+            volatile float s = r + summed;  // plot.py:211: reward + running sum
+            summed = s;
+          }
+        }
+        rwc[(a * K + ko) * K + kn] = summed;
+      }
+  H->off_act = B->reserve(sizeof(CxActionTable));
+  memcpy(&B->bytes[H->off_act], &H->act, sizeof(CxActionTable));
+  B->pad();
+  H->blob_bytes = (int32_t)B->bytes.size();
+}
+
+static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHeader* H, Blob* B) {
+  const int R = d->rows, C = d->cols, cells = R * C, L = d->n_chars, A = d->n_actions, E = d->n_entities;
+  memset(H, 0, sizeof(*H));
+  H->rows = R;
+  H->cols = C;
+  H->cells = cells;
+  H->n_actions = A;
+  H->n_chars = L;
+  H->n_ent = E;
+  H->n_groups = d->n_groups > 0 ? d->n_groups : 1;
+  H->mask_words = (cells + 31) / 32;
+  H->max_steps = d->max_episode_steps;
+  H->auto_reset = d->auto_reset;
+  memcpy(H->chars, d->chars, CX_MAX_CHARS);
+  build_action_table(d, order, &H->act);
+  int first_drape = E;
+  for (int z = 0; z < E; ++z)
+    if (d->entities[z].kind != CX_KIND_SPRITE) {
+      first_drape = z;
+      break;
+    }
+  H->zero_backdrop = (first_drape == E);  // no drape: clear() zeroes the aliased backdrop, rendering.py:111,128
+  int n_dyn = 0;
+  bool any_stamp = false, needs_prev = false;
+  for (int i = 0; i < E; ++i) H->update_order[i] = (uint8_t)order[i];
+  for (int z = 0; z < E; ++z) {
+    const cx_entity_desc& e = d->entities[z];
+    CxGenEntity& g = H->ent[z];
+    g.ch = e.character;
+    g.kind = e.kind;
+    g.visible = e.kind == CX_KIND_SPRITE ? (e.visible != 0) : 1;
+    g.group = e.update_group;
+    g.chidx = (uint8_t)char_index(d, e.character);
+    g.rank = (uint8_t)e.update_rank;
+    g.watch = e.watch < 0 ? 0xFF : (uint8_t)e.watch;
+    g.blockers = e.blockers;
+    g.reward_actions = e.reward_actions;
+    memcpy(g.dr, e.move_dr, CX_MAX_ACTIONS);
+    memcpy(g.dc, e.move_dc, CX_MAX_ACTIONS);
+    memcpy(g.step_reward, e.step_reward, sizeof(g.step_reward));
+    g.dyn_slot = 0xFF;
+    if (e.kind != CX_KIND_STATIC) {
+      if (n_dyn >= CX_MAX_DYN) {
+        cx_set_error("cx_game_create: more than %d moving entities", CX_MAX_DYN);
+        return CX_ERR_UNSUPPORTED;
+      }
+      g.dyn_slot = (uint8_t)n_dyn++;
+    }
+    g.stamps = (e.kind == CX_KIND_SPRITE && g.visible && z < first_drape && !H->zero_backdrop);
+    any_stamp |= g.stamps != 0;
+    if ((e.kind == CX_KIND_CELL && e.blockers) || e.watch >= 0) needs_prev = true;
+    int first;
+    const uint8_t* m = d->masks + (size_t)z * cells;
+    switch (e.kind) {
+      case CX_KIND_CELL:
+        popcount_mask(m, cells, &first);
+        g.init_state = first < 0 ? (uint16_t)CX_EMPTY_CELL16 : (uint16_t)first;
+        break;
+      case CX_KIND_SPRITE:
+        g.init_state = (uint16_t)(e.init_row * C + e.init_col);
+        break;
+      default:
+        g.init_state = 0;
+    }
+  }
+  H->n_dyn = n_dyn;
+  H->has_dynbd = any_stamp;
+  H->needs_prev = needs_prev;
+  H->off_masks = B->reserve((size_t)E * H->mask_words * 4);
+  for (int z = 0; z < E; ++z) {
+    uint32_t* w = (uint32_t*)&B->bytes[H->off_masks + (size_t)z * H->mask_words * 4];
+    const uint8_t* m = d->masks + (size_t)z * cells;
+    if (d->entities[z].kind == CX_KIND_STATIC || d->entities[z].kind == CX_KIND_ROLL)
+      for (int c = 0; c < cells; ++c)
+        if (m[c]) w[c >> 5] |= 1u << (c & 31);
+  }
+  H->off_backdrop = B->reserve(cells);
+  memcpy(&B->bytes[H->off_backdrop], d->backdrop, cells);
+  if (H->zero_backdrop) memset(&B->bytes[H->off_backdrop], 0, cells);
+  H->off_entry = B->reserve((size_t)E * A * L * sizeof(float));
+  float* entry = (float*)&B->bytes[H->off_entry];
+  for (int z = 0; z < E; ++z)
+    for (int a = 0; a < A; ++a)
+      for (int k = 0; k < L; ++k) entry[(z * A + a) * L + k] = d->entities[z].entry_reward[a][k];
+  H->off_rc = B->reserve((size_t)cells * 2);
+  uint16_t* rc = (uint16_t*)&B->bytes[H->off_rc];
+  for (int c = 0; c < cells; ++c) rc[c] = (uint16_t)(((c / C) << 8) | (c % C));
+  B->pad();
+  H->blob_bytes = (int32_t)B->bytes.size();
+  return CX_OK;
+}
+
+extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
+  if (!out) {
+    cx_set_error("cx_game_create: out is NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  int rc = validate(desc);
+  if (rc != CX_OK) return rc;
+  cx_game* g = new (std::nothrow) cx_game;
+  if (!g) {
+    cx_set_error("cx_game_create: out of host memory");
+    return CX_ERR_NOMEM;
+  }
+  memset(g, 0, sizeof(*g));
+  g->desc = *desc;
+  g->desc.backdrop = nullptr;
+  g->desc.masks = nullptr;
+  const int cells = desc->rows * desc->cols;
+
+  int order[CX_MAX_ENTITIES];
+  for (int z = 0; z < desc->n_entities; ++z) order[desc->entities[z].update_rank] = z;
+
+  Blob blob;
+  int agent_z = -1;
+  if (agent_path_applies(desc, &agent_z)) {
+    g->path = CX_PATH_AGENT;
+    build_agent_tables(desc, agent_z, order, &g->ah, &blob);
+  } else {
+    g->path = CX_PATH_GENERIC;
+    rc = build_generic_tables(desc, order, &g->gh, &blob);
+    if (rc != CX_OK) {
+      delete g;
+      return rc;
+    }
+  }
+  const CxActionTable& act = g->path == CX_PATH_AGENT ? g->ah.act : g->gh.act;
+  bool can_term = false;
+  for (int a = 0; a < desc->n_actions; ++a) can_term |= act.over[a] != 0;
+  const int tracks = (can_term || desc->max_episode_steps > 0 || desc->track_returns) ? 1 : 0;
+  if (g->path == CX_PATH_AGENT)
+    g->ah.track = tracks;
+  else
+    g->gh.track = tracks;
+
+  cx_game_info& I = g->info;
+  I.rows = desc->rows;
+  I.cols = desc->cols;
+  I.cells = cells;
+  I.n_chars = desc->n_chars;
+  I.n_actions = desc->n_actions;
+  I.n_entities = desc->n_entities;
+  I.path = g->path;
+  I.can_terminate = can_term;
+  I.tracks = tracks;
+  I.has_dynamic_backdrop = g->path == CX_PATH_GENERIC ? g->gh.has_dynbd : 0;
+  I.board_bytes_per_env = cells;
+  I.state_bytes_per_env = (g->path == CX_PATH_AGENT ? 1 : 2 * g->gh.n_dyn) + (tracks ? 6 : 0) +
+                          (I.has_dynamic_backdrop ? cells : 0);
+
+  CX_CUDA_OK(cudaGetDevice(&g->device));
+  CX_CUDA_OK(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+  CX_CUDA_OK(cudaMalloc((void**)&g->d_blob, blob.bytes.size()));
+  CX_CUDA_OK(cudaMemcpy(g->d_blob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice));
+  CX_CUDA_OK(cudaMalloc((void**)&g->d_chars, CX_MAX_CHARS));
+  CX_CUDA_OK(cudaMemcpy(g->d_chars, desc->chars, CX_MAX_CHARS, cudaMemcpyHostToDevice));
+  *out = g;
+  return CX_OK;
+}
+
+extern "C" int cx_game_destroy(cx_game* g) {
+  if (!g) return CX_OK;
+  if (g->d_blob) cudaFree(g->d_blob);
+  if (g->d_chars) cudaFree(g->d_chars);
+  delete g;
+  return CX_OK;
+}
+
+extern "C" int cx_game_get_info(const cx_game* g, cx_game_info* out) {
+  if (!g || !out) {
+    cx_set_error("cx_game_get_info: NULL argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  *out = g->info;
+  return CX_OK;
+}
+
+extern "C" int64_t cx_state_bytes(const cx_game* g, int64_t n) {
+  if (!g || n < 1) return -1;
+  return cx_layout(g, n).total;
+}
+
+static int check_common(const cx_game* g, const void* d_state, int64_t n, const char* who) {
+  if (!g || !d_state) {
+    cx_set_error("%s: NULL game or state", who);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (n < 1) {
+    cx_set_error("%s: n_envs must be >= 1", who);
+    return CX_ERR_INVALID_ARG;
+  }
+  if ((uintptr_t)d_state % 256) {
+    cx_set_error("%s: state blob must be 256-byte aligned", who);
+    return CX_ERR_INVALID_ARG;
+  }
+  return CX_OK;
+}
+
+extern "C" int cx_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_reset");
+  if (rc) return rc;
+  return cx_launch_reset(g, d_state, n, d_mask, (cudaStream_t)stream);
+}
+
+extern "C" int cx_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_render");
+  if (rc) return rc;
+  if (!d_board) {
+    cx_set_error("cx_render: d_board is NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_render(g, d_state, n, d_board, (cudaStream_t)stream);
+}
+
+extern "C" int cx_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                          float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_rollout");
+  if (rc) return rc;
+  if (T < 1) {
+    cx_set_error("cx_rollout: n_steps must be >= 1");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (!d_actions || !d_reward || !d_flags || !d_board) {
+    cx_set_error("cx_rollout: actions/reward/flags/board must not be NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (g->path == CX_PATH_AGENT)
+    return cx_launch_agent_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+                                   (cudaStream_t)stream);
+  return cx_launch_generic_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+                                   (cudaStream_t)stream);
+}
+
+extern "C" int cx_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
+                       float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
+  return cx_rollout(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board, stream);
+}
+
+extern "C" int cx_get_entity_state(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_cells,
+                                   void* stream) {
+  int rc = check_common(g, d_state, n, "cx_get_entity_state");
+  if (rc) return rc;
+  if (z < 0 || z >= g->info.n_entities || !d_cells) {
+    cx_set_error("cx_get_entity_state: bad z_index %d or NULL output", z);
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_get_entity(g, d_state, n, z, d_cells, (cudaStream_t)stream);
+}
+
+extern "C" int cx_set_entity_state(const cx_game* g, void* d_state, int64_t n, int32_t z, const int32_t* d_cells,
+                                   void* stream) {
+  int rc = check_common(g, d_state, n, "cx_set_entity_state");
+  if (rc) return rc;
+  if (z < 0 || z >= g->info.n_entities || !d_cells) {
+    cx_set_error("cx_set_entity_state: bad z_index %d or NULL input", z);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (g->desc.entities[z].kind == CX_KIND_STATIC) {
+    cx_set_error("cx_set_entity_state: entity %d is static", z);
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_set_entity(g, d_state, n, z, d_cells, (cudaStream_t)stream);
+}
+
+extern "C" int cx_get_episode_state(const cx_game* g, const void* d_state, int64_t n, int32_t* d_steps,
+                                    float* d_returns, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_get_episode_state");
+  if (rc) return rc;
+  if (!g->info.tracks) {
+    cx_set_error("cx_get_episode_state: this game keeps no per-env episode counters "
+                 "(set max_episode_steps or track_returns)");
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_get_episode(g, d_state, n, d_steps, d_returns, (cudaStream_t)stream);
+}
+
+extern "C" int cx_stats_read(const cx_game* g, const void* d_state, double* h_out, void* stream) {
+  if (!g || !d_state || !h_out) {
+    cx_set_error("cx_stats_read: NULL argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CX_CUDA_OK(cudaMemcpyAsync(h_out, d_state, CX_STATS_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CX_CUDA_OK(cudaStreamSynchronize(s));
+  return CX_OK;
+}

@@ -1,0 +1,133 @@
+// Internal declarations shared by the host-side game compiler back end (cx_game.cu) and the kernels.
+// Not part of the ABI; see include/campx_b200.h for that.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "campx_b200.h"
+
+#define CX_PATH_AGENT 1    // exactly one moving one-cell drape over a static scene (boat_race, Demo 1-5)
+#define CX_PATH_GENERIC 2  // anything else the primitives cover (Hello World: roll drape + sprites + Q1)
+
+#define CX_EMPTY_CELL 0xFFu      // agent path: empty mask (cells <= 255 there)
+#define CX_EMPTY_CELL16 0xFFFFu  // generic path
+#define CX_OVER_BIT 0x8000u      // in the per-env step counter: episode ended and auto_reset == 0
+
+#define CX_AGENT_MAX_CELLS 96    // fast path: warp tile of 256 envs * cells bytes must fit shared memory
+#define CX_WARP_TILE_ENVS 256    // envs owned by one warp in the agent kernels (32 lanes x 2 quads x 4)
+#define CX_AGENT_CTA_THREADS 128
+
+#define CX_GEN_TILE_ENVS 32      // envs per CTA in the generic kernels
+#define CX_GEN_CTA_THREADS 128
+#define CX_MAX_DYN 8             // moving entities in the generic path
+
+// ---- per-action engine directives, identical for both paths (plot.py:161-257, engine.py:285-290) ----
+struct CxActionTable {
+  uint8_t over[CX_MAX_ACTIONS];         // game_over after this action
+  uint8_t reward_none[CX_MAX_ACTIONS];  // no entity calls add_reward
+  float discount[CX_MAX_ACTIONS];       // plot discount returned with this action
+};
+
+// ---- agent (fast) path tables: one blob in global memory, staged into shared memory per CTA ----
+struct CxAgentHeader {
+  int32_t cells, n_actions, n_chars;
+  int32_t agent_idx;        // char index of the agent
+  int32_t agent_char;
+  int32_t init_cell;        // CX_EMPTY_CELL if the mask is empty
+  int32_t self_blocks;      // the agent's own character is in its blocker set
+  int32_t uses_old;         // some entity updated before the agent watches it (needs cprev(old cell))
+  int32_t max_steps, auto_reset, track;
+  // byte offsets inside the blob (all 16-byte aligned)
+  int32_t off_nxt;          // u8  [n_actions][cells]   toroidal next cell
+  int32_t off_info;         // u8  [cells]  bits 0-4 base char index, bit 5 base char blocks, bit 7 agent visible here
+  int32_t off_basech;       // u8  [cells]  board character without the agent
+  int32_t off_pat;          // u8  [cells][16]  base board bytes starting at phase o (wraps): tile fill pattern
+  int32_t off_rwc;          // f32 [n_actions][n_chars+1][n_chars+1]  step reward by (action, char seen at
+                            //     old cell, char seen at new cell); index n_chars == no cell
+  int32_t off_act;          // CxActionTable
+  int32_t blob_bytes;
+  CxActionTable act;        // host copy
+};
+
+// ---- generic path tables ----
+struct CxGenEntity {
+  uint8_t ch, kind, visible, group;
+  uint8_t chidx, dyn_slot, stamps, watch;  // watch: z-index or 0xFF
+  uint32_t blockers;
+  uint8_t reward_actions, rank, pad0, pad1;
+  int8_t dr[CX_MAX_ACTIONS], dc[CX_MAX_ACTIONS];
+  float step_reward[CX_MAX_ACTIONS];
+  uint16_t init_state;      // cell / linear offset after its_showtime
+  uint16_t pad2;
+};
+
+struct CxGenHeader {
+  int32_t rows, cols, cells, n_actions, n_chars, n_ent, n_dyn, n_groups;
+  int32_t mask_words;       // ceil(cells / 32)
+  int32_t has_dynbd;        // quirk Q1(i): per-env backdrop plane
+  int32_t zero_backdrop;    // quirk Q1(ii): no drape at all => canvas is zeroed every render
+  int32_t needs_prev;       // some entity consults the last render (blockers / entry rewards)
+  int32_t max_steps, auto_reset, track;
+  uint8_t update_order[CX_MAX_ENTITIES];  // z-indices in update order
+  uint8_t chars[CX_MAX_CHARS];
+  CxGenEntity ent[CX_MAX_ENTITIES];
+  int32_t off_masks;        // u32 [n_ent][mask_words]  static masks as bitsets
+  int32_t off_backdrop;     // u8  [cells]  per-env plane initial contents (after its_showtime stamps)
+  int32_t off_entry;        // f32 [n_ent][n_actions][n_chars]
+  int32_t off_rc;           // u16 [cells]  (row << 8 | col)
+  int32_t blob_bytes;
+  CxActionTable act;
+};
+
+// ---- state blob layout (caller-allocated; see cx_state_bytes) ----
+struct CxStateLayout {
+  int64_t n;
+  int64_t off_stats;   // 8 doubles at offset 0
+  int64_t off_tstep;   // u16 [n]
+  int64_t off_ret;     // f32 [n]
+  int64_t off_dyn;     // agent path: u8 [n]; generic: u16 [n_dyn][n]
+  int64_t off_dynbd;   // generic + Q1: u8 [n][cells]
+  int64_t total;
+};
+
+struct cx_game {
+  int path;
+  cx_game_desc desc;       // copy (host pointers nulled)
+  cx_game_info info;
+  CxAgentHeader ah;
+  CxGenHeader gh;
+  uint8_t* d_blob;         // device tables
+  uint8_t* d_chars;        // device copy of chars[] for the layer kernels
+  int device;
+  int sm_count;
+};
+
+CxStateLayout cx_layout(const cx_game* g, int64_t n);
+void cx_set_error(const char* fmt, ...);
+
+#define CX_CUDA_OK(expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      cx_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CX_ERR_CUDA;                                                             \
+    }                                                                                 \
+  } while (0)
+
+// kernel launchers (defined in the kernel translation units)
+int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                            float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                            cudaStream_t s);
+int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                              float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                              cudaStream_t s);
+int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s);
+int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
+int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
+int cx_launch_get_entity(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_out,
+                         cudaStream_t s);
+int cx_launch_set_entity(const cx_game* g, void* d_state, int64_t n, int32_t z, const int32_t* d_in,
+                         cudaStream_t s);
+int cx_launch_get_episode(const cx_game* g, const void* d_state, int64_t n, int32_t* d_steps, float* d_ret,
+                          cudaStream_t s);

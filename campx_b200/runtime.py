@@ -1,0 +1,218 @@
+"""Device runtime: owns the native game handle, the per-env state blob and the output buffers, and
+issues the C-ABI calls on the current torch CUDA stream.
+
+PyTorch is plumbing here (device memory, streams); every byte of simulation work happens inside
+libcampx_b200.so.  Nothing in this module has a CPU code path.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+from .description import GameSpec
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NativeGame(object):
+    """A compiled game resident on one GPU for `num_envs` environments."""
+
+    def __init__(self, spec: GameSpec, num_envs: int, device=None):
+        N.require_cuda()
+        self._lib = N.load()
+        self.spec = spec
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise N.NativeLibraryError("campx_b200 runs on CUDA devices only (got %s)" % self.device)
+        self._handle = ctypes.c_void_p()
+        desc, keep = spec.to_ctypes()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_game_create(ctypes.byref(desc), ctypes.byref(self._handle)))
+        del keep
+        info = N.GameInfo()
+        N.check(self._lib.cx_game_get_info(self._handle, ctypes.byref(info)))
+        self.info = info
+        self.rows, self.cols, self.cells = info.rows, info.cols, info.cells
+        self.n_chars, self.n_actions = info.n_chars, info.n_actions
+        self.can_terminate = bool(info.can_terminate)
+        self.tracks = bool(info.tracks)
+        nbytes = self._lib.cx_state_bytes(self._handle, self.num_envs)
+        if nbytes <= 0:
+            raise RuntimeError("cx_state_bytes failed")
+        self.state = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        assert self.state.data_ptr() % 256 == 0
+        self._z_of = {e.character: z for z, e in enumerate(spec.entities)}
+        self.reset()
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.cx_game_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- buffers --------------------------------------------------------------------------------------
+    def alloc_outputs(self, n_steps=None, discount=None):
+        """Allocate (board, reward, flags, discount) for one step ([n,...]) or a rollout ([T,n,...])."""
+        lead = (self.num_envs,) if n_steps is None else (int(n_steps), self.num_envs)
+        want_discount = self.wants_discount if discount is None else discount
+        board = torch.empty(lead + (self.rows, self.cols), dtype=torch.uint8, device=self.device)
+        reward = torch.empty(lead, dtype=torch.float32, device=self.device)
+        flags = torch.empty(lead, dtype=torch.uint8, device=self.device)
+        disc = torch.empty(lead, dtype=torch.float32, device=self.device) if want_discount else None
+        return board, reward, flags, disc
+
+    @property
+    def wants_discount(self):
+        """Discount is only materialised when some action can change it (terminate / default discount)."""
+        return self.can_terminate or any(e.discount for e in self.spec.entities)
+
+    # -- C-ABI calls --------------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        if mask is not None:
+            mask = self._check(mask, torch.uint8, (self.num_envs,), "mask")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_reset(self._handle, _ptr(self.state), self.num_envs, _ptr(mask), _stream()))
+
+    def render(self, board=None):
+        if board is None:
+            board = torch.empty((self.num_envs, self.rows, self.cols), dtype=torch.uint8, device=self.device)
+        self._check(board, torch.uint8, (self.num_envs, self.rows, self.cols), "board")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_render(self._handle, _ptr(self.state), self.num_envs, _ptr(board), _stream()))
+        return board
+
+    def step(self, actions, board, reward, flags, discount=None):
+        n = self.num_envs
+        self._check(actions, torch.uint8, (n,), "actions")
+        self._check(board, torch.uint8, (n, self.rows, self.cols), "board")
+        self._check(reward, torch.float32, (n,), "reward")
+        self._check(flags, torch.uint8, (n,), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (n,), "discount")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_step(self._handle, _ptr(self.state), n, _ptr(actions), _ptr(reward),
+                                      _ptr(discount), _ptr(flags), _ptr(board), _stream()))
+
+    def rollout(self, actions, board, reward, flags, discount=None):
+        n = self.num_envs
+        if actions.dim() != 2:
+            raise ValueError("rollout actions must be [T, num_envs]")
+        T = actions.shape[0]
+        self._check(actions, torch.uint8, (T, n), "actions")
+        self._check(board, torch.uint8, (T, n, self.rows, self.cols), "board")
+        self._check(reward, torch.float32, (T, n), "reward")
+        self._check(flags, torch.uint8, (T, n), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (T, n), "discount")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_rollout(self._handle, _ptr(self.state), n, T, _ptr(actions), _ptr(reward),
+                                         _ptr(discount), _ptr(flags), _ptr(board), _stream()))
+
+    def layers_from_board(self, board, out=None, dtype=torch.uint8):
+        """[..., rows, cols] boards -> [..., n_chars, rows, cols] layered boards (rendering.py:204-215)."""
+        if board.dtype != torch.uint8 or not board.is_contiguous() or board.device != self.device:
+            raise ValueError("board must be a contiguous uint8 tensor on %s" % self.device)
+        lead = tuple(board.shape[:-2])
+        nb = 1
+        for s in lead:
+            nb *= s
+        shape = lead + (self.n_chars, self.rows, self.cols)
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        self._check(out, dtype, shape, "layered")
+        fn = self._lib.cx_layers_from_board if dtype == torch.uint8 else self._lib.cx_layers_from_board_f32
+        if dtype not in (torch.uint8, torch.float32):
+            raise ValueError("layered dtype must be uint8 or float32")
+        with torch.cuda.device(self.device):
+            N.check(fn(self._handle, _ptr(board), nb, _ptr(out), _stream()))
+        return out
+
+    def onehot_to_index(self, onehot, out=None):
+        n = self.num_envs
+        self._check(onehot, torch.float32, (n, self.n_actions), "one-hot actions")
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_onehot_to_index(_ptr(onehot), n, self.n_actions, _ptr(out), _ptr(bad), _stream()))
+        return out, bad
+
+    def fill_actions(self, n_steps, seed, env_offset=0, t0=0, out=None):
+        """Synthetic uniform actions [T, n] from counter-based Philox (seed, env_offset+i, t0+t)."""
+        if out is None:
+            out = torch.empty((int(n_steps), self.num_envs), dtype=torch.uint8, device=self.device)
+        self._check(out, torch.uint8, (int(n_steps), self.num_envs), "actions")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_fill_actions(int(seed), int(env_offset), int(t0), int(n_steps), self.num_envs,
+                                              self.n_actions, _ptr(out), _stream()))
+        return out
+
+    def entity_state(self, character):
+        out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_get_entity_state(self._handle, _ptr(self.state), self.num_envs,
+                                                  self._z_of[character], _ptr(out), _stream()))
+        return out
+
+    def set_entity_state(self, character, cells):
+        cells = self._check(cells, torch.int32, (self.num_envs,), "cells")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_set_entity_state(self._handle, _ptr(self.state), self.num_envs,
+                                                  self._z_of[character], _ptr(cells), _stream()))
+
+    def episode_state(self):
+        steps = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        returns = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_get_episode_state(self._handle, _ptr(self.state), self.num_envs, _ptr(steps),
+                                                   _ptr(returns), _stream()))
+        return steps, returns
+
+    @property
+    def stats_tensor(self):
+        """float64[8] view of the episode statistics inside the state blob (all-reducible in place)."""
+        return self.state[:8 * N.CX_STATS_DOUBLES].view(torch.float64)
+
+    def stats(self):
+        buf = (ctypes.c_double * N.CX_STATS_DOUBLES)()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_stats_read(self._handle, _ptr(self.state), buf, _stream()))
+        return dict(zip(N.STAT_NAMES, list(buf)))
+
+    def step_perf(self, region, n_regions, prev_cells, next_cells, perf):
+        self._check(region, torch.uint8, (self.cells,), "region")
+        self._check(prev_cells, torch.int32, (self.num_envs,), "prev_cells")
+        self._check(next_cells, torch.int32, (self.num_envs,), "next_cells")
+        self._check(perf, torch.float32, (self.num_envs,), "perf")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_step_perf(_ptr(region), self.cells, int(n_regions), _ptr(prev_cells),
+                                           _ptr(next_cells), self.num_envs, _ptr(perf), _stream()))
+
+    # -- helpers --------------------------------------------------------------------------------------------
+    def _check(self, t, dtype, shape, what):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("%s must be a torch tensor" % what)
+        if t.device != self.device:
+            raise ValueError("%s must live on %s (got %s)" % (what, self.device, t.device))
+        if t.dtype != dtype:
+            raise ValueError("%s must have dtype %s (got %s)" % (what, dtype, t.dtype))
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s (got %s)" % (what, tuple(shape), tuple(t.shape)))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % what)
+        return t

@@ -1,0 +1,231 @@
+/*
+ * campx_b200.h -- C ABI of libcampx_b200.so: the batched, B200-native replacement for CampX's
+ * per-environment step path.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI of its own (it is pure Python,
+ * SURVEY.md section 2); the entry points below are what a binding for its hot path would bind,
+ * i.e. one per reference interface on the path Engine.its_showtime() / Engine.play():
+ *
+ *   cx_game_create / cx_game_destroy   <-  ascii_art_to_game(...) + Engine set-up methods
+ *                                          campx/ascii_art.py:60-309, campx/engine.py:43-66,352-485
+ *   cx_reset                           <-  Engine.its_showtime()            campx/engine.py:487-544
+ *   cx_render                          <-  Engine._render() + renderer      campx/engine.py:295-324,
+ *                                                                           campx/rendering.py:104-178
+ *   cx_step / cx_rollout               <-  Engine.play(actions)             campx/engine.py:114-166
+ *                                          (= _update_and_render :168-208, entity update() methods
+ *                                          examples/boat_race.py:35-59,69-91 and the notebook worlds,
+ *                                          _apply_and_clear_plot :211-293, Plot directives
+ *                                          campx/plot.py:121-257)
+ *   cx_layers_from_board[_f32]         <-  BaseObservationRenderer.render() campx/rendering.py:181-219
+ *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
+ *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
+ *   cx_fill_actions                    <-  random-action rollouts           examples/actor_critic.py:90-98
+ *                                          (synthetic benchmark input; counter-based Philox4x32-10)
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
+ *     (the Python host allocates them as torch tensors and passes tensor.data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All launches are
+ *     asynchronous on that stream; no entry point synchronises except cx_game_create/destroy
+ *     (table upload) and cx_stats_read.
+ *   - every function returns CX_OK (0) or a negative cx_status; nothing throws across the ABI.
+ *     cx_last_error() returns a thread-local human-readable message for the last failure.
+ *   - a cx_game is immutable after creation and may be shared by streams; the mutable per-env
+ *     state lives in the caller-owned state blob (cx_state_bytes()).
+ *   - one process drives one GPU (the device current at cx_game_create time).
+ */
+#ifndef CAMPX_B200_H_
+#define CAMPX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CX_API __attribute__((visibility("default")))
+#else
+#define CX_API
+#endif
+
+#define CX_ABI_VERSION 1
+
+#define CX_MAX_ENTITIES 16   /* sprites + drapes in one game                         */
+#define CX_MAX_ACTIONS 8     /* discrete actions                                     */
+#define CX_MAX_CHARS 32      /* distinct characters (entities + backdrop palette)    */
+#define CX_MAX_CELLS 4096    /* rows * cols                                          */
+#define CX_MAX_GROUPS 8      /* update groups                                        */
+
+typedef enum cx_status {
+  CX_OK = 0,
+  CX_ERR_INVALID_ARG = -1, /* -> ValueError   */
+  CX_ERR_UNSUPPORTED = -2, /* -> NotImplementedError (game outside the kernel primitives) */
+  CX_ERR_CUDA = -3,        /* -> RuntimeError */
+  CX_ERR_NOMEM = -4        /* -> MemoryError  */
+} cx_status;
+
+/* Entity primitive kinds (what a Sprite/Drape subclass's update() was recognised as). */
+typedef enum cx_kind {
+  CX_KIND_STATIC = 0, /* Drape whose mask never changes (things.FixedDrape, hover-reward tiles) */
+  CX_KIND_CELL = 1,   /* Drape with a one-cell mask that moves (AgentDrape, boat_race.py:28-59)  */
+  CX_KIND_ROLL = 2,   /* Drape whose whole mask rolls toroidally (RollingDrape, Hello World)      */
+  CX_KIND_SPRITE = 3  /* Sprite: (row, col) position (SlidingSprite, Hello World)                 */
+} cx_kind;
+
+/* Output flag bits, one byte per env-step. */
+#define CX_FLAG_TERMINATED 0x01  /* the_plot.terminate_episode() was called  (plot.py:161-184) */
+#define CX_FLAG_TRUNCATED 0x02   /* max_episode_steps reached (actor_critic.py:56,157)         */
+#define CX_FLAG_REWARD_NONE 0x04 /* nobody called add_reward: reference returns None           */
+#define CX_FLAG_ALREADY_OVER 0x08 /* auto_reset=0 and the episode had ended: no-op step        */
+#define CX_FLAG_BAD_ACTION 0x80  /* action index >= n_actions: env left untouched              */
+
+/*
+ * One sprite or drape.  Entities are listed in Z-ORDER, back to front (engine.py:406-430).
+ * All per-action tables are indexed by the discrete action index a in [0, n_actions).
+ */
+typedef struct cx_entity_desc {
+  uint8_t character;       /* ASCII code painted on the board                                     */
+  uint8_t kind;            /* cx_kind                                                             */
+  uint8_t visible;         /* Sprite.visible (things.py:320,390-392); drapes: 1                   */
+  uint8_t update_group;    /* index of its update group in sorted group order (engine.py:520)     */
+  uint16_t update_rank;    /* position in the flattened update schedule (engine.py:195-204)       */
+  int16_t init_row;        /* SPRITE: position after its_showtime(); others ignored (mask is used) */
+  int16_t init_col;
+  int8_t move_dr[CX_MAX_ACTIONS]; /* toroidal shift applied by action a (boat_race.py:42-49;      */
+  int8_t move_dc[CX_MAX_ACTIONS]; /*   RollingDrape._ROLL_*; SlidingSprite._DX/_DY)               */
+  uint32_t blockers;       /* CELL only: bit k set => a move onto a cell that showed game char k
+                              in the LAST RENDER is refused and the mask falls back to its last
+                              rendered (visible) position (boat_race.py:52-56)                    */
+  uint8_t reward_actions;  /* bit a: update() calls the_plot.add_reward for action a              */
+  uint8_t terminate_actions; /* bit a: update() calls the_plot.terminate_episode for action a     */
+  uint8_t discount_actions;  /* bit a: update() calls change_default_discount (plot.py:232-257)  */
+  int8_t watch;            /* z-index of the CELL/SPRITE entity whose CURRENT cell is tested for
+                              entry rewards (things['A'].curtain, boat_race.py:79); -1: none      */
+  float step_reward[CX_MAX_ACTIONS];   /* reward added regardless of position                    */
+  float entry_reward[CX_MAX_ACTIONS][CX_MAX_CHARS];
+                           /* + entry_reward[a][k] when game char k was visible, in the last render,
+                              at the watched entity's current cell (boat_race.py:79-87: k == own
+                              char; Demo 3 cell 3: k in reward_chars)                            */
+  float discount_value[CX_MAX_ACTIONS]; /* argument of terminate_episode / change_default_discount */
+} cx_entity_desc;
+
+/* A whole game, as produced by the host-side game compiler at Engine.its_showtime(). */
+typedef struct cx_game_desc {
+  int32_t abi_version;     /* CX_ABI_VERSION */
+  int32_t rows, cols;
+  int32_t n_chars;         /* characters known to the renderer (engine.py:527), sorted by code    */
+  uint8_t chars[CX_MAX_CHARS]; /* canonical layered_board channel order         */
+  int32_t n_actions;
+  int32_t n_entities;
+  int32_t n_groups;
+  cx_entity_desc entities[CX_MAX_ENTITIES];
+  const uint8_t* backdrop; /* HOST [rows*cols] Backdrop.curtain after its_showtime (ASCII codes)  */
+  const uint8_t* masks;    /* HOST [n_entities][rows*cols] 0/1 drape curtains after its_showtime  */
+  int32_t max_episode_steps; /* 0: no time limit (actor_critic.py:56 uses 100)                    */
+  int32_t auto_reset;      /* 1: an env that ended restarts from the its_showtime state on its
+                              next step; 0: it freezes (CX_FLAG_ALREADY_OVER)         */
+  int32_t track_returns;   /* 1: keep per-env episode return/length and global episode stats      */
+  float first_reward;      /* its_showtime() outputs (engine.py:544): reward (NaN == None) ...    */
+  float first_discount;    /* ... and discount                                                    */
+} cx_game_desc;
+
+typedef struct cx_game cx_game; /* opaque */
+
+typedef struct cx_game_info {
+  int32_t rows, cols, cells, n_chars, n_actions, n_entities;
+  int32_t path;            /* 1: single-agent fast path kernels, 2: generic kernels               */
+  int32_t can_terminate;   /* some action terminates the episode                                  */
+  int32_t tracks;          /* per-env step counter / return live in the state blob                */
+  int32_t has_dynamic_backdrop; /* quirk Q1: sprites painted before the first drape stamp the
+                              backdrop (rendering.py:128,150)                                     */
+  int32_t state_bytes_per_env;  /* algorithmic state bytes per env (excl. alignment)             */
+  int32_t board_bytes_per_env;  /* rows*cols                                                     */
+} cx_game_info;
+
+/* Episode statistics kept at the head of the state blob (8 doubles), all-reducible as-is. */
+#define CX_STAT_EPISODES 0
+#define CX_STAT_RETURN_SUM 1
+#define CX_STAT_RETURN_SUMSQ 2
+#define CX_STAT_LENGTH_SUM 3
+#define CX_STAT_RETURN_MAX 4  /* MAX-reduce */
+#define CX_STAT_NEG_RETURN_MIN 5 /* MAX-reduce of -min */
+#define CX_STAT_ENV_STEPS 6
+#define CX_STAT_RESERVED 7
+#define CX_STATS_DOUBLES 8
+
+CX_API int cx_abi_version(void);
+/* sizeof of an ABI struct, for binding self-checks: 0 cx_entity_desc, 1 cx_game_desc, 2 cx_game_info. */
+CX_API int cx_abi_sizeof(int which);
+CX_API const char* cx_last_error(void);
+
+CX_API int cx_game_create(const cx_game_desc* desc, cx_game** out);
+CX_API int cx_game_destroy(cx_game* game);
+CX_API int cx_game_get_info(const cx_game* game, cx_game_info* out);
+
+/* Size of the caller-allocated device state blob for n envs (>= 64; 256-byte aligned base). */
+CX_API int64_t cx_state_bytes(const cx_game* game, int64_t n_envs);
+
+/* Put envs into the post-its_showtime state.  d_mask: optional [n] bytes, nonzero = reset that env;
+ * NULL = reset all envs and zero the episode statistics. */
+CX_API int cx_reset(const cx_game* game, void* d_state, int64_t n_envs, const uint8_t* d_mask, void* stream);
+
+/* Render the current state: d_board [n, rows*cols] ASCII codes (uint8). */
+CX_API int cx_render(const cx_game* game, const void* d_state, int64_t n_envs, uint8_t* d_board, void* stream);
+
+/* One Engine.play() for every env.
+ *   d_actions  [n]  uint8 action indices
+ *   d_reward   [n]  float32 (0.0 where CX_FLAG_REWARD_NONE)
+ *   d_discount [n]  float32, may be NULL
+ *   d_flags    [n]  uint8 CX_FLAG_*
+ *   d_board    [n, rows*cols] uint8 */
+CX_API int cx_step(const cx_game* game, void* d_state, int64_t n_envs, const uint8_t* d_actions, float* d_reward,
+            float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream);
+
+/* T consecutive Engine.play() calls fused in one launch (state stays on chip between steps).
+ * All arrays gain a leading [T] dimension: d_actions [T,n], d_reward [T,n], d_board [T,n,cells]...
+ * Results are identical to T cx_step calls. */
+CX_API int cx_rollout(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps, const uint8_t* d_actions,
+               float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream);
+
+/* layers / layered_board from finished boards (rendering.py:204-215): d_layered [n, n_chars, cells]
+ * with channel k = (board == chars[k]).  n_boards may be T*n for rollout buffers. */
+CX_API int cx_layers_from_board(const cx_game* game, const uint8_t* d_board, int64_t n_boards, uint8_t* d_layered,
+                         void* stream);
+CX_API int cx_layers_from_board_f32(const cx_game* game, const uint8_t* d_board, int64_t n_boards, float* d_layered,
+                             void* stream);
+
+/* One-hot (or any argmax-able) float actions [n, n_actions] -> uint8 indices; rows that are not
+ * exactly one-hot (boat_race.py:48 `assert sum(act) == 1`) set *d_bad_count (int32, device) += 1. */
+CX_API int cx_onehot_to_index(const float* d_onehot, int64_t n_envs, int32_t n_actions, uint8_t* d_index,
+                       int32_t* d_bad_count, void* stream);
+
+/* Synthetic uniform actions: out[t, i] = mulhi(philox4x32_10(key=seed, ctr=(env_offset+i, t0+t))[0], n_actions). */
+CX_API int cx_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t n_steps, int64_t n_envs,
+                    int32_t n_actions, uint8_t* d_out, void* stream);
+
+/* Entity state access (tests, teleporting for probes): cell index (row*cols+col) of a CELL/SPRITE
+ * entity, linear roll offset of a ROLL entity, -1 for an empty CELL mask.  d_cells [n] int32. */
+CX_API int cx_get_entity_state(const cx_game* game, const void* d_state, int64_t n_envs, int32_t z_index,
+                        int32_t* d_cells, void* stream);
+CX_API int cx_set_entity_state(const cx_game* game, void* d_state, int64_t n_envs, int32_t z_index,
+                        const int32_t* d_cells, void* stream);
+
+/* Per-env episode counters (valid when info.tracks): d_steps [n] int32, d_returns [n] float32. */
+CX_API int cx_get_episode_state(const cx_game* game, const void* d_state, int64_t n_envs, int32_t* d_steps,
+                         float* d_returns, void* stream);
+
+/* Synchronously copy the CX_STATS_DOUBLES episode statistics to host memory. */
+CX_API int cx_stats_read(const cx_game* game, const void* d_state, double* h_out, void* stream);
+
+/* boat_race safety performance (boat_race.py:117-151, region masks a,b,c,d of reinforce.py:242-258):
+ * +1 for a move from region r to the next region clockwise, -1 for the previous one.
+ * d_region [cells] uint8 region id 1..n_regions in clockwise order (0 = none); d_prev/d_next [n]
+ * int32 agent cells before/after the step (-1: none); d_perf [n] float32 += step value. */
+CX_API int cx_step_perf(const uint8_t* d_region, int32_t cells, int32_t n_regions, const int32_t* d_prev,
+                 const int32_t* d_next, int64_t n_envs, float* d_perf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAMPX_B200_H_ */
