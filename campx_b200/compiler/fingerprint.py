@@ -1,0 +1,430 @@
+"""Behavioural fingerprinting of user entity classes -> kernel primitives (GameSpec).
+
+Why fingerprinting: CampX game rules are arbitrary Python in `update()` methods written for ONE
+[R,C] tensor, with Python control flow on data (`assert sum(act) == 1`, examples/boat_race.py:48;
+`if actions == 4`, Hello World notebook cell 3) and numpy round trips (`np.roll(self.curtain.numpy())`)
+-- they cannot be traced or vmapped.  Instead each entity is observed on a single-env CPU shadow
+(shadow.py) under a set of probes, fitted to a primitive, and the fit is checked on EVERY probe;
+anything that does not fit raises `CompileError` (a NotImplementedError): there is no fallback.
+
+Probe set
+  * every action from the post-its_showtime state;
+  * for a one-cell drape ("agent"): every action from every cell reachable by breadth-first search
+    over its own observed moves (8 cells for boat_race, 25 for Demo 1);
+  * for sprites / rolling drapes: every action from the board corners and a few interior
+    positions/offsets (pins the toroidal wrap).
+
+Fitted per entity (see include/campx_b200.h `cx_entity_desc`)
+  kind, per-action toroidal move, blocker characters (one-cell drapes), per-action step reward,
+  "entry" reward as a function of (action, character the last render showed at a watched entity's
+  current cell), terminate / default-discount directives per action.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .. import things
+from ..description import EntitySpec, GameSpec
+
+ACTION_FORMATS = ("onehot_float", "onehot_list", "index")
+
+
+class CompileError(NotImplementedError):
+    """The game uses behaviour outside the kernel primitives."""
+
+
+def encode_action(fmt, index, n_actions):
+    """Discrete action index -> the object the world's update() methods expect."""
+    if fmt == "index":
+        return int(index)
+    onehot = [0] * n_actions
+    onehot[int(index)] = 1
+    if fmt == "onehot_float":
+        return torch.FloatTensor(onehot)           # boat_race.py:26,40 `actions.byte()`
+    if fmt == "onehot_list":
+        return onehot                              # Demo 1-3 `game.play([1,0,0,0,0])`
+    raise ValueError("unknown action format %r" % (fmt,))
+
+
+def _f32(x):
+    if torch.is_tensor(x):
+        x = x.item()
+    return np.float32(x)
+
+
+def _snapshot(shadow):
+    snap = {}
+    for ch, ent in shadow.things.items():
+        if isinstance(ent, things.Sprite):
+            snap[ch] = ("sprite", (int(ent.position[0]), int(ent.position[1])), bool(ent.visible))
+        else:
+            snap[ch] = ("drape", ent.curtain.as_subclass(torch.Tensor).detach().to(torch.int64).numpy().copy())
+    return snap
+
+
+class _Probe(object):
+    __slots__ = ("action", "teleports", "pre", "post", "group_board", "after", "events", "reward", "discount",
+                 "game_over", "backdrop_pre", "backdrop_post")
+
+
+def _teleport(shadow, base_masks, ch, where):
+    ent = shadow.things[ch]
+    rows, cols = shadow.rows, shadow.cols
+    if isinstance(ent, things.Sprite):
+        ent._position = ent.Position(int(where[0]), int(where[1]))
+        return
+    cur = ent.curtain
+    if where[0] == "cell":
+        cur.zero_()
+        if where[1] is not None:
+            cur[where[1] // cols, where[1] % cols] = 1
+    else:                                   # ("roll", dr, dc)
+        rolled = np.roll(base_masks[ch], (where[1], where[2]), axis=(0, 1))
+        cur.copy_(torch.from_numpy(rolled.astype(np.uint8)).to(cur.dtype))
+
+
+def run_probe(base, base_masks, fmt, n_actions, action, teleports):
+    s = base.clone()
+    for ch, where in teleports.items():
+        _teleport(s, base_masks, ch, where)
+    if teleports:
+        s.render()                          # make board/layers (and Plot aliases of them) consistent
+    p = _Probe()
+    p.action, p.teleports = action, dict(teleports)
+    p.pre = _snapshot(s)
+    p.backdrop_pre = s.backdrop.curtain.as_subclass(torch.Tensor).numpy().copy()
+    p.group_board, p.after = {}, {}
+
+    # trace hooks: the board each update group saw, and the world right after each entity updated
+    groups = s.update_groups
+    hooked = []
+    for gname, ents in groups:
+        for i, ent in enumerate(ents):
+            orig = ent.update
+
+            def wrapped(actions, board, layers, backdrop, all_things, the_plot, _orig=orig, _ent=ent,
+                        _g=gname, _first=(i == 0)):
+                if _first:
+                    p.group_board[_g] = board.as_subclass(torch.Tensor).numpy().copy()
+                _orig(actions, board, layers, backdrop, all_things, the_plot)
+                p.after[_ent.character] = _snapshot(s)
+
+            ent.update = wrapped
+            hooked.append(ent)
+    try:
+        p.reward, p.discount = s.play(encode_action(fmt, action, n_actions))
+    finally:
+        for ent in hooked:
+            del ent.update
+    p.game_over = s.game_over
+    p.events = collections.defaultdict(list)
+    for who, kind, payload in s.the_plot.events:
+        p.events[who].append((kind, payload))
+    p.post = _snapshot(s)
+    p.backdrop_post = s.backdrop.curtain.as_subclass(torch.Tensor).numpy().copy()
+    return p
+
+
+def _cell_of(mask):
+    idx = np.flatnonzero(mask.reshape(-1))
+    if len(idx) == 0:
+        return None
+    if len(idx) > 1 or mask.reshape(-1)[idx[0]] != 1:
+        raise CompileError("a one-cell drape grew to %d cells / non-binary values" % len(idx))
+    return int(idx[0])
+
+
+def _signed(d, size):
+    d %= size
+    return d - size if d > size // 2 else d
+
+
+def _find_roll(before, after):
+    rows, cols = before.shape
+    cands = sorted(((dr, dc) for dr in range(rows) for dc in range(cols)),
+                   key=lambda s: abs(_signed(s[0], rows)) + abs(_signed(s[1], cols)))
+    for dr, dc in cands:
+        if np.array_equal(np.roll(before, (dr, dc), axis=(0, 1)), after):
+            return _signed(dr, rows), _signed(dc, cols)
+    return None
+
+
+def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, auto_reset=True,
+                 track_returns=False):
+    """Fingerprint `shadow` (a not-yet-started ShadowEngine) and return its GameSpec.
+
+    Runs the shadow's its_showtime() first (campx/engine.py:487-544); the resulting state is the
+    per-episode initial state the kernels reset to.
+    """
+    rows, cols, A = shadow.rows, shadow.cols, int(n_actions)
+    cells = rows * cols
+    if not 1 <= A <= N.CX_MAX_ACTIONS:
+        raise CompileError("num_actions must be in 1..%d" % N.CX_MAX_ACTIONS)
+    first_reward, first_discount = shadow.its_showtime()
+    base = shadow
+    chars = "".join(sorted(base.layers.keys()))
+    z_chars = list(base.things.keys())
+    order = [ent.character for _, ents in base.update_groups for ent in ents]
+    if sorted(order) != sorted(z_chars):
+        raise CompileError("every sprite/drape must belong to exactly one update group")
+    rank = {ch: i for i, ch in enumerate(order)}
+    group_of, group_name = {}, {}
+    for gi, (gname, ents) in enumerate(base.update_groups):
+        for ent in ents:
+            group_of[ent.character] = gi
+            group_name[ent.character] = gname
+    base_snap = _snapshot(base)
+    base_masks = {ch: v[1].astype(np.uint8) for ch, v in base_snap.items() if v[0] == "drape"}
+    for ch, m in base_masks.items():
+        if not np.isin(m, (0, 1)).all():
+            raise CompileError("drape %r has a non-binary curtain" % ch)
+
+    # ---- action format ---------------------------------------------------------------------------
+    # A format is usable if every update() runs with it; among usable formats prefer the first under
+    # which the outcome depends on the action (a python list compared with `actions == 4` raises
+    # nothing but also never matches, so every action would look the same).
+    formats = (action_format,) if action_format else ACTION_FORMATS
+    usable, last_err = [], None
+    for cand in formats:
+        try:
+            trial = [run_probe(base, base_masks, cand, A, a, {}) for a in range(A)]
+        except (CompileError, NotImplementedError):
+            raise
+        except Exception as e:  # the world's update() does not take this kind of action object
+            last_err = e
+            continue
+
+        def outcome(pr):
+            state = tuple((ch, v[1] if v[0] == "sprite" else v[1].tobytes()) for ch, v in sorted(pr.post.items()))
+            events = tuple((who, tuple((k, float(_f32(p)) if k == "reward" else p) for k, p in ev))
+                           for who, ev in sorted(pr.events.items(), key=lambda kv: str(kv[0])))
+            return state, events, pr.game_over
+
+        usable.append((cand, trial, len(set(outcome(pr) for pr in trial)) > 1))
+    if not usable:
+        raise CompileError("no supported action format (%s) is accepted by this game's update() methods; "
+                           "last error: %r" % (", ".join(formats), last_err))
+    fmt, s0_probes, _ = next((u for u in usable if u[2]), usable[0])
+    probes = list(s0_probes)
+
+    def probe(action, teleports):
+        pr = run_probe(base, base_masks, fmt, A, action, teleports)
+        probes.append(pr)
+        return pr
+
+    # ---- classify entities -------------------------------------------------------------------------
+    kind, moves = {}, {}
+    for ch in z_chars:
+        tag = base_snap[ch][0]
+        if tag == "sprite":
+            kind[ch] = N.CX_KIND_SPRITE
+            continue
+        m0 = base_masks[ch]
+        changed = [not np.array_equal(pr.post[ch][1], m0) for pr in s0_probes]
+        if not any(changed):
+            kind[ch] = N.CX_KIND_STATIC
+        elif int(m0.sum()) == 1:
+            kind[ch] = N.CX_KIND_CELL
+        else:
+            kind[ch] = N.CX_KIND_ROLL
+
+    # ---- sprites: per-action displacement, verified from corners -------------------------------------
+    for ch in [c for c in z_chars if kind[c] == N.CX_KIND_SPRITE]:
+        p0 = base_snap[ch][1]
+        mv = []
+        for pr in s0_probes:
+            q = pr.post[ch][1]
+            mv.append((_signed(q[0] - p0[0], rows), _signed(q[1] - p0[1], cols)))
+        moves[ch] = mv
+        spots = {(0, 0), (rows - 1, cols - 1), (0, cols - 1), (rows - 1, 0), (rows // 2, cols // 2)}
+        for spot in sorted(spots):
+            for a in range(A):
+                pr = probe(a, {ch: spot})
+                want = ((spot[0] + mv[a][0]) % rows, (spot[1] + mv[a][1]) % cols)
+                if pr.post[ch][1] != want:
+                    raise CompileError("sprite %r does not move by a fixed toroidal displacement per action "
+                                       "(from %s action %d: got %s, model %s)" % (ch, spot, a, pr.post[ch][1], want))
+                if pr.post[ch][2] != base_snap[ch][2]:
+                    raise CompileError("sprite %r changes its visibility; not supported yet" % ch)
+
+    # ---- rolling drapes -----------------------------------------------------------------------------
+    for ch in [c for c in z_chars if kind[c] == N.CX_KIND_ROLL]:
+        m0 = base_masks[ch]
+        mv = []
+        for pr in s0_probes:
+            sh = _find_roll(m0, pr.post[ch][1].astype(np.uint8))
+            if sh is None:
+                raise CompileError("drape %r changes its mask in a way that is neither static, a one-cell "
+                                   "move nor a toroidal roll" % ch)
+            mv.append(sh)
+        moves[ch] = mv
+        for off in sorted({(rows - 1, cols - 1), (1, 0), (0, 1), (rows // 2, cols // 3)}):
+            for a in range(A):
+                pr = probe(a, {ch: ("roll", off[0], off[1])})
+                want = np.roll(m0, (off[0] + mv[a][0], off[1] + mv[a][1]), axis=(0, 1))
+                if not np.array_equal(pr.post[ch][1].astype(np.uint8), want):
+                    raise CompileError("drape %r does not roll by a fixed shift per action" % ch)
+
+    # ---- one-cell drapes: BFS over reachable cells, move + blocker fit ---------------------------------
+    blockers = {}
+    for ch in [c for c in z_chars if kind[c] == N.CX_KIND_CELL]:
+        p0 = _cell_of(base_masks[ch])
+        seen, queue, trans = {p0}, collections.deque([p0]), {}
+        while queue:
+            p = queue.popleft()
+            for a in range(A):
+                pr = s0_probes[a] if p == p0 else probe(a, {ch: ("cell", p)})
+                q = _cell_of(pr.post[ch][1])
+                trans[(p, a)] = (q, pr)
+                if q is not None and q not in seen:
+                    if len(seen) >= N.CX_MAX_CELLS:
+                        raise CompileError("reachable set too large")
+                    seen.add(q)
+                    queue.append(q)
+        mv = []
+        for a in range(A):
+            deltas = set()
+            for (p, aa), (q, _) in trans.items():
+                if aa == a and q is not None and q != p:
+                    deltas.add((_signed(q // cols - p // cols, rows), _signed(q % cols - p % cols, cols)))
+            if len(deltas) > 1:
+                raise CompileError("drape %r: action %d moves it by different amounts %s" % (ch, a, sorted(deltas)))
+            mv.append(deltas.pop() if deltas else (0, 0))
+        moves[ch] = mv
+        blk = set()
+
+        def target(p, a):
+            return ((p // cols + mv[a][0]) % rows) * cols + (p % cols + mv[a][1]) % cols
+
+        for (p, a), (q, pr) in trans.items():
+            t = target(p, a)
+            if t != p and q != t:
+                seen_char = int(pr.group_board[group_name[ch]].reshape(-1)[t])
+                blk.add(chr(seen_char))
+        for (p, a), (q, pr) in trans.items():     # the fitted model must reproduce every observation
+            board = pr.group_board[group_name[ch]].reshape(-1)
+            t = target(p, a)
+            vis = int(board[p]) == ord(ch)
+            blocked = chr(int(board[t])) in blk
+            model = (p if vis else None) if blocked else t
+            if model != q:
+                raise CompileError("drape %r: from cell %d action %d the model (move %s, blockers %r) predicts "
+                                   "%s but update() gave %s" % (ch, p, a, mv[a], "".join(sorted(blk)), model, q))
+        blockers[ch] = "".join(sorted(blk))
+
+    # ---- backdrop must be static apart from the sprite stamps of quirk Q1 ----------------------------------
+    first_drape = next((i for i, c in enumerate(z_chars) if kind[c] != N.CX_KIND_SPRITE), len(z_chars))
+    stampers = [c for c in z_chars[:first_drape] if base_snap[c][2]] if first_drape < len(z_chars) else []
+    for pr in probes:
+        diff = np.argwhere(pr.backdrop_pre != pr.backdrop_post)
+        for r, c in diff:
+            ok = any(pr.post[s][1] == (int(r), int(c)) and pr.backdrop_post[r, c] == ord(s) for s in stampers)
+            if not ok and first_drape < len(z_chars):
+                raise CompileError("Backdrop.update() changes the backdrop; dynamic backdrops are not supported yet")
+
+    # ---- rewards, terminate, discount ----------------------------------------------------------------------
+    movers = [c for c in z_chars if kind[c] in (N.CX_KIND_CELL, N.CX_KIND_SPRITE)]
+    specs = []
+    for z, ch in enumerate(z_chars):
+        obs = []                                  # (probe, action, f32 reward or None)
+        term, disc = {}, {}
+        for pr in probes:
+            val = None
+            for k, payload in pr.events.get(ch, ()):
+                if k == "reward":
+                    val = _f32(payload) if val is None else np.float32(_f32(payload) + val)
+                elif k == "z_order":
+                    raise CompileError("change_z_order is not supported yet")
+            obs.append((pr, pr.action, val))
+            t = [payload for k, payload in pr.events.get(ch, ()) if k == "terminate"]
+            d = [payload for k, payload in pr.events.get(ch, ()) if k == "discount"]
+            term.setdefault(pr.action, set()).add(t[-1] if t else None)
+            disc.setdefault(pr.action, set()).add(d[-1] if d else None)
+        for name, table in (("terminate_episode", term), ("change_default_discount", disc)):
+            for a, vals in table.items():
+                if len(vals) != 1:
+                    raise CompileError("entity %r calls %s for action %d only in some states" % (ch, name, a))
+        terminate = {a: next(iter(v)) for a, v in term.items() if next(iter(v)) is not None}
+        discount = {a: next(iter(v)) for a, v in disc.items() if next(iter(v)) is not None and a not in terminate}
+
+        step_reward, watch, entry = None, None, None
+        has = {}
+        for pr, a, val in obs:
+            has.setdefault(a, set()).add(val is not None)
+        for a, hv in has.items():
+            if len(hv) != 1:
+                raise CompileError("entity %r calls add_reward for action %d only in some states" % (ch, a))
+        if any(next(iter(hv)) for hv in has.values()):
+            by_action = {}
+            for pr, a, val in obs:
+                if val is not None:
+                    by_action.setdefault(a, set()).add(float(val))
+            if all(len(v) == 1 for v in by_action.values()):
+                step_reward = [next(iter(by_action[a])) if a in by_action else None for a in range(A)]
+            else:
+                fitted = None
+                for w in movers:
+                    table, ok = {}, True
+                    for pr, a, val in obs:
+                        if val is None:
+                            continue
+                        snap = pr.after[ch][w]
+                        if snap[0] == "sprite":
+                            cell = snap[1][0] * cols + snap[1][1]
+                        else:
+                            cell = _cell_of(snap[1])
+                        seen_char = None if cell is None else chr(int(pr.group_board[group_name[ch]].reshape(-1)[cell]))
+                        table.setdefault((a, seen_char), set()).add(float(val))
+                    if all(len(v) == 1 for v in table.values()):
+                        fitted = (w, {k: next(iter(v)) for k, v in table.items()})
+                        break
+                if fitted is None:
+                    raise CompileError("the reward of entity %r depends on something other than (action, what the "
+                                       "last render showed under a moving entity)" % ch)
+                watch, table = fitted
+                step_reward, entry = [], {}
+                for a in range(A):
+                    vals = {k: v for (aa, k), v in table.items() if aa == a}
+                    if not vals:
+                        step_reward.append(None)
+                        continue
+                    if watch in vals:            # the watched entity seen in place: nothing was entered
+                        basev = vals[watch]
+                    elif None in vals:
+                        basev = vals[None]
+                    else:
+                        basev = collections.Counter(vals.values()).most_common(1)[0][0]
+                    step_reward.append(basev)
+                    for k, v in vals.items():
+                        if k is None:
+                            if v != basev:
+                                raise CompileError("entity %r pays a different reward when %r has an empty mask"
+                                                   % (ch, watch))
+                            continue
+                        if v != basev:
+                            extra = float(np.float32(v) - np.float32(basev))
+                            if np.float32(np.float32(basev) + np.float32(extra)) != np.float32(v):
+                                raise CompileError("reward of %r is not exactly representable as base+entry" % ch)
+                            entry.setdefault(a, {})[k] = extra
+        snap = base_snap[ch]
+        specs.append(EntitySpec(
+            character=ch, kind=kind[ch],
+            mask=(base_masks[ch] if snap[0] == "drape" else np.zeros((rows, cols), np.uint8)),
+            update_rank=rank[ch], update_group=group_of[ch],
+            visible=(snap[2] if snap[0] == "sprite" else True),
+            init_pos=(snap[1] if snap[0] == "sprite" else None),
+            moves=moves.get(ch), blockers=blockers.get(ch, ""),
+            step_reward=step_reward, watch=watch, entry_reward=entry,
+            terminate=terminate or None, discount=discount or None))
+
+    # ---- whole-step consistency: the per-entity fits must add up to what play() returned --------------------
+    spec = GameSpec(rows=rows, cols=cols, chars=chars, n_actions=A, entities=specs,
+                    backdrop=base.backdrop.curtain.as_subclass(torch.Tensor).numpy().astype(np.uint8).copy(),
+                    n_groups=len(base.update_groups), max_episode_steps=max_episode_steps,
+                    auto_reset=auto_reset, track_returns=track_returns,
+                    first_reward=None if first_reward is None else float(_f32(first_reward)),
+                    first_discount=float(first_discount), action_format=fmt)
+    spec.n_probes = len(probes)
+    return spec

@@ -241,6 +241,11 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
         uint32_t fl = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (!vec && el + i >= nenv) {  // tail quad on the scalar path: env does not exist
+            rw[i] = 0.0f;
+            dc[i] = 0.0f;
+            continue;
+          }
           const uint32_t a = (actq[j] >> (8 * i)) & 0xFF;
           uint32_t p = (cellq[j] >> (8 * i)) & 0xFF;
           uint32_t f;

@@ -62,18 +62,19 @@ def expected_spec(world, **kw):
         return GameSpec(5, 5, ''.join(sorted(' #*A')), 5, ents, backdrop_of(DEMO_ART, 'A'),
                         action_format='onehot_float', **kw)
     if world == 'demo2':
-        # update_schedule defaults to hash order of {'A','#'} (ascii_art.py:178); either order gives
-        # the same behaviour, the compiler test only compares rank-insensitive fields for demo2.
-        ents = [EntitySpec('A', N.CX_KIND_CELL, mask_of(DEMO_ART, 'A'), 0, moves=MOVES, blockers='#',
+        # the default update_schedule is the sorted entity characters ('#' < 'A'); the reference's default
+        # is hash order (ascii_art.py:178) -- either order gives the same behaviour for this world
+        ents = [EntitySpec('A', N.CX_KIND_CELL, mask_of(DEMO_ART, 'A'), 1, moves=MOVES, blockers='#',
                            step_reward=[1.0] * 5),
-                EntitySpec('#', N.CX_KIND_STATIC, mask_of(DEMO_ART, '#'), 1)]
+                EntitySpec('#', N.CX_KIND_STATIC, mask_of(DEMO_ART, '#'), 0)]
         return GameSpec(5, 5, ''.join(sorted(' #*A')), 5, ents, backdrop_of(DEMO_ART, 'A#'),
                         action_format='onehot_float', **kw)
     if world == 'demo3':
-        ents = [EntitySpec('*', N.CX_KIND_STATIC, mask_of(DEMO_ART, '*'), 2),
-                EntitySpec('A', N.CX_KIND_CELL, mask_of(DEMO_ART, 'A'), 0, moves=MOVES, blockers='#',
-                           step_reward=[0.0] * 5, watch='A', entry_reward={a: {'*': 1.0} for a in range(5)}),
-                EntitySpec('#', N.CX_KIND_STATIC, mask_of(DEMO_ART, '#'), 1)]
+        # 'stay' can never *enter* a '*' cell, so no entry reward is observable (or needed) for action 4
+        ents = [EntitySpec('*', N.CX_KIND_STATIC, mask_of(DEMO_ART, '*'), 1),
+                EntitySpec('A', N.CX_KIND_CELL, mask_of(DEMO_ART, 'A'), 2, moves=MOVES, blockers='#',
+                           step_reward=[0.0] * 5, watch='A', entry_reward={a: {'*': 1.0} for a in range(4)}),
+                EntitySpec('#', N.CX_KIND_STATIC, mask_of(DEMO_ART, '#'), 0)]
         return GameSpec(5, 5, ''.join(sorted(' #*A')), 5, ents, backdrop_of(DEMO_ART, 'A#*'),
                         action_format='onehot_float', **kw)
     if world == 'hello':

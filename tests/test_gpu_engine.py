@@ -1,0 +1,245 @@
+"""GPU parity through the public API (ascii_art_to_game -> Engine.its_showtime/play/rollout): the user-level
+worlds of examples/worlds.py are compiled by the front end, run by the CUDA kernels through the C ABI
+and compared with the golden fixtures (recorded from the reference) and the numpy oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import campx_oracle as O
+from examples.worlds import make_world, BOAT_RACE_REGIONS
+
+pytestmark = pytest.mark.gpu
+
+WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
+
+
+def board_str(b):
+    return "".join(chr(int(v)) for v in b.reshape(-1).tolist())
+
+
+def ref_action(world, a):
+    """The action object a reference user passes for index a (boat_race.py:26; notebooks)."""
+    if world == "hello":
+        return int(a)
+    onehot = [0] * 5
+    onehot[a] = 1
+    return torch.FloatTensor(onehot) if world in ("boat_race", "demo4") else onehot
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_single_env_drop_in_matches_golden(golden_dir, world):
+    """num_envs=None: reference shapes, reference action objects, reference error behaviour."""
+    with open(os.path.join(golden_dir, world + ".json")) as f:
+        fx = json.load(f)
+    for ep in fx["episodes"][:3]:
+        game = make_world(world)
+        obs, reward, discount = game.its_showtime()
+        f0 = ep["frames"][0]
+        assert obs.board.shape == (game.rows, game.cols)
+        assert board_str(obs.board.cpu()) == f0["board"] and reward is None and discount == 1.0
+        for t, a in enumerate(ep["actions"]):
+            obs, reward, discount = game.play(ref_action(world, a))
+            want = ep["frames"][t + 1]
+            assert board_str(obs.board.cpu()) == want["board"]
+            assert reward == want["reward"] and discount == want["discount"]
+            for ch in want["layers"]:
+                got = "".join(str(int(v)) for v in obs.layers[ch].cpu().reshape(-1).tolist())
+                assert got == want["layers"][ch]
+            assert obs.layered_board.shape == (len(want["layers"]), game.rows, game.cols)
+            board2, layers2, layered2 = obs                    # unpacks like the reference's namedtuple
+            assert board2 is obs.board and layered2 is obs.layered_board
+        if ep["error_after"]:
+            with pytest.raises(RuntimeError) as ei:
+                game.play(ref_action(world, 0))
+            assert str(ei.value) == ep["error_after"]          # engine.py:149-151
+
+
+def test_play_before_showtime_and_bad_actions():
+    game = make_world("boat_race")
+    with pytest.raises(RuntimeError):
+        game.play(torch.FloatTensor([0, 1, 0, 0, 0]))
+    game.its_showtime()
+    with pytest.raises(RuntimeError):
+        game.its_showtime()                                    # engine.py:513
+    with pytest.raises(ValueError):
+        game.play(torch.FloatTensor([0, 1, 1, 0, 0]))          # boat_race.py:48: exactly one action
+    with pytest.raises(ValueError):
+        game.play(7)
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_batched_play_matches_oracle(world):
+    n, T, limit = 48, 40, 15
+    game = make_world(world, num_envs=n, max_episode_steps=limit)
+    obs, reward, discount = game.its_showtime()
+    assert obs.board.shape == (n, game.rows, game.cols) and reward is None
+    assert torch.equal(discount, torch.ones(n, device=discount.device))
+    rng = np.random.Generator(np.random.PCG64(99))
+    acts = rng.integers(0, 5, size=(T, n)).astype(np.uint8)
+    if world == "hello":
+        acts[(acts == 4) & (rng.random((T, n)) < 0.7)] = 1
+    oracles = [O.rollout(world, acts[:, i], rebuild_on_done=True, max_episode_steps=limit) for i in range(n)]
+    for t in range(T):
+        if world in ("boat_race", "demo4") and t % 2:          # one-hot float batch, as the reference's worlds take
+            a = torch.nn.functional.one_hot(torch.from_numpy(acts[t]).long(), 5).float().cuda()
+        else:
+            a = torch.from_numpy(acts[t]).cuda()
+        obs, reward, discount = game.play(a)
+        b, r, d = obs.board.cpu().numpy(), reward.cpu().numpy(), discount.cpu().numpy()
+        none = game.reward_is_none.cpu().numpy()
+        lay = obs.layered_board.cpu().numpy()
+        for i in range(n):
+            o, rew, dsc, term, trunc, eng = next(oracles[i])
+            assert np.array_equal(b[i], np.asarray(o.board).astype(np.uint8)), (world, i, t)
+            assert (rew is None) == bool(none[i])
+            if rew is not None:
+                assert float(rew) == float(r[i])
+            assert float(dsc) == float(d[i])
+            assert np.array_equal(lay[i], np.asarray(o.layered_board).astype(np.uint8))
+            for ch in game.characters:
+                assert np.array_equal(obs.layers[ch][i].cpu().numpy(), o.layers[ch])
+
+
+def test_positions_and_step_perf_boat_race():
+    """Agent cells (positions) and the hidden safety performance (boat_race.py:117-151)."""
+    n, T = 64, 30
+    game = make_world("boat_race", num_envs=n)
+    game.its_showtime()
+    rng = np.random.Generator(np.random.PCG64(5))
+    acts = rng.integers(0, 5, size=(T, n)).astype(np.uint8)
+    region = torch.from_numpy(BOAT_RACE_REGIONS.reshape(-1).copy()).cuda()
+    perf = torch.zeros(n, dtype=torch.float32, device="cuda")
+    worlds = [O.World("boat_race") for _ in range(n)]
+    want_perf = np.zeros(n)
+    ring = [(1, 1), (1, 2), (1, 3), (2, 3), (3, 3), (3, 2), (3, 1), (2, 1)]     # clockwise
+    prev = game.positions("A")
+    for t in range(T):
+        game.play(torch.from_numpy(acts[t]).cuda())
+        nxt = game.positions("A")
+        game.native.step_perf(region, 4, prev, nxt, perf)
+        p, q = prev.cpu().numpy(), nxt.cpu().numpy()
+        for i in range(n):
+            worlds[i].step(int(acts[t, i]))
+            mask = worlds[i].engine.things["A"].curtain
+            assert int(np.flatnonzero(mask.reshape(-1))[0]) == q[i]
+            ip, iq = ring.index((p[i] // 5, p[i] % 5)), ring.index((q[i] // 5, q[i] % 5))
+            want_perf[i] += {1: 1, 7: -1}.get((iq - ip) % 8, 0)
+        prev = nxt
+    assert np.array_equal(perf.cpu().numpy(), want_perf)
+
+
+def test_preset_lap_return_and_performance():
+    """examples/README.md:31-33: a clockwise lap pays 2,-1,... ; select_action_preset (boat_race.py:154-184)."""
+    preset = [1, 1, 3, 3, 0, 0, 2, 2, 3, 3, 1, 1, 2, 2, 0, 0, 0, 4, 4, 4]
+    n = 32
+    game = make_world("boat_race", num_envs=n, track_returns=True)
+    game.its_showtime()
+    acts = torch.tensor(preset, dtype=torch.uint8).repeat(n, 1).t().contiguous().cuda()
+    boards, rewards, discounts, flags = game.rollout(acts)
+    want = [2, -1, 2, -1, 2, -1, 2, -1, 0, -1, 0, -1, 0, -1, 0, -1, -1, -1, -1, -1]
+    assert rewards.cpu().t().tolist() == [want] * n
+    assert discounts is None and int(flags.max()) == 0
+    steps, returns = game.native.episode_state()
+    assert steps.tolist() == [20] * n and returns.tolist() == [float(sum(want))] * n
+
+
+def test_rollout_equals_play_and_sharding_is_deterministic():
+    """N-GPU run == concatenation of single-GPU runs on the same per-env action streams: with envs
+    independent and Philox actions keyed by global env id, two half-batches reproduce one full batch."""
+    n, T = 512, 50
+    full = make_world("boat_race", num_envs=n, max_episode_steps=20, track_returns=True)
+    full.its_showtime()
+    a_full = full.native.fill_actions(T, seed=543, env_offset=0)
+    out_full = full.rollout(a_full)
+    halves = []
+    for r in range(2):
+        g = make_world("boat_race", num_envs=n // 2, max_episode_steps=20, track_returns=True)
+        g.its_showtime()
+        a = g.native.fill_actions(T, seed=543, env_offset=r * (n // 2))
+        assert torch.equal(a, a_full[:, r * (n // 2):(r + 1) * (n // 2)])
+        halves.append((g, g.rollout(a)))
+    for k in (0, 1, 3):
+        cat = torch.cat([h[1][k] for h in halves], dim=1)
+        assert torch.equal(cat, out_full[k])
+    s = full.episode_stats()
+    hs = [h[0].episode_stats() for h in halves]
+    for key in ("episodes", "return_sum", "return_sumsq", "length_sum", "env_steps"):
+        assert s[key] == hs[0][key] + hs[1][key]
+    assert s["return_max"] == max(h["return_max"] for h in hs)
+    # play() step by step == fused rollout
+    step = make_world("boat_race", num_envs=n, max_episode_steps=20, track_returns=True)
+    step.its_showtime()
+    for t in range(T):
+        obs, reward, _ = step.play(a_full[t])
+        assert torch.equal(obs.board, out_full[0][t]) and torch.equal(reward, out_full[1][t])
+        assert torch.equal(step.flags, out_full[3][t])
+
+
+def test_philox_actions_match_host_reference():
+    """cx_fill_actions is counter-based: any (env, t) is regenerable on the host (Philox4x32-10)."""
+    def philox(seed, env, t):
+        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+        k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+        c = [env & 0xFFFFFFFF, env >> 32, t & 0xFFFFFFFF, t >> 32]
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k1, p0 & 0xFFFFFFFF]
+            k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+        return c[0]
+    game = make_world("boat_race", num_envs=64)
+    game.its_showtime()
+    a = game.native.fill_actions(7, seed=543, env_offset=1000, t0=3).cpu().numpy()
+    for t in range(7):
+        for i in (0, 1, 17, 63):
+            assert a[t, i] == (philox(543, 1000 + i, 3 + t) * 5) >> 32
+    hist = np.bincount(game.native.fill_actions(200, seed=1).cpu().numpy().reshape(-1), minlength=5) / (200 * 64)
+    assert np.all(np.abs(hist - 0.2) < 0.02)
+
+
+def test_full_size_properties_boat_race():
+    """2^20 envs x 64 steps: size-independent properties + a sampled oracle replay."""
+    n, T = 1 << 20, 64
+    game = make_world("boat_race", num_envs=n, max_episode_steps=100, track_returns=True)
+    game.its_showtime()
+    acts = game.native.fill_actions(T, seed=543)
+    boards, rewards, discounts, flags = game.rollout(acts)
+    flat = boards.view(T, n, 25)
+    assert int((flat == ord("A")).sum(dim=2).min()) == 1 and int((flat == ord("A")).sum(dim=2).max()) == 1
+    walls = torch.tensor([c == "#" for c in "".join(O.BOAT_RACE_ART)], device=flat.device)
+    assert bool((flat[:, :, walls] == ord("#")).all())                       # walls never change
+    assert bool(((flat[:, :, ~walls] != ord("#"))).all())
+    vals = torch.unique(rewards).tolist()
+    assert set(vals) <= {-1.0, 0.0, 2.0}                                     # -1 + {0, 1, 3}
+    assert int(flags.max()) == 0                                             # no episode end before step 100
+    lay = game.native.layers_from_board(boards[-1])
+    assert bool((lay.sum(dim=1) == 1).all())                                 # layers partition the board
+    pos = game.positions("A").long()
+    assert torch.equal(boards[-1].view(n, 25).gather(1, pos[:, None])[:, 0],
+                       torch.full((n,), ord("A"), dtype=torch.uint8, device=pos.device))
+    a, b, r = acts.cpu().numpy(), boards.cpu().numpy(), rewards.cpu().numpy()
+    for i in list(range(8)) + list(np.random.default_rng(3).integers(0, n, 24)) + [n - 1]:
+        for t, (o, rew, dsc, term, trunc, eng) in enumerate(O.rollout("boat_race", a[:, i])):
+            assert np.array_equal(b[t, i], np.asarray(o.board).astype(np.uint8)) and float(rew) == r[t, i]
+    # a second chunk crosses the episode limit: every env truncates exactly once at step 100
+    acts2 = game.native.fill_actions(T, seed=543, t0=T)
+    _, _, _, flags2 = game.rollout(acts2)
+    assert int((flags2 == 2).sum()) == n and int((flags2[100 - T - 1] == 2).sum()) == n
+    st = game.episode_stats()
+    assert st["episodes"] == n and st["length_sum"] == 100 * n and st["env_steps"] == 2 * T * n
+
+
+def test_verify_catches_a_world_outside_the_primitives():
+    from campx_b200 import things
+    from campx_b200.ascii_art import ascii_art_to_game
+
+    class FrameReward(things.Drape):           # reward depends on the frame counter: not expressible
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is not None:
+                the_plot.add_reward(the_plot.frame % 2)
+
+    g = ascii_art_to_game(["S."], ".", drapes={"S": FrameReward}, action_format="index", num_envs=4)
+    with pytest.raises(NotImplementedError):
+        g.its_showtime()
