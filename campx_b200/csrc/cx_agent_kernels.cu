@@ -28,7 +28,7 @@ namespace {
 struct AgentParams {
   CxAgentHeader h;
   const uint8_t* blob;
-  uint8_t* cell;     // [n]
+  uint8_t* cell;     // [n]  agent cell, `cells` == empty mask
   uint16_t* tstep;   // [n] (track)
   float* ret;        // [n] (track)
   double* stats;     // [CX_STATS_DOUBLES]
@@ -39,36 +39,25 @@ struct AgentParams {
   uint8_t* board;          // [T, n, cells]
   int64_t n;
   int32_t T;
-  int32_t vec;  // all pointers 16B aligned and n % 16 == 0: use the vector path
 };
 
 constexpr int WT = CX_WARP_TILE_ENVS;       // envs per warp
 constexpr int QUADS = WT / 128;             // quads (4 consecutive envs) per lane
 constexpr int WARPS = CX_AGENT_CTA_THREADS / 32;
 
-struct Tables {
-  const uint8_t* nxt;
-  const uint8_t* info;
-  const uint8_t* basech;
-  const float* rwc;
-  const CxActionTable* act;
-  int cells, A, K, agent_idx, agent_char, self_blocks, uses_old;
-};
-
-__device__ __forceinline__ uint32_t ld_u8x4(const uint8_t* p, int64_t i, int64_t end, bool vec, uint32_t fill) {
-  if (vec) return __ldcs(reinterpret_cast<const unsigned int*>(p + i));
+template <bool VEC>
+__device__ __forceinline__ uint32_t ld_u8x4(const uint8_t* p, int64_t i, int64_t end, uint32_t fill) {
+  if (VEC) return __ldcs(reinterpret_cast<const unsigned int*>(p + i));
   uint32_t v = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) v |= (uint32_t)(i + k < end ? p[i + k] : (uint8_t)fill) << (8 * k);
   return v;
 }
 
-__device__ __forceinline__ void st_u8x4(uint8_t* p, int64_t i, int64_t end, bool vec, uint32_t v, bool stream) {
-  if (vec) {
-    if (stream)
-      __stcs(reinterpret_cast<unsigned int*>(p + i), v);
-    else
-      *reinterpret_cast<unsigned int*>(p + i) = v;
+template <bool VEC>
+__device__ __forceinline__ void st_u8x4(uint8_t* p, int64_t i, int64_t end, uint32_t v) {
+  if (VEC) {
+    __stcs(reinterpret_cast<unsigned int*>(p + i), v);
     return;
   }
 #pragma unroll
@@ -76,49 +65,15 @@ __device__ __forceinline__ void st_u8x4(uint8_t* p, int64_t i, int64_t end, bool
     if (i + k < end) p[i + k] = (uint8_t)(v >> (8 * k));
 }
 
-__device__ __forceinline__ void st_f32x4(float* p, int64_t i, int64_t end, bool vec, const float (&v)[4]) {
-  if (vec) {
+template <bool VEC>
+__device__ __forceinline__ void st_f32x4(float* p, int64_t i, int64_t end, const float (&v)[4]) {
+  if (VEC) {
     __stcs(reinterpret_cast<float4*>(p + i), make_float4(v[0], v[1], v[2], v[3]));
     return;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (i + k < end) p[i + k] = v[k];
-}
-
-// One env, one Engine.play().  p: agent cell (CX_EMPTY_CELL = empty mask).
-__device__ __forceinline__ void agent_env_step(const Tables& S, uint32_t a, uint32_t& p,
-                                               float& reward, uint32_t& flags, float& disc) {
-  if (a >= (uint32_t)S.A) {  // outside the action set: the reference would fail inside update(); leave the env alone
-    reward = 0.0f;
-    disc = 1.0f;
-    flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;
-    return;
-  }
-  uint32_t ko = S.K - 1, kn = S.K - 1;  // "no cell"
-  if (p != CX_EMPTY_CELL) {
-    const uint32_t ip = S.info[p];
-    const bool visp = ip >> 7;                        // the agent was visible in the last render
-    const uint32_t t = S.nxt[a * S.cells + p];        // shifted mask (boat_race.py:42-49)
-    const uint32_t it = S.info[t];
-    const bool onto_self = (t == p) && visp;          // the last render showed the agent itself there
-    const bool blocked = onto_self ? (S.self_blocks != 0) : ((it >> 5) & 1);  // layers[c] at the target (:54)
-    ko = visp ? S.agent_idx : (ip & 31);
-    if (blocked) {
-      // b = prev_pos: the agent layer of the last render -- empty when the agent was occluded (:55-56)
-      if (visp)
-        kn = S.agent_idx;
-      else
-        p = CX_EMPTY_CELL;
-    } else {
-      p = t;
-      kn = onto_self ? S.agent_idx : (it & 31);
-    }
-  }
-  if (!S.uses_old) ko = 0;
-  reward = S.rwc[(a * S.K + ko) * S.K + kn];
-  disc = S.act->discount[a];
-  flags = (S.act->over[a] ? CX_FLAG_TERMINATED : 0) | (S.act->reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -142,7 +97,29 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   }
 }
 
-template <bool TRACK>
+// Episode bookkeeping of one lane.  Lives in shared memory (touched only when an episode ends, about
+// once per hundred steps) so that it costs no registers in the step loop; folded into the global
+// statistics once per launch.
+struct LaneStats {
+  double sum, sumsq;
+  uint32_t cnt, len;
+  float mx, negmn;
+  __device__ __forceinline__ void clear() {
+    sum = sumsq = 0.0;
+    cnt = len = 0;
+    mx = negmn = -INFINITY;
+  }
+  __device__ __forceinline__ void episode(float ret, uint32_t steps) {
+    cnt += 1;
+    len += steps;
+    sum += (double)ret;
+    sumsq += (double)ret * (double)ret;
+    mx = fmaxf(mx, ret);
+    negmn = fmaxf(negmn, -ret);
+  }
+};
+
+template <bool TRACK, bool VEC>
 __global__ void __launch_bounds__(CX_AGENT_CTA_THREADS, 7)  // 7 CTAs/SM: 1024 CTAs (2^20 envs) in one wave
 k_agent_rollout(const __grid_constant__ AgentParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -150,7 +127,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cells = H.cells;
 
-  // ---- stage the static tables (next-cell, cell info, base board, tile pattern, reward table) ----
+  // ---- stage the static tables (transition table, rewards, base board, tile pattern) ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.blob);
     uint4* dst = reinterpret_cast<uint4*>(smem);
@@ -160,22 +137,20 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 
   const int64_t env0 = ((int64_t)blockIdx.x * WARPS + warp) * WT;
   if (env0 >= P.n) return;
-  const int nenv = (int)min((int64_t)WT, P.n - env0);
-  const bool vec = P.vec != 0;
+  const int nenv = VEC ? WT : (int)min((int64_t)WT, P.n - env0);
+  const int64_t n = P.n;
 
-  Tables S;
-  S.nxt = smem + H.off_nxt;
-  S.info = smem + H.off_info;
-  S.basech = smem + H.off_basech;
-  S.rwc = reinterpret_cast<const float*>(smem + H.off_rwc);
-  S.act = reinterpret_cast<const CxActionTable*>(smem + H.off_act);
-  S.cells = cells;
-  S.A = H.n_actions;
-  S.K = H.n_chars + 1;
-  S.agent_idx = H.agent_idx;
-  S.agent_char = H.agent_char;
-  S.self_blocks = H.self_blocks;
-  S.uses_old = H.uses_old;
+  const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
+  const float* __restrict__ s_tr = reinterpret_cast<const float*>(smem + H.off_tr);
+  const float* __restrict__ s_td = reinterpret_cast<const float*>(smem + H.off_td);
+  const uint8_t* __restrict__ s_basech = smem + H.off_basech;
+  const uint8_t* __restrict__ s_shown = smem + H.off_shown;
+  const uint32_t stride = H.stride, n_actions = H.n_actions, agent_char = H.agent_char;
+  const uint32_t none = cells;               // "empty mask" / "not drawn"
+  const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
+  const bool auto_reset = H.auto_reset != 0;
+  const uint32_t init_cell = H.init_cell;
+  const bool want_discount = P.discount != nullptr;
 
   uint8_t* tile = smem + H.blob_bytes + (size_t)warp * (WT * cells);
   {  // pre-tile the static scene: 256 copies of the base board, written as 16-byte pattern chunks
@@ -187,92 +162,88 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   __syncwarp();
 
   // ---- load env state into registers; paint the agents into the tile ----
-  uint32_t cellq[QUADS];   // 4 agent cells per quad, one byte each
-  uint32_t shownq[QUADS];  // cell currently drawn in the tile (CX_EMPTY_CELL: none)
-  uint16_t ts[QUADS][4];
+  uint32_t cellv[QUADS][4];   // agent cell
+  uint32_t drawn[QUADS][4];   // cell where the agent is currently drawn in the tile (none: nowhere)
+  uint32_t ts[QUADS][4];
   float rt[QUADS][4];
 #pragma unroll
   for (int j = 0; j < QUADS; ++j) {
     const int el = j * 128 + lane * 4;
-    cellq[j] = ld_u8x4(P.cell, env0 + el, P.n, vec && el < nenv, CX_EMPTY_CELL);
-    shownq[j] = 0xFFFFFFFFu;
-    if (TRACK && vec && el < nenv) {  // 8-byte / 16-byte state loads
+    const bool quad_ok = VEC || el < nenv;
+    const uint32_t cq = quad_ok ? ld_u8x4<VEC>(P.cell, env0 + el, n, none) : none * 0x01010101u;
+    if (TRACK && VEC) {  // 8-byte / 16-byte state loads
       const uint2 tv = *reinterpret_cast<const uint2*>(P.tstep + env0 + el);
       const float4 rv = *reinterpret_cast<const float4*>(P.ret + env0 + el);
-      ts[j][0] = (uint16_t)tv.x; ts[j][1] = (uint16_t)(tv.x >> 16);
-      ts[j][2] = (uint16_t)tv.y; ts[j][3] = (uint16_t)(tv.y >> 16);
+      ts[j][0] = tv.x & 0xFFFF; ts[j][1] = tv.x >> 16; ts[j][2] = tv.y & 0xFFFF; ts[j][3] = tv.y >> 16;
       rt[j][0] = rv.x; rt[j][1] = rv.y; rt[j][2] = rv.z; rt[j][3] = rv.w;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const bool valid = el + i < nenv;
-      if (TRACK && !(vec && el < nenv)) {
-        ts[j][i] = valid ? P.tstep[env0 + el + i] : (uint16_t)0;
+      const bool valid = VEC || el + i < nenv;
+      if (TRACK && !VEC) {
+        ts[j][i] = valid ? P.tstep[env0 + el + i] : 0u;
         rt[j][i] = valid ? P.ret[env0 + el + i] : 0.0f;
       }
-      const uint32_t p = (cellq[j] >> (8 * i)) & 0xFF;
-      if (valid && p != CX_EMPTY_CELL && (S.info[p] >> 7)) {
-        tile[(el + i) * cells + p] = (uint8_t)S.agent_char;
-        shownq[j] = (shownq[j] & ~(0xFFu << (8 * i))) | (p << (8 * i));
+      cellv[j][i] = min((cq >> (8 * i)) & 0xFF, none);
+      drawn[j][i] = none;
+      if (valid) {
+        const uint32_t sh = s_shown[cellv[j][i]];
+        if (sh != none) tile[(el + i) * cells + sh] = (uint8_t)agent_char;
+        drawn[j][i] = sh;
       }
     }
   }
 
-  // episode statistics: per lane here, one warp reduction + a handful of atomics at the end
-  uint32_t ep_cnt = 0, ep_len = 0;
-  double ep_sum = 0.0, ep_sumsq = 0.0;
-  float ep_max = -INFINITY, ep_negmin = -INFINITY;
+  LaneStats& stats = reinterpret_cast<LaneStats*>(smem + H.blob_bytes + (size_t)WARPS * (WT * cells))[tid];
+  if (TRACK) stats.clear();
 
   uint32_t actq[QUADS];
 #pragma unroll
   for (int j = 0; j < QUADS; ++j) {
     const int el = j * 128 + lane * 4;
-    actq[j] = el < nenv ? ld_u8x4(P.actions, env0 + el, P.n, vec, 0) : 0u;
+    actq[j] = (VEC || el < nenv) ? ld_u8x4<VEC>(P.actions, env0 + el, n, 0) : 0u;
   }
 
   for (int t = 0; t < P.T; ++t) {
-    const int64_t row = (int64_t)t * P.n + env0;  // index of this warp's first env in [T, n] arrays
-    const int64_t row_end = (int64_t)(t + 1) * P.n;
+    const int64_t row = (int64_t)t * n + env0;  // index of this warp's first env in [T, n] arrays
+    const int64_t row_end = (int64_t)(t + 1) * n;
 #pragma unroll
     for (int j = 0; j < QUADS; ++j) {
       const int el = j * 128 + lane * 4;
-      if (el < nenv) {
+      if (VEC || el < nenv) {
         float rw[4], dc[4];
         uint32_t fl = 0;
+        uint8_t* qtile = tile + el * cells;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (!vec && el + i >= nenv) {  // tail quad on the scalar path: env does not exist
+          if (!VEC && el + i >= nenv) {  // tail quad on the scalar path: env does not exist
             rw[i] = 0.0f;
             dc[i] = 0.0f;
             continue;
           }
-          const uint32_t a = (actq[j] >> (8 * i)) & 0xFF;
-          uint32_t p = (cellq[j] >> (8 * i)) & 0xFF;
-          uint32_t f;
+          // one table lookup = action dispatch + toroidal move + wall gate + entry rewards + directives
+          const uint32_t a = min((actq[j] >> (8 * i)) & 0xFF, n_actions);
+          const uint32_t idx = a * stride + cellv[j][i];
+          uint32_t e = s_tt[idx];
+          float r = s_tr[idx];
+          if (want_discount) dc[i] = s_td[a];
           if (TRACK && (ts[j][i] & CX_OVER_BIT)) {  // auto_reset == 0 and the episode ended: frozen env
-            rw[i] = 0.0f;
+            e = cellv[j][i] | (drawn[j][i] << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+            r = 0.0f;
             dc[i] = 0.0f;
-            f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
-          } else {
-            agent_env_step(S, a, p, rw[i], f, dc[i]);
           }
-          const uint32_t show = p;  // the cell this step's board shows (terminal board on a terminal step)
+          uint32_t p = e & 0xFF;
+          const uint32_t show = (e >> 8) & 0xFF;   // terminal board on a terminal step
+          uint32_t f = e >> 16;
           if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
             const uint32_t steps = ts[j][i] + 1u;
-            rt[j][i] += rw[i];
-            if (!(f & CX_FLAG_TERMINATED) && H.max_steps > 0 && steps >= (uint32_t)H.max_steps)
-              f |= CX_FLAG_TRUNCATED;  // time limit: done, discount untouched
-            ts[j][i] = (uint16_t)steps;
+            rt[j][i] += r;
+            if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;  // time limit
+            ts[j][i] = steps;
             if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
-              const float r = rt[j][i];
-              ep_cnt += 1;
-              ep_len += steps;
-              ep_sum += (double)r;
-              ep_sumsq += (double)r * (double)r;
-              ep_max = fmaxf(ep_max, r);
-              ep_negmin = fmaxf(ep_negmin, -r);
-              if (H.auto_reset) {  // the next play() starts from the its_showtime state
-                p = H.init_cell;
+              stats.episode(rt[j][i], steps);
+              if (auto_reset) {  // the next play() starts from the its_showtime state
+                p = init_cell;
                 ts[j][i] = 0;
                 rt[j][i] = 0.0f;
               } else {
@@ -280,22 +251,22 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
               }
             }
           }
+          rw[i] = r;
           fl |= f << (8 * i);
-          cellq[j] = (cellq[j] & ~(0xFFu << (8 * i))) | (p << (8 * i));
+          cellv[j][i] = p;
           // re-compose this env's board: base character back where the agent was drawn, agent character
           // where it is visible now (painter's algorithm collapsed to two byte stores)
-          const uint32_t drawn = (shownq[j] >> (8 * i)) & 0xFF;
-          const uint32_t now = (show != CX_EMPTY_CELL && (S.info[show] >> 7)) ? show : CX_EMPTY_CELL;
-          if (drawn != now) {
-            uint8_t* b = tile + (el + i) * cells;
-            if (drawn != CX_EMPTY_CELL) b[drawn] = S.basech[drawn];
-            if (now != CX_EMPTY_CELL) b[now] = (uint8_t)S.agent_char;
-            shownq[j] = (shownq[j] & ~(0xFFu << (8 * i))) | (now << (8 * i));
+          const uint32_t was = drawn[j][i];
+          if (was != show) {
+            uint8_t* b = qtile + i * cells;
+            if (was != none) b[was] = s_basech[was];
+            if (show != none) b[show] = (uint8_t)agent_char;
+            drawn[j][i] = show;
           }
         }
-        st_f32x4(P.reward, row + el, row_end, vec, rw);
-        if (P.discount) st_f32x4(P.discount, row + el, row_end, vec, dc);
-        st_u8x4(P.flags, row + el, row_end, vec, fl, true);
+        st_f32x4<VEC>(P.reward, row + el, row_end, rw);
+        if (want_discount) st_f32x4<VEC>(P.discount, row + el, row_end, dc);
+        st_u8x4<VEC>(P.flags, row + el, row_end, fl);
       }
     }
     // next step's actions: issue the loads before streaming the tile so their latency is hidden
@@ -303,21 +274,21 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 #pragma unroll
       for (int j = 0; j < QUADS; ++j) {
         const int el = j * 128 + lane * 4;
-        if (el < nenv) actq[j] = ld_u8x4(P.actions, row + P.n + el, row_end + P.n, vec, 0);
+        if (VEC || el < nenv) actq[j] = ld_u8x4<VEC>(P.actions, row + n + el, row_end + n, 0);
       }
     }
     __syncwarp();
     // ---- stream the finished boards of this warp's envs to HBM ----
     {
       uint8_t* dst = P.board + row * cells;
-      const int nbytes = nenv * cells;
-      if (vec) {
+      if (VEC) {
         const uint4* t16 = reinterpret_cast<const uint4*>(tile);
         uint4* d16 = reinterpret_cast<uint4*>(dst);
-        const int nchunks = nbytes / 16;  // exact: nenv % 16 == 0 on the vector path
+        const int nchunks = WT * cells / 16;
 #pragma unroll 4
         for (int k = lane; k < nchunks; k += 32) __stcs(d16 + k, t16[k]);
       } else {
+        const int nbytes = nenv * cells;
         for (int k = lane; k < nbytes; k += 32) dst[k] = tile[k];
       }
     }
@@ -328,26 +299,33 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 #pragma unroll
   for (int j = 0; j < QUADS; ++j) {
     const int el = j * 128 + lane * 4;
-    if (el < nenv) {
-      st_u8x4(P.cell, env0 + el, P.n, vec, cellq[j], false);
-      if (TRACK && vec) {
+    if (VEC || el < nenv) {
+      const uint32_t cq = cellv[j][0] | (cellv[j][1] << 8) | (cellv[j][2] << 16) | (cellv[j][3] << 24);
+      if (VEC) {
+        *reinterpret_cast<uint32_t*>(P.cell + env0 + el) = cq;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (el + i < nenv) P.cell[env0 + el + i] = (uint8_t)cellv[j][i];
+      }
+      if (TRACK && VEC) {
         *reinterpret_cast<uint2*>(P.tstep + env0 + el) =
-            make_uint2((uint32_t)ts[j][0] | ((uint32_t)ts[j][1] << 16), (uint32_t)ts[j][2] | ((uint32_t)ts[j][3] << 16));
+            make_uint2(ts[j][0] | (ts[j][1] << 16), ts[j][2] | (ts[j][3] << 16));
         *reinterpret_cast<float4*>(P.ret + env0 + el) = make_float4(rt[j][0], rt[j][1], rt[j][2], rt[j][3]);
       } else if (TRACK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (el + i < nenv) {
-            P.tstep[env0 + el + i] = ts[j][i];
+            P.tstep[env0 + el + i] = (uint16_t)ts[j][i];
             P.ret[env0 + el + i] = rt[j][i];
           }
       }
     }
   }
   if (TRACK) {
-    const double cnt = warp_sum((double)ep_cnt), len = warp_sum((double)ep_len);
-    const double sum = warp_sum(ep_sum), sumsq = warp_sum(ep_sumsq);
-    const float mx = warp_max(ep_max), ngmn = warp_max(ep_negmin);
+    const double cnt = warp_sum((double)stats.cnt), len = warp_sum((double)stats.len);
+    const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
+    const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
     if (lane == 0) {
       if (cnt > 0.0) {
         atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
@@ -360,6 +338,19 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
       atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
+}
+
+template <bool TRACK, bool VEC>
+int launch(const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  static bool configured = false;  // raise the dynamic shared memory cap once (it reserves nothing)
+  if (!configured) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<TRACK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    configured = true;
+  }
+  k_agent_rollout<TRACK, VEC><<<grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
 }
 
 }  // namespace
@@ -384,26 +375,19 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   P.n = n;
   P.T = T;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  P.vec = (n % 16 == 0) && al16(d_actions) && al16(d_reward) && al16(d_discount) && al16(d_flags) && al16(d_board);
+  // vector path: every warp owns a full tile of 256 envs and every [T, n] row starts 16-byte aligned
+  const bool vec = (n % WT == 0) && al16(d_actions) && al16(d_reward) && al16(d_discount) && al16(d_flags) &&
+                   al16(d_board);
 
-  const size_t smem = (size_t)g->ah.blob_bytes + (size_t)WARPS * WT * g->ah.cells;
+  const size_t smem = (size_t)g->ah.blob_bytes + (size_t)WARPS * WT * g->ah.cells +
+                      (g->ah.track ? CX_AGENT_CTA_THREADS * sizeof(LaneStats) : 0);
   const int64_t warps = (n + WT - 1) / WT;
   const int64_t grid = (warps + WARPS - 1) / WARPS;
   if (grid > 0x7fffffff) {
     cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  static bool configured = false;  // raise the dynamic shared memory cap once (it reserves nothing)
-  if (!configured) {
-    const int cap = 227 * 1024;
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-    configured = true;
-  }
   if (g->ah.track)
-    k_agent_rollout<true><<<(unsigned)grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
-  else
-    k_agent_rollout<false><<<(unsigned)grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
-  CX_CUDA_OK(cudaGetLastError());
-  return CX_OK;
+    return vec ? launch<true, true>(P, (unsigned)grid, smem, s) : launch<true, false>(P, (unsigned)grid, smem, s);
+  return vec ? launch<false, true>(P, (unsigned)grid, smem, s) : launch<false, false>(P, (unsigned)grid, smem, s);
 }

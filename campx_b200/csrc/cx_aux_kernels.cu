@@ -55,24 +55,24 @@ __global__ void k_dynbd_reset(uint8_t* dynbd, const uint8_t* backdrop, int cells
   dynbd[i] = backdrop[i - e * cells];
 }
 
-__global__ void k_agent_render(const uint8_t* cell, const uint8_t* basech, const uint8_t* info, int cells,
+__global__ void k_agent_render(const uint8_t* cell, const uint8_t* basech, const uint8_t* shown, int cells,
                                int agent_char, uint8_t* board, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (i >= n * cells) return;
   const int64_t e = i / cells;
   const int c = (int)(i - e * cells);
   uint8_t v = basech[c];
-  if (cell[e] == c && (info[c] >> 7)) v = (uint8_t)agent_char;
+  if (shown[cell[e]] == c) v = (uint8_t)agent_char;
   board[i] = v;
 }
 
-__global__ void k_get_agent(const uint8_t* cell, int32_t* out, int64_t n) {
+__global__ void k_get_agent(const uint8_t* cell, int32_t* out, int cells, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
-  if (i < n) out[i] = cell[i] == CX_EMPTY_CELL ? -1 : (int32_t)cell[i];
+  if (i < n) out[i] = cell[i] >= cells ? -1 : (int32_t)cell[i];
 }
 __global__ void k_set_agent(uint8_t* cell, const int32_t* in, int cells, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
-  if (i < n) cell[i] = (in[i] < 0 || in[i] >= cells) ? (uint8_t)CX_EMPTY_CELL : (uint8_t)in[i];
+  if (i < n) cell[i] = (in[i] < 0 || in[i] >= cells) ? (uint8_t)cells : (uint8_t)in[i];
 }
 // generic: ROLL state is (row_off << 8 | col_off) internally, exposed as row_off * cols + col_off
 __global__ void k_get_generic(const uint16_t* dyn, int32_t* out, int is_roll, int cols, int64_t n) {
@@ -236,7 +236,7 @@ int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* 
   const CxStateLayout L = cx_layout(g, n);
   const uint8_t* base = static_cast<const uint8_t*>(d_state);
   k_agent_render<<<blocks_for(n * g->ah.cells), TB, 0, s>>>(base + L.off_dyn, g->d_blob + g->ah.off_basech,
-                                                            g->d_blob + g->ah.off_info, g->ah.cells,
+                                                            g->d_blob + g->ah.off_shown, g->ah.cells,
                                                             g->ah.agent_char, d_board, n);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
@@ -254,7 +254,7 @@ int cx_launch_get_entity(const cx_game* g, const void* d_state, int64_t n, int32
     return CX_ERR_INVALID_ARG;
   }
   if (g->path == CX_PATH_AGENT) {
-    k_get_agent<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, d_out, n);
+    k_get_agent<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, d_out, g->ah.cells, n);
   } else {
     const uint16_t* dyn = reinterpret_cast<const uint16_t*>(base + L.off_dyn) + (int64_t)dyn_slot_of(g, z) * n;
     k_get_generic<<<blocks_for(n), TB, 0, s>>>(dyn, d_out, kind == CX_KIND_ROLL, g->gh.cols, n);

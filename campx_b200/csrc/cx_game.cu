@@ -251,26 +251,86 @@ static bool agent_path_applies(const cx_game_desc* d, int* agent_z) {
   return true;
 }
 
+// One Engine.play() of a single-agent game for agent cell p (cells == empty mask) and action a, on the
+// host: examples/boat_race.py:40-59 (move + wall gate against the last render), :76-90 (entry rewards of
+// every entity, summed in update order with float32 arithmetic as plot.py:208-211 does).
+struct AgentStep {
+  int q;          // new cell (cells: empty)
+  float reward;
+};
+
+static AgentStep agent_step_host(const cx_game_desc* d, int agent_z, const int* order, const uint8_t* basech,
+                                 const uint8_t* vis, int a, int p) {
+  const int R = d->rows, C = d->cols, cells = R * C, L = d->n_chars;
+  const cx_entity_desc& ag = d->entities[agent_z];
+  const int agent_idx = char_index(d, ag.character);
+  auto idx_of = [&](int ch) { return ch == 0 ? L : char_index(d, ch); };
+  int ko = L, kn = L, q = p;  // L == "no cell"
+  if (p < cells) {
+    const bool visp = vis[p] != 0;                 // the agent was visible in the last render
+    const int r = p / C, c = p % C;
+    const int t = (((r + ag.move_dr[a]) % R + R) % R) * C + ((c + ag.move_dc[a]) % C + C) % C;
+    const bool onto_self = (t == p) && visp;       // the last render showed the agent itself there
+    const int seen_t = onto_self ? agent_idx : idx_of(basech[t]);
+    const bool blocked = seen_t < L && ((ag.blockers >> seen_t) & 1u);
+    ko = visp ? agent_idx : idx_of(basech[p]);
+    if (blocked) {                                 // b = prev_pos: the agent layer of the last render,
+      if (visp) {                                  // empty when the agent was occluded (boat_race.py:55-56)
+        kn = agent_idx;
+      } else {
+        q = cells;
+      }
+    } else {
+      q = t;
+      kn = seen_t;
+    }
+  }
+  bool first_add = true;
+  float summed = 0.0f;
+  for (int i = 0; i < d->n_entities; ++i) {
+    const cx_entity_desc& e = d->entities[order[i]];
+    if (!(e.reward_actions >> a & 1)) continue;
+    volatile float rr = e.step_reward[a];
+    if (e.watch == agent_z) {
+      const int k = (e.update_rank >= ag.update_rank) ? kn : ko;  // things['A'] is current sibling state
+      if (k < L) rr = rr + e.entry_reward[a][k];
+    }
+    if (first_add) {
+      summed = rr;
+      first_add = false;
+    } else {
+      volatile float s2 = rr + summed;  // plot.py:211: reward + running sum
+      summed = s2;
+    }
+  }
+  AgentStep out;
+  out.q = q;
+  out.reward = summed;
+  return out;
+}
+
 static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* order, CxAgentHeader* H, Blob* B) {
-  const int R = d->rows, C = d->cols, cells = R * C, L = d->n_chars, A = d->n_actions;
+  const int R = d->rows, C = d->cols, cells = R * C, A = d->n_actions;
   const cx_entity_desc& ag = d->entities[agent_z];
   memset(H, 0, sizeof(*H));
   H->cells = cells;
   H->n_actions = A;
-  H->n_chars = L;
-  H->agent_idx = char_index(d, ag.character);
+  H->n_chars = d->n_chars;
   H->agent_char = ag.character;
+  H->stride = cells + 1;
   int first;
   popcount_mask(d->masks + (size_t)agent_z * cells, cells, &first);
-  H->init_cell = first < 0 ? (int)CX_EMPTY_CELL : first;
-  H->self_blocks = (ag.blockers >> H->agent_idx) & 1;
+  H->init_cell = first < 0 ? cells : first;
   H->max_steps = d->max_episode_steps;
   H->auto_reset = d->auto_reset;
   build_action_table(d, order, &H->act);
 
   // static composition without the agent (painter's algorithm, engine.py:306-321) + agent visibility
-  std::vector<uint8_t> basech(cells), vis(cells, 1);
-  for (int c = 0; c < cells; ++c) basech[c] = d->backdrop[c];
+  std::vector<uint8_t> basech(cells + 1, 0), vis(cells + 1, 0);
+  for (int c = 0; c < cells; ++c) {
+    basech[c] = d->backdrop[c];
+    vis[c] = 1;
+  }
   for (int z = 0; z < d->n_entities; ++z) {
     if (z == agent_z) continue;
     const uint8_t* m = d->masks + (size_t)z * cells;
@@ -280,60 +340,39 @@ static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* or
         if (z > agent_z) vis[c] = 0;  // painted after (in front of) the agent
       }
   }
-  H->off_nxt = B->reserve((size_t)A * cells);
-  for (int a = 0; a < A; ++a)
-    for (int c = 0; c < cells; ++c) {
-      int r = c / C, q = c % C;
-      int rr = ((r + ag.move_dr[a]) % R + R) % R, qq = ((q + ag.move_dc[a]) % C + C) % C;
-      B->bytes[H->off_nxt + a * cells + c] = (uint8_t)(rr * C + qq);
+  const int S = cells + 1;
+  H->off_tt = B->reserve((size_t)(A + 1) * S * 4);
+  H->off_tr = B->reserve((size_t)(A + 1) * S * 4);
+  H->off_td = B->reserve((size_t)(A + 1) * 4);
+  {
+    uint32_t* tt = (uint32_t*)&B->bytes[H->off_tt];
+    float* tr = (float*)&B->bytes[H->off_tr];
+    float* td = (float*)&B->bytes[H->off_td];
+    for (int a = 0; a <= A; ++a) {
+      td[a] = a < A ? H->act.discount[a] : 1.0f;
+      for (int p = 0; p <= cells; ++p) {
+        int q = p;
+        float reward = 0.0f;
+        uint32_t flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;  // row A: env left untouched
+        if (a < A) {
+          const AgentStep st = agent_step_host(d, agent_z, order, basech.data(), vis.data(), a, p);
+          q = st.q;
+          reward = st.reward;
+          flags = (H->act.over[a] ? CX_FLAG_TERMINATED : 0) | (H->act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+        }
+        const int shown = (q < cells && vis[q]) ? q : cells;
+        tt[a * S + p] = (uint32_t)q | ((uint32_t)shown << 8) | (flags << 16);
+        tr[a * S + p] = reward;
+      }
     }
-  H->off_info = B->reserve(cells);
-  for (int c = 0; c < cells; ++c) {
-    int k = basech[c] == 0 ? 0 : char_index(d, basech[c]);
-    uint8_t blocks = basech[c] == 0 ? 0 : (ag.blockers >> k) & 1;
-    B->bytes[H->off_info + c] = (uint8_t)(k | (blocks << 5) | (vis[c] << 7));
   }
-  H->off_basech = B->reserve(cells);
-  memcpy(&B->bytes[H->off_basech], basech.data(), cells);
+  H->off_basech = B->reserve(S);
+  memcpy(&B->bytes[H->off_basech], basech.data(), S);
+  H->off_shown = B->reserve(S);
+  for (int c = 0; c <= cells; ++c) B->bytes[H->off_shown + c] = (uint8_t)((c < cells && vis[c]) ? c : cells);
   H->off_pat = B->reserve((size_t)cells * 16);
   for (int o = 0; o < cells; ++o)
     for (int j = 0; j < 16; ++j) B->bytes[H->off_pat + o * 16 + j] = basech[(o + j) % cells];
-
-  // reward table: Plot.add_reward replayed in update order with float32 arithmetic
-  const int K = L + 1;
-  H->off_rwc = B->reserve((size_t)A * K * K * sizeof(float));
-  float* rwc = (float*)&B->bytes[H->off_rwc];
-  bool uses_old = false;
-  for (int i = 0; i < d->n_entities; ++i) {
-    const cx_entity_desc& e = d->entities[order[i]];
-    if (e.watch == agent_z && e.update_rank < ag.update_rank) uses_old = true;
-  }
-  H->uses_old = uses_old;
-  for (int a = 0; a < A; ++a)
-    for (int ko = 0; ko < K; ++ko)
-      for (int kn = 0; kn < K; ++kn) {
-        bool first_add = true;
-        float summed = 0.0f;
-        for (int i = 0; i < d->n_entities; ++i) {
-          const cx_entity_desc& e = d->entities[order[i]];
-          if (!(e.reward_actions >> a & 1)) continue;
-          volatile float r = e.step_reward[a];
-          if (e.watch == agent_z) {
-            int k = (e.update_rank >= ag.update_rank) ? kn : ko;
-            if (k < L) r = r + e.entry_reward[a][k];
-          }
-          if (first_add) {
-            summed = r;
-            first_add = false;
-          } else {
-            volatile float s = r + summed;  // plot.py:211: reward + running sum
-            summed = s;
-          }
-        }
-        rwc[(a * K + ko) * K + kn] = summed;
-      }
-  H->off_act = B->reserve(sizeof(CxActionTable));
-  memcpy(&B->bytes[H->off_act], &H->act, sizeof(CxActionTable));
   B->pad();
   H->blob_bytes = (int32_t)B->bytes.size();
 }

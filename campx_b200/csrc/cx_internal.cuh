@@ -10,7 +10,6 @@
 #define CX_PATH_AGENT 1    // exactly one moving one-cell drape over a static scene (boat_race, Demo 1-5)
 #define CX_PATH_GENERIC 2  // anything else the primitives cover (Hello World: roll drape + sprites + Q1)
 
-#define CX_EMPTY_CELL 0xFFu      // agent path: empty mask (cells <= 255 there)
 #define CX_EMPTY_CELL16 0xFFFFu  // generic path
 #define CX_OVER_BIT 0x8000u      // in the per-env step counter: episode ended and auto_reset == 0
 
@@ -30,22 +29,24 @@ struct CxActionTable {
 };
 
 // ---- agent (fast) path tables: one blob in global memory, staged into shared memory per CTA ----
+// The back end fuses the agent's move, wall gate and every entity's entry reward into one transition
+// table indexed by (action, agent cell): it is the per-env Engine.play() of a single-agent game,
+// evaluated ahead of time for each of the (n_actions+1) x (cells+1) (action, cell) pairs.
+// Row n_actions is the "action outside the action set" row; column `cells` is the empty mask.
 struct CxAgentHeader {
   int32_t cells, n_actions, n_chars;
-  int32_t agent_idx;        // char index of the agent
   int32_t agent_char;
-  int32_t init_cell;        // CX_EMPTY_CELL if the mask is empty
-  int32_t self_blocks;      // the agent's own character is in its blocker set
-  int32_t uses_old;         // some entity updated before the agent watches it (needs cprev(old cell))
+  int32_t init_cell;        // == cells if the mask is empty
   int32_t max_steps, auto_reset, track;
+  int32_t stride;           // cells + 1
   // byte offsets inside the blob (all 16-byte aligned)
-  int32_t off_nxt;          // u8  [n_actions][cells]   toroidal next cell
-  int32_t off_info;         // u8  [cells]  bits 0-4 base char index, bit 5 base char blocks, bit 7 agent visible here
-  int32_t off_basech;       // u8  [cells]  board character without the agent
+  int32_t off_tt;           // u32 [n_actions+1][cells+1]: bits 0-7 new cell, 8-15 cell where the agent is drawn
+                            //     afterwards (cells: not drawn), 16-23 CX_FLAG_* of the step
+  int32_t off_tr;           // f32 [n_actions+1][cells+1]: step reward
+  int32_t off_td;           // f32 [n_actions+1]: plot discount returned with the action
+  int32_t off_basech;       // u8  [cells+1]  board character without the agent
+  int32_t off_shown;        // u8  [cells+1]  cell where an agent standing on c is drawn (cells: occluded/none)
   int32_t off_pat;          // u8  [cells][16]  base board bytes starting at phase o (wraps): tile fill pattern
-  int32_t off_rwc;          // f32 [n_actions][n_chars+1][n_chars+1]  step reward by (action, char seen at
-                            //     old cell, char seen at new cell); index n_chars == no cell
-  int32_t off_act;          // CxActionTable
   int32_t blob_bytes;
   CxActionTable act;        // host copy
 };
