@@ -204,6 +204,11 @@ static int validate(const cx_game_desc* d) {
       }
     }
     for (int a = 0; a < d->n_actions; ++a) {
+      if (abs((int)e.move_dr[a]) >= d->rows + (d->rows == 1) || abs((int)e.move_dc[a]) >= d->cols + (d->cols == 1)) {
+        cx_set_error("cx_game_create: entity %d action %d moves by (%d, %d), not less than the board size", z, a,
+                     e.move_dr[a], e.move_dc[a]);
+        return CX_ERR_INVALID_ARG;
+      }
       const float dv = e.discount_value[a];
       if (((e.terminate_actions | e.discount_actions) >> a & 1) && !(dv >= 0.0f && dv <= 1.0f)) {
         cx_set_error("Pcontinue must be in range [0,1]");  // plot.py:176-177,250-251
@@ -464,6 +469,26 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
   H->off_rc = B->reserve((size_t)cells * 2);
   uint16_t* rc = (uint16_t*)&B->bytes[H->off_rc];
   for (int c = 0; c < cells; ++c) rc[c] = (uint16_t)(((c / C) << 8) | (c % C));
+  H->off_rowbits = -1;
+  if (C <= 64) {  // per-row bitsets: the fast composition path
+    H->off_rowbits = B->reserve((size_t)E * R * 8);
+    uint64_t* rb = (uint64_t*)&B->bytes[H->off_rowbits];
+    for (int z = 0; z < E; ++z) {
+      const uint8_t* m = d->masks + (size_t)z * cells;
+      if (d->entities[z].kind == CX_KIND_STATIC || d->entities[z].kind == CX_KIND_ROLL)
+        for (int c = 0; c < cells; ++c)
+          if (m[c]) rb[z * R + c / C] |= 1ull << (c % C);
+    }
+  }
+  // envs per warp: small tiles keep ~30 warps per SM resident (two byte tiles per env in shared memory)
+  // while the (env,row) composition tasks still fill the 32 lanes
+  int tile = cells >= 128 ? 8 : (cells >= 32 ? 16 : 32);
+  if (const char* dbg = getenv("CX_GEN_TILE")) {  // development knob
+    const int v = atoi(dbg);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) tile = v;
+  }
+  while (tile > 1 && (size_t)2 * tile * cells > 96 * 1024) tile >>= 1;
+  H->tile_envs = tile;
   B->pad();
   H->blob_bytes = (int32_t)B->bytes.size();
   return CX_OK;

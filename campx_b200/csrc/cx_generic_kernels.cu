@@ -9,18 +9,29 @@
 //   entry rewards              boat_race.py:76-90, Demo 3 cell 3
 //   painter's algorithm        engine.py:306-321 + rendering.py:111,128,150,173-178 -- including the
 //                              storage aliasing: sprites painted before the first drape write into the
-//                              backdrop itself (per-env backdrop plane `dynbd`), and a game without any
-//                              drape has its canvas zeroed at every render
+//                              backdrop itself (per-env backdrop plane), and a game without any drape
+//                              has its canvas zeroed at every render
 //   plot directives            campx/plot.py:161-257, engine.py:285-290
 //
-// Layout: one CTA owns CX_GEN_TILE_ENVS consecutive envs for all T steps.  Phase 1 (one thread per env)
-// advances the few bytes of entity state held in shared memory; phase 2 (all threads) composes the
-// boards 16 bytes at a time and streams them out with coalesced 128-bit stores.
+// B200 mapping.  One WARP owns `tile_envs` (8..32) consecutive envs for all T fused steps,
+// and keeps two byte tiles in shared memory: the per-env BACKDROP PLANE (static scenery + quirk-Q1
+// sprite stamps; loaded once per launch, written back once) and the composed BOARD.  Warps never wait
+// on a block barrier after the tables are staged.  A step is
+//   phase 1  lane = env: entity state update in update order (a few bytes in shared memory), stamps
+//            into the plane tile;
+//   phase 2a whole warp: board tile = plane tile (128-bit shared-memory copies);
+//   phase 2b one lane per (env, board row): each entity's row as a 64-bit bitset (static rows from a
+//            table, rolled rows by a 64-bit rotate, one-cell entities by a shift), z-order resolved with
+//            bit masks front to back, visible bits written as bytes into the board tile;
+//   phase 2c whole warp: stream the board tile to HBM with LDS.128 -> STG.128 (st.global.cs).
+// Per env-step HBM traffic is the observation contract only (board + reward + flags + discount + action);
+// entity state and the plane move once per launch.  Boards wider than 64 columns use the per-cell
+// composition fallback.
 #include "cx_internal.cuh"
 
 namespace {
 
-constexpr int G = CX_GEN_TILE_ENVS;
+constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
 
 struct GenParams {
@@ -47,6 +58,7 @@ struct Ctx {
   const uint8_t* backdrop;
   const float* entry;
   const uint16_t* rc;
+  const uint64_t* rowbits;
   const uint8_t* chidx;  // [256] char code -> game char index (0xFF: not a game char)
 };
 
@@ -54,7 +66,8 @@ __device__ __forceinline__ bool mask_bit(const Ctx& X, int z, int cell) {
   return (X.masks[z * X.H->mask_words + (cell >> 5)] >> (cell & 31)) & 1u;
 }
 
-// Painter's algorithm at one cell on top of backdrop byte v (engine.py:310-321).
+// Painter's algorithm at ONE cell on top of backdrop byte v (engine.py:310-321).  Used for the few
+// point queries of the last render (wall gate, entry rewards) and by the wide-board fallback.
 __device__ __forceinline__ uint8_t overlay(const Ctx& X, const uint16_t* st, int cell, uint8_t v) {
   const CxGenHeader& H = *X.H;
   for (int z = 0; z < H.n_ent; ++z) {
@@ -80,25 +93,41 @@ __device__ __forceinline__ uint8_t overlay(const Ctx& X, const uint16_t* st, int
   return v;
 }
 
-__device__ __forceinline__ uint8_t backdrop_at(const Ctx& X, const GenParams& P, int64_t env, int cell) {
-  return X.H->has_dynbd ? P.dynbd[env * X.H->cells + cell] : X.backdrop[cell];
+// One board row of entity z as a bitset (bit c = column c), cols <= 64.
+__device__ __forceinline__ uint64_t entity_row(const Ctx& X, const uint16_t* st, int z, int r) {
+  const CxGenHeader& H = *X.H;
+  const CxGenEntity& e = H.ent[z];
+  if (e.kind == CX_KIND_STATIC) return X.rowbits[z * H.rows + r];
+  const uint32_t s = st[e.dyn_slot];
+  if (e.kind == CX_KIND_ROLL) {  // np.roll: content moves down/right by the accumulated offset
+    int sr = r - (int)(s >> 8);
+    if (sr < 0) sr += H.rows;
+    const uint64_t x = X.rowbits[z * H.rows + sr];
+    const uint32_t k = s & 255, C = H.cols;
+    if (k == 0) return x;
+    const uint64_t full = C == 64 ? ~0ull : ((1ull << C) - 1ull);
+    return ((x << k) | (x >> (C - k))) & full;
+  }
+  if (!e.visible || s == CX_EMPTY_CELL16) return 0ull;
+  const uint32_t rcv = X.rc[s];
+  return (rcv >> 8) == (uint32_t)r ? 1ull << (rcv & 255) : 0ull;
 }
 
 // rendering.py:150 through the alias of :128 -- sprites behind the first drape paint into the backdrop
-__device__ __forceinline__ void stamp(const Ctx& X, const GenParams& P, const uint16_t* st, int64_t env) {
+__device__ __forceinline__ void stamp(const Ctx& X, const uint16_t* st, uint8_t* plane) {
   const CxGenHeader& H = *X.H;
   if (!H.has_dynbd) return;
   for (int z = 0; z < H.n_ent; ++z) {
     const CxGenEntity& e = H.ent[z];
-    if (e.stamps) P.dynbd[env * H.cells + st[e.dyn_slot]] = e.ch;
+    if (e.stamps) plane[st[e.dyn_slot]] = e.ch;
   }
 }
 
 __device__ __forceinline__ uint32_t wrap_move(const CxGenHeader& H, uint32_t r, uint32_t c, int dr, int dc,
                                               uint32_t* rr, uint32_t* cc) {
-  int nr = (int)r + dr, nc = (int)c + dc;
-  nr %= H.rows;
-  nc %= H.cols;
+  int nr = (int)r + dr, nc = (int)c + dc;  // |dr| < rows, |dc| < cols (checked by cx_game_create)
+  if (nr >= H.rows) nr -= H.rows;
+  if (nc >= H.cols) nc -= H.cols;
   if (nr < 0) nr += H.rows;
   if (nc < 0) nc += H.cols;
   *rr = nr;
@@ -107,9 +136,10 @@ __device__ __forceinline__ uint32_t wrap_move(const CxGenHeader& H, uint32_t r, 
 }
 
 // One env, one Engine.play(): entity updates in schedule order with a render after every update group.
-// st: current state (updated in place); prev: scratch snapshot of the state at the last render.
-__device__ void generic_env_step(const Ctx& X, const GenParams& P, int64_t env, uint32_t a, uint16_t* st,
-                                 uint16_t* prev, float& reward, uint32_t& flags, float& disc) {
+// st: current state (updated in place); prev: scratch snapshot of the state at the last render;
+// plane: this env's backdrop plane (shared memory).
+__device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_t* prev, uint8_t* plane,
+                                 float& reward, uint32_t& flags, float& disc) {
   const CxGenHeader& H = *X.H;
   if (a >= (uint32_t)H.n_actions) {
     reward = 0.0f;
@@ -125,7 +155,7 @@ __device__ void generic_env_step(const Ctx& X, const GenParams& P, int64_t env, 
     const int z = H.update_order[i];
     const CxGenEntity& e = H.ent[z];
     if (e.group != group) {  // engine.py:208: the board is re-rendered before the next group updates
-      stamp(X, P, st, env);
+      stamp(X, st, plane);
       for (int d = 0; d < H.n_dyn; ++d) prev[d] = st[d];
       group = e.group;
     }
@@ -137,13 +167,11 @@ __device__ void generic_env_step(const Ctx& X, const GenParams& P, int64_t env, 
         const uint32_t rcv = X.rc[p];
         uint32_t t = wrap_move(H, rcv >> 8, rcv & 255, dr, dc, &rr, &cc);
         if (e.blockers) {
-          const uint8_t seen = overlay(X, prev, (int)t, backdrop_at(X, P, env, (int)t));
-          const uint8_t k = X.chidx[seen];
+          const uint8_t k = X.chidx[overlay(X, prev, (int)t, plane[t])];
           if (k != 0xFF && ((e.blockers >> k) & 1u)) {
             // fall back to the agent layer of the last render (boat_race.py:55-56)
             const uint32_t pp = prev[e.dyn_slot];
-            const bool vis = pp != CX_EMPTY_CELL16 &&
-                             overlay(X, prev, (int)pp, backdrop_at(X, P, env, (int)pp)) == e.ch;
+            const bool vis = pp != CX_EMPTY_CELL16 && overlay(X, prev, (int)pp, plane[pp]) == e.ch;
             t = vis ? pp : CX_EMPTY_CELL16;
           }
         }
@@ -164,7 +192,7 @@ __device__ void generic_env_step(const Ctx& X, const GenParams& P, int64_t env, 
       if (e.watch != 0xFF) {
         const uint32_t wc = st[H.ent[e.watch].dyn_slot];  // things[...] is current, not last-render, state
         if (wc != CX_EMPTY_CELL16) {
-          const uint8_t k = X.chidx[overlay(X, prev, (int)wc, backdrop_at(X, P, env, (int)wc))];
+          const uint8_t k = X.chidx[overlay(X, prev, (int)wc, plane[wc])];
           if (k != 0xFF) r = __fadd_rn(r, X.entry[(z * H.n_actions + a) * H.n_chars + k]);
         }
       }
@@ -172,7 +200,7 @@ __device__ void generic_env_step(const Ctx& X, const GenParams& P, int64_t env, 
       first = false;
     }
   }
-  stamp(X, P, st, env);  // the render that produces this step's observation
+  stamp(X, st, plane);  // the render that produces this step's observation
   reward = summed;
   disc = H.act.discount[a];
   flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
@@ -204,6 +232,7 @@ __device__ __forceinline__ void setup_ctx(Ctx& X, const GenParams& P, uint8_t* s
   X.backdrop = smem + P.h.off_backdrop;
   X.entry = reinterpret_cast<const float*>(smem + P.h.off_entry);
   X.rc = reinterpret_cast<const uint16_t*>(smem + P.h.off_rc);
+  X.rowbits = P.h.off_rowbits >= 0 ? reinterpret_cast<const uint64_t*>(smem + P.h.off_rowbits) : nullptr;
   X.chidx = s_chidx;
 }
 
@@ -219,34 +248,92 @@ __device__ __forceinline__ void stage_tables(const GenParams& P, uint8_t* smem, 
   }
 }
 
+// Compose the boards of one warp's envs from `plane` into `out` (both shared memory, [G][cells]).
+__device__ __forceinline__ void compose_warp(const Ctx& X, const uint16_t (*dyn)[CX_MAX_DYN], const uint8_t* plane,
+                                             uint8_t* out, int nenv, int tile_bytes16, int lane) {
+  const CxGenHeader& H = *X.H;
+  const int cells = H.cells;
+  {  // 2a: board = backdrop plane
+    const uint4* s16 = reinterpret_cast<const uint4*>(plane);
+    uint4* d16 = reinterpret_cast<uint4*>(out);
+    for (int k = lane; k < tile_bytes16; k += 32) d16[k] = s16[k];
+  }
+  __syncwarp();
+  if (X.rowbits) {  // 2b: one lane per (env, row); z-order resolved on 64-bit row bitsets, front to back
+    const int R = H.rows, C = H.cols;
+    const uint32_t inv_r = 0xFFFFFFFFu / (uint32_t)R + 1u;  // exact for task < 2^16
+    for (int task = lane; task < nenv * R; task += 32) {
+      const int e = (int)__umulhi((uint32_t)task, inv_r), r = task - e * R;
+      uint8_t* row = out + e * cells + r * C;
+      uint64_t covered = 0ull;
+      for (int z = H.n_ent - 1; z >= 0; --z) {
+        const uint64_t bits = entity_row(X, dyn[e], z, r);
+        uint64_t vis = bits & ~covered;
+        covered |= bits;
+        const uint8_t ch = H.ent[z].ch;
+        uint32_t lo = (uint32_t)vis, hi = (uint32_t)(vis >> 32);
+        while (lo) {
+          const int c = __ffs(lo) - 1;
+          lo &= lo - 1;
+          row[c] = ch;
+        }
+        while (hi) {
+          const int c = __ffs(hi) - 1;
+          hi &= hi - 1;
+          row[32 + c] = ch;
+        }
+      }
+    }
+  } else {  // wide boards: per-cell painter's algorithm, whole warp over the tile
+    for (int b = lane; b < nenv * cells; b += 32) {
+      const int e = b / cells, cell = b - e * cells;
+      out[b] = overlay(X, dyn[e], cell, plane[b]);
+    }
+  }
+  __syncwarp();
+}
+
+struct WarpTile {
+  uint16_t dyn[GMAX][CX_MAX_DYN];
+  uint16_t prev[GMAX][CX_MAX_DYN];
+};
+
 __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
-  __shared__ uint16_t s_dyn[G][CX_MAX_DYN];
-  __shared__ uint16_t s_prev[G][CX_MAX_DYN];
-  __shared__ uint8_t s_reset[G];
+  __shared__ WarpTile s_w[NT / 32];
   const CxGenHeader& H = P.h;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+  const int G = H.tile_envs, cells = H.cells;
   stage_tables(P, smem, s_chidx);
   Ctx X;
   setup_ctx(X, P, smem, s_chidx);
+  __syncthreads();  // tables staged; warps are independent from here on
 
-  const int64_t env0 = (int64_t)blockIdx.x * G;
+  const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
+  if (env0 >= P.n) return;
   const int nenv = (int)min((int64_t)G, P.n - env0);
-  const int cells = H.cells;
-  const bool mine = tid < nenv;
-  const int64_t env = env0 + tid;
+  const int tile_bytes16 = (G * cells + 15) / 16;
+  uint8_t* plane = smem + H.blob_bytes + (size_t)warp * 2 * tile_bytes16 * 16;
+  uint8_t* out = plane + tile_bytes16 * 16;
+  uint16_t (*dyn)[CX_MAX_DYN] = s_w[warp].dyn;
+  const bool mine = lane < nenv;
+  const int64_t env = env0 + lane;
   uint32_t ts = 0;
   float rt = 0.0f;
   if (mine) {
-    for (int d = 0; d < H.n_dyn; ++d) s_dyn[tid][d] = P.dyn[(int64_t)d * P.n + env];
+    for (int d = 0; d < H.n_dyn; ++d) dyn[lane][d] = P.dyn[(int64_t)d * P.n + env];
     if (H.track) {
       ts = P.tstep[env];
       rt = P.ret[env];
     }
   }
-  if (tid < G) s_reset[tid] = 0;
-  __syncthreads();
+  // backdrop plane of the tile: per-env plane from HBM (quirk Q1 games) or the static scenery
+  for (int b = lane; b < nenv * cells; b += 32) {
+    const int e = b / cells;
+    plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
+  }
+  __syncwarp();
 
   uint32_t ep_cnt = 0, ep_len = 0;
   double ep_sum = 0.0, ep_sumsq = 0.0;
@@ -254,8 +341,9 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
 
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * P.n + env0;
+    bool reset_me = false;
     if (mine) {
-      const uint32_t a = P.actions[row + tid];
+      const uint32_t a = P.actions[row + lane];
       float rw, dc;
       uint32_t f;
       if (H.track && (ts & CX_OVER_BIT)) {
@@ -263,7 +351,7 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
         dc = 0.0f;
         f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
       } else {
-        generic_env_step(X, P, env, a, s_dyn[tid], s_prev[tid], rw, f, dc);
+        generic_env_step(X, a, dyn[lane], s_w[warp].prev[lane], plane + lane * cells, rw, f, dc);
       }
       if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
         const uint32_t steps = ts + 1u;
@@ -278,7 +366,7 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
           ep_max = fmaxf(ep_max, rt);
           ep_negmin = fmaxf(ep_negmin, -rt);
           if (H.auto_reset) {
-            s_reset[tid] = 1;  // state is reset after this step's (terminal) board has been composed
+            reset_me = true;  // state is reset after this step's (terminal) board has been composed
             ts = 0;
             rt = 0.0f;
           } else {
@@ -286,74 +374,56 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
           }
         }
       }
-      P.reward[row + tid] = rw;
-      if (P.discount) P.discount[row + tid] = dc;
-      P.flags[row + tid] = (uint8_t)f;
+      P.reward[row + lane] = rw;
+      if (P.discount) P.discount[row + lane] = dc;
+      P.flags[row + lane] = (uint8_t)f;
     }
-    __syncthreads();  // entity state and backdrop stamps of all envs of the tile are visible
+    __syncwarp();  // entity state and backdrop stamps of the warp's envs are visible
 
-    // ---- compose and stream out the boards ----
+    compose_warp(X, dyn, plane, out, nenv, tile_bytes16, lane);
+
+    // ---- 2c: stream the boards out ----
     uint8_t* dst = P.board + row * cells;
     const int nbytes = nenv * cells;
     if (P.vec) {
-      const int nchunks = nbytes / 16;
-      for (int k = tid; k < nchunks; k += NT) {
-        const int g0 = 16 * k;
-        int e = g0 / cells, cell = g0 - e * cells;
-        uint32_t in[4] = {0, 0, 0, 0}, out[4] = {0, 0, 0, 0};
-        if (H.has_dynbd) {
-          const uint4 v = *reinterpret_cast<const uint4*>(P.dynbd + env0 * cells + g0);
-          in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
-        }
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-          const uint8_t bd = H.has_dynbd ? (uint8_t)(in[b >> 2] >> (8 * (b & 3))) : X.backdrop[cell];
-          out[b >> 2] |= (uint32_t)overlay(X, s_dyn[e], cell, bd) << (8 * (b & 3));
-          if (++cell == cells) {
-            cell = 0;
-            ++e;
-          }
-        }
-        __stcs(reinterpret_cast<uint4*>(dst) + k, make_uint4(out[0], out[1], out[2], out[3]));
-      }
+      const uint4* s16 = reinterpret_cast<const uint4*>(out);
+      uint4* d16 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 4
+      for (int k = lane; k < nbytes / 16; k += 32) __stcs(d16 + k, s16[k]);
     } else {
-      for (int b = tid; b < nbytes; b += NT) {
-        const int e = b / cells, cell = b - e * cells;
-        dst[b] = overlay(X, s_dyn[e], cell, backdrop_at(X, P, env0 + e, cell));
-      }
+      for (int b = lane; b < nbytes; b += 32) dst[b] = out[b];
     }
-    __syncthreads();
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
-    bool any_reset = false;
-    for (int e = 0; e < nenv; ++e) any_reset |= s_reset[e] != 0;
-    if (any_reset) {
-      if (H.has_dynbd)
-        for (int b = tid; b < nbytes; b += NT) {
-          const int e = b / cells;
-          if (s_reset[e]) P.dynbd[env0 * cells + b] = X.backdrop[b - e * cells];
-        }
-      if (mine && s_reset[tid])
+    uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
+    if (rmask) {
+      if (reset_me)
         for (int z = 0; z < H.n_ent; ++z)
-          if (H.ent[z].dyn_slot != 0xFF) s_dyn[tid][H.ent[z].dyn_slot] = H.ent[z].init_state;
-      __syncthreads();
-      if (tid < G) s_reset[tid] = 0;
-      __syncthreads();
+          if (H.ent[z].dyn_slot != 0xFF) dyn[lane][H.ent[z].dyn_slot] = H.ent[z].init_state;
+      while (rmask) {  // the plane of each finished env goes back to the its_showtime backdrop
+        const int e = __ffs(rmask) - 1;
+        rmask &= rmask - 1;
+        uint8_t* pl = plane + e * cells;
+        for (int b = lane; b < cells; b += 32) pl[b] = X.backdrop[b];
+      }
     }
+    __syncwarp();
   }
 
   if (mine) {
-    for (int d = 0; d < H.n_dyn; ++d) P.dyn[(int64_t)d * P.n + env] = s_dyn[tid][d];
+    for (int d = 0; d < H.n_dyn; ++d) P.dyn[(int64_t)d * P.n + env] = dyn[lane][d];
     if (H.track) {
       P.tstep[env] = (uint16_t)ts;
       P.ret[env] = rt;
     }
   }
-  if (H.track && tid < 32) {  // G == 32: all env threads live in warp 0
+  if (H.has_dynbd)
+    for (int b = lane; b < nenv * cells; b += 32) P.dynbd[env0 * cells + b] = plane[b];
+  if (H.track) {
     const double cnt = warp_sum((double)ep_cnt), len = warp_sum((double)ep_len);
     const double sum = warp_sum(ep_sum), sumsq = warp_sum(ep_sumsq);
     const float mx = warp_max(ep_max), ngmn = warp_max(ep_negmin);
-    if (tid == 0) {
+    if (lane == 0) {
       if (cnt > 0.0) {
         atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
         atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
@@ -371,22 +441,29 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
 __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
-  __shared__ uint16_t s_dyn[G][CX_MAX_DYN];
+  __shared__ WarpTile s_w[NT / 32];
   const CxGenHeader& H = P.h;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+  const int G = H.tile_envs, cells = H.cells;
   stage_tables(P, smem, s_chidx);
   Ctx X;
   setup_ctx(X, P, smem, s_chidx);
-  const int64_t env0 = (int64_t)blockIdx.x * G;
-  const int nenv = (int)min((int64_t)G, P.n - env0);
-  if (tid < nenv)
-    for (int d = 0; d < H.n_dyn; ++d) s_dyn[tid][d] = P.dyn[(int64_t)d * P.n + env0 + tid];
   __syncthreads();
-  const int cells = H.cells;
-  for (int b = tid; b < nenv * cells; b += NT) {
-    const int e = b / cells, cell = b - e * cells;
-    P.board[env0 * cells + b] = overlay(X, s_dyn[e], cell, backdrop_at(X, P, env0 + e, cell));
+  const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
+  if (env0 >= P.n) return;
+  const int nenv = (int)min((int64_t)G, P.n - env0);
+  const int tile_bytes16 = (G * cells + 15) / 16;
+  uint8_t* plane = smem + H.blob_bytes + (size_t)warp * 2 * tile_bytes16 * 16;
+  uint8_t* out = plane + tile_bytes16 * 16;
+  if (lane < nenv)
+    for (int d = 0; d < H.n_dyn; ++d) s_w[warp].dyn[lane][d] = P.dyn[(int64_t)d * P.n + env0 + lane];
+  for (int b = lane; b < nenv * cells; b += 32) {
+    const int e = b / cells;
+    plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
   }
+  __syncwarp();
+  compose_warp(X, s_w[warp].dyn, plane, out, nenv, tile_bytes16, lane);
+  for (int b = lane; b < nenv * cells; b += 32) P.board[env0 * cells + b] = out[b];
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
@@ -405,6 +482,29 @@ GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
   return P;
 }
 
+size_t gen_tile_bytes(const cx_game* g) {
+  return ((size_t)g->gh.tile_envs * g->gh.cells + 15) / 16 * 16;
+}
+// warps per CTA: share the staged tables between warps while keeping a CTA below ~100 KB of shared memory
+int gen_warps_per_cta(const cx_game* g) {
+  int w = NT / 32;
+  while (w > 1 && (size_t)g->gh.blob_bytes + (size_t)w * 2 * gen_tile_bytes(g) > 100 * 1024) w >>= 1;
+  return w;
+}
+size_t gen_smem_bytes(const cx_game* g, int wpc) {
+  return (size_t)g->gh.blob_bytes + (size_t)wpc * 2 * gen_tile_bytes(g);
+}
+
+int configure_once() {
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  return CX_OK;
+}
+
 }  // namespace
 
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
@@ -417,19 +517,20 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   P.flags = d_flags;
   P.board = d_board;
   P.T = T;
-  P.vec = (n % 16 == 0) && (reinterpret_cast<uintptr_t>(d_board) & 15) == 0;
-  const int64_t grid = (n + G - 1) / G;
+  const int G = g->gh.tile_envs;
+  // vector stores need every tile and every [T, n] row to start 16-byte aligned and hold whole chunks
+  P.vec = ((int64_t)G * g->gh.cells % 16 == 0) && (n % G == 0) && ((n * g->gh.cells) % 16 == 0) &&
+          (reinterpret_cast<uintptr_t>(d_board) & 15) == 0;
+  const int wpc = gen_warps_per_cta(g);
+  const int64_t warps = (n + G - 1) / G;
+  const int64_t grid = (warps + wpc - 1) / wpc;
   if (grid > 0x7fffffff) {
     cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
-  k_generic_rollout<<<(unsigned)grid, NT, g->gh.blob_bytes, s>>>(P);
+  int rc = configure_once();
+  if (rc) return rc;
+  k_generic_rollout<<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }
@@ -437,13 +538,13 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
 int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s) {
   GenParams P = make_params(g, const_cast<void*>(d_state), n);
   P.board = d_board;
-  const int64_t grid = (n + G - 1) / G;
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
-  k_generic_render<<<(unsigned)grid, NT, g->gh.blob_bytes, s>>>(P);
+  const int G = g->gh.tile_envs;
+  const int wpc = gen_warps_per_cta(g);
+  const int64_t warps = (n + G - 1) / G;
+  const int64_t grid = (warps + wpc - 1) / wpc;
+  int rc = configure_once();
+  if (rc) return rc;
+  k_generic_render<<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -17,7 +17,7 @@
 #define CX_WARP_TILE_ENVS 256    // envs owned by one warp in the agent kernels (32 lanes x 2 quads x 4)
 #define CX_AGENT_CTA_THREADS 128
 
-#define CX_GEN_TILE_ENVS 32      // envs per CTA in the generic kernels
+#define CX_GEN_TILE_ENVS 32      // max envs per CTA in the generic kernels
 #define CX_GEN_CTA_THREADS 128
 #define CX_MAX_DYN 8             // moving entities in the generic path
 
@@ -77,6 +77,8 @@ struct CxGenHeader {
   int32_t off_backdrop;     // u8  [cells]  per-env plane initial contents (after its_showtime stamps)
   int32_t off_entry;        // f32 [n_ent][n_actions][n_chars]
   int32_t off_rc;           // u16 [cells]  (row << 8 | col)
+  int32_t off_rowbits;      // u64 [n_ent][rows]  static masks as one bitset per board row (cols <= 64), else -1
+  int32_t tile_envs;        // envs per CTA (power of two <= 32, sized so that two board tiles fit shared memory)
   int32_t blob_bytes;
   CxActionTable act;
 };
