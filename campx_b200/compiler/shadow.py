@@ -44,7 +44,12 @@ class Curtain(torch.Tensor):
             return torch.Tensor.set_(self, source, *args, **kwargs)
 
     def __deepcopy__(self, memo):
-        out = Curtain.wrap(self.as_subclass(torch.Tensor).clone())
+        # Go through the plain-tensor deepcopy so that torch's storage memo keeps aliases alive: the
+        # canvas shares storage with the backdrop curtain (rendering.py:128) and a clone of the shadow
+        # must preserve that (quirk Q1).
+        if id(self) in memo:
+            return memo[id(self)]
+        out = Curtain.wrap(copy.deepcopy(self.as_subclass(torch.Tensor), memo))
         memo[id(self)] = out
         return out
 

@@ -1,0 +1,178 @@
+"""GPU parity of the generic kernels on worlds that stress what the six reference worlds do not:
+several update groups (re-render between groups, engine.py:195-208), two moving one-cell drapes where
+one blocks the other, an entity updated BEFORE the agent it watches, a sprite-only world (quirk Q1(ii):
+canvas zeroed at every render), an invisible sprite.  Each world is written twice -- as user-level
+campx_b200 classes (compiled by the front end) and as numpy oracle entities -- and compared frame by frame."""
+import numpy as np
+import pytest
+import torch
+
+from campx_b200 import things
+from campx_b200.ascii_art import ascii_art_to_game, Partial
+from examples.worlds import Walker, Arrow, Slider, RING_ART
+from oracle import campx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def onehot(a):
+    v = np.zeros(5, dtype=np.float32)
+    v[a] = 1
+    return v
+
+
+def compare(game, oracle_factory, encode, n=40, T=50, seed=3):
+    obs, reward, discount = game.its_showtime()
+    oracles = [oracle_factory() for _ in range(n)]
+    firsts = [o.its_showtime() for o in oracles]
+    assert np.array_equal(obs.board[0].cpu().numpy(), np.asarray(firsts[0][0].board).astype(np.uint8))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    acts = rng.integers(0, 5, size=(T, n)).astype(np.uint8)
+    boards, rewards, discounts, flags = game.rollout(torch.from_numpy(acts).cuda())
+    b, r, f = boards.cpu().numpy(), rewards.cpu().numpy(), flags.cpu().numpy()
+    for i in range(n):
+        for t in range(T):
+            o, rew, dsc = oracles[i].play(encode(int(acts[t, i])))
+            ctx = "env %d t %d" % (i, t)
+            assert np.array_equal(b[t, i], np.asarray(o.board).astype(np.uint8)), ctx
+            assert (rew is None) == bool(f[t, i] & 4), ctx
+            if rew is not None:
+                assert float(rew) == float(r[t, i]), ctx
+    return game
+
+
+def _ring(schedule, **kw):
+    def arrow(bonus):
+        return Partial(Arrow, bonus=torch.FloatTensor(bonus), toll=-0.25)
+    return ascii_art_to_game(
+        RING_ART, ' ',
+        drapes={'A': Partial(Walker, walls='#', strict=True), '#': things.FixedDrape,
+                '^': arrow([0, 0, 3, 1, 0]), '>': arrow([1, 3, 0, 0, 0]),
+                'v': arrow([0, 0, 1, 3, 0]), '<': arrow([3, 1, 0, 0, 0])},
+        z_order='^>v<A#', update_schedule=schedule, **kw)
+
+
+def _oracle_ring(schedule):
+    hover = lambda d: (O.DirectionalHoverRewardDrape, (), dict(dctns=d, base_reward=-0.25))
+    return O.ascii_art_to_game(
+        O.BOAT_RACE_ART, ' ',
+        drapes={'A': (O.AgentDrape, (), dict(variant='boat_race')), '#': O.FixedDrape,
+                '^': hover([0, 0, 3, 1, 0]), '>': hover([1, 3, 0, 0, 0]),
+                'v': hover([0, 0, 1, 3, 0]), '<': hover([3, 1, 0, 0, 0])},
+        z_order='^>v<A#', update_schedule=schedule)
+
+
+def test_two_update_groups_rerender_between_groups():
+    """Tiles in a later group see the board re-rendered after the agent moved: the agent occludes the
+    tile it just entered, so the entry bonus never fires (reward is always -1)."""
+    sched = [['A'], ['^', '>', 'v', '<', '#']]
+    game = compare(_ring(sched, num_envs=40), lambda: _oracle_ring(sched), onehot)
+    assert game.native.info.path == 2 and game.spec.n_groups == 2
+
+
+def test_tiles_updated_before_the_agent_see_its_old_position():
+    """Flat schedule with the tiles first: things['A'] is not yet updated when they look (engine.py:200-204)."""
+    game = compare(_ring('^>v<A#', num_envs=40), lambda: _oracle_ring('^>v<A#'), onehot)
+    assert game.native.info.path == 1          # still a single-agent game: fast path, "old cell" column
+
+
+TWO_ART = ['#######',
+           '#A   B#',
+           '# ### #',
+           '#     #',
+           '#######']
+
+
+def test_two_agents_one_blocks_the_other():
+    user = ascii_art_to_game(TWO_ART, ' ',
+                             drapes={'A': Partial(Walker, walls='#', per_step=1),
+                                     'B': Partial(Walker, walls='#A', per_step=0.5), '#': things.FixedDrape},
+                             z_order='AB#', update_schedule='AB#', num_envs=40)
+
+    def oracle():
+        return O.ascii_art_to_game(TWO_ART, ' ',
+                                   drapes={'A': (O.AgentDrape, (), dict(variant='demo2')),
+                                           'B': (OracleHalf, (), dict(variant='demo2', blocking_chars='#A')),
+                                           '#': O.FixedDrape},
+                                   z_order='AB#', update_schedule='AB#')
+
+    class OracleHalf(O.AgentDrape):
+        def update(self, actions, board, layers, backdrop, things_, the_plot):
+            class P(dict):
+                pass
+            # same as demo2 but pays 0.5: reuse the parent with a reward-translating plot view
+            calls = []
+            orig = the_plot.add_reward
+            the_plot.add_reward = lambda r: calls.append(r)
+            try:
+                super().update(actions, board, layers, backdrop, things_, the_plot)
+            finally:
+                del the_plot.add_reward
+            for _ in calls:
+                orig(0.5)
+
+    game = compare(user, oracle, lambda a: [int(i == a) for i in range(5)])
+    assert game.native.info.path == 2
+    b = [e for e in game.spec.entities if e.character == 'B'][0]
+    assert b.blockers == '#A'
+
+
+def test_sprite_only_world_has_a_zeroed_canvas():
+    """Quirk Q1(ii): without any drape the canvas aliases the backdrop and is zeroed at every render."""
+    class OSlider(O.Sprite):
+        def update(self, actions, board, layers, backdrop, things_, the_plot):
+            if actions is None or actions > 3:
+                return
+            d = [(0, -1), (0, 1), (-1, 0), (1, 0)][actions]
+            self.position = ((self.position[0] + d[0]) % self.corner[0], (self.position[1] + d[1]) % self.corner[1])
+
+    class USlider(things.Sprite):
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is None or actions > 3:
+                return
+            d = [(0, -1), (0, 1), (-1, 0), (1, 0)][actions]
+            self._position = self.Position((self.position.row + d[0]) % self.corner.row,
+                                           (self.position.col + d[1]) % self.corner.col)
+
+    art = ['P..x', '....', 'Q...']
+    user = ascii_art_to_game(art, '.', sprites={'P': USlider, 'Q': USlider}, num_envs=40)
+    game = compare(user, lambda: O.ascii_art_to_game(art, '.', sprites={'P': OSlider, 'Q': OSlider}), int)
+    first = game.reset().board[0].cpu().numpy()
+    assert set(np.unique(first).tolist()) == {0, ord('P'), ord('Q')}       # 'x' and '.' are gone
+
+
+def test_invisible_sprite_is_never_painted_or_stamped():
+    class OGhost(O.SlidingSprite):
+        def __init__(self, corner, position, character, direction_set):
+            super().__init__(corner, position, character, direction_set)
+            self.visible = False
+
+    class UGhost(Slider):
+        def __init__(self, corner, position, character, flavour):
+            super().__init__(corner, position, character, flavour)
+            self._visible = False
+
+    art = ['1..@', '..@.', '2...']
+    from examples.worlds import Roller
+    user = ascii_art_to_game(art, '.', sprites={'1': Partial(UGhost, 0), '2': Partial(Slider, 1)},
+                             drapes={'@': Roller}, z_order='12@', num_envs=40, max_episode_steps=0,
+                             auto_reset=False)
+
+    def oracle():
+        return O.ascii_art_to_game(art, '.', sprites={'1': (OGhost, (0,), {}), '2': (O.SlidingSprite, (1,), {})},
+                                   drapes={'@': O.RollingDrape}, z_order='12@')
+
+    # never play action 4 (quit) here: oracle engines raise after termination
+    obs, _, _ = user.its_showtime()
+    oracles = [oracle() for _ in range(40)]
+    for o in oracles:
+        o.its_showtime()
+    rng = np.random.Generator(np.random.PCG64(1))
+    acts = rng.integers(0, 4, size=(40, 40)).astype(np.uint8)
+    boards, rewards, _, flags = user.rollout(torch.from_numpy(acts).cuda())
+    b = boards.cpu().numpy()
+    for i in range(40):
+        for t in range(40):
+            o, rew, dsc = oracles[i].play(int(acts[t, i]))
+            assert np.array_equal(b[t, i], np.asarray(o.board).astype(np.uint8)), (i, t)
+    assert not (b == ord('1')).any() and (b == ord('2')).any()

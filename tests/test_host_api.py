@@ -155,3 +155,28 @@ def test_shadow_matches_golden_boat_race(golden_dir):
                 if r is not None:
                     assert float(r) == want["reward"]
                 assert float(d) == want["discount"]
+
+
+def test_shadow_clone_keeps_canvas_backdrop_aliasing(golden_dir):
+    """Quirk Q1(ii) on the compile-time shadow and on its clones: in a sprite-only world the canvas
+    aliases the backdrop storage (rendering.py:128) and clear() zeroes it (rendering.py:111)."""
+    import json
+    import os
+    with open(os.path.join(golden_dir, "engine_semantics.json")) as f:
+        want = json.load(f)["cases"]["sprite_only_world_boards"]
+
+    class Still(things.Sprite):
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is None:
+                return
+            self._position = self.Position(self._position.row, (self._position.col + 1) % self.corner.col)
+
+    g = ascii_art_to_game(["P..", "..."], ".", sprites={"P": Still}, action_format="index")
+    spec = g.compile()
+    assert spec.backdrop.reshape(-1).tolist() == want[0]          # zeros + the sprite, as after its_showtime
+    sh = g._shadow.clone().clone()
+    boards = []
+    for _ in range(2):
+        sh.play(0)
+        boards.append(sh.board.reshape(-1).tolist())
+    assert boards == want[1:]
