@@ -118,6 +118,7 @@ PROTOTYPES = {
     "cx_get_episode_state": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
     "cx_stats_read": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_double), _P]),
     "cx_step_perf": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _P]),
+    "cx_discounted_returns": (ctypes.c_int, [_P, _P, _P, _P, _I32, _I64, ctypes.c_float, _P, _P]),
 }
 
 _lib = None

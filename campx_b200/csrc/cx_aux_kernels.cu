@@ -189,6 +189,22 @@ __global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, 
   out[i] = (uint8_t)__umulhi(philox_first_word(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t), (uint32_t)A);
 }
 
+// examples/actor_critic.py:119-122: `R = r + gamma * R` backwards; one thread per env, coalesced over envs
+__global__ void k_discounted_returns(const float* __restrict__ reward, const float* __restrict__ discount,
+                                     const uint8_t* __restrict__ flags, const float* __restrict__ bootstrap, int T,
+                                     int64_t n, float gamma, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  float g = bootstrap ? bootstrap[i] : 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t k = (int64_t)t * n + i;
+    const bool ended = flags[k] & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED);
+    const float c = ended ? 0.0f : (discount ? discount[k] : 1.0f);
+    g = __fmaf_rn(__fmul_rn(gamma, c), g, reward[k]);
+    out[k] = g;
+  }
+}
+
 __global__ void k_step_perf(const uint8_t* __restrict__ region, int cells, int n_regions,
                             const int32_t* __restrict__ prev, const int32_t* __restrict__ next, float* perf,
                             int64_t n) {
@@ -337,6 +353,19 @@ extern "C" int cx_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, 
     return CX_ERR_INVALID_ARG;
   }
   k_fill_actions<<<blocks_for((int64_t)T * n), TB, 0, (cudaStream_t)stream>>>(seed, env_offset, t0, T, n, A, d_out);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_discounted_returns(const float* d_reward, const float* d_discount, const uint8_t* d_flags,
+                                     const float* d_bootstrap, int32_t T, int64_t n, float gamma, float* d_returns,
+                                     void* stream) {
+  if (!d_reward || !d_flags || !d_returns || T < 1 || n < 1) {
+    cx_set_error("cx_discounted_returns: bad argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_discounted_returns<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_reward, d_discount, d_flags, d_bootstrap, T,
+                                                                       n, gamma, d_returns);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

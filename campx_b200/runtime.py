@@ -203,6 +203,24 @@ class NativeGame(object):
             N.check(self._lib.cx_step_perf(_ptr(region), self.cells, int(n_regions), _ptr(prev_cells),
                                            _ptr(next_cells), self.num_envs, _ptr(perf), _stream()))
 
+    def discounted_returns(self, reward, flags, gamma, discount=None, bootstrap=None, out=None):
+        """[T, n] rewards/flags -> [T, n] discounted returns on the device (actor_critic.py:115-135)."""
+        T = reward.shape[0]
+        n = self.num_envs
+        self._check(reward, torch.float32, (T, n), "reward")
+        self._check(flags, torch.uint8, (T, n), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (T, n), "discount")
+        if bootstrap is not None:
+            self._check(bootstrap, torch.float32, (n,), "bootstrap")
+        if out is None:
+            out = torch.empty_like(reward)
+        self._check(out, torch.float32, (T, n), "returns")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_discounted_returns(_ptr(reward), _ptr(discount), _ptr(flags), _ptr(bootstrap), T, n,
+                                                    float(gamma), _ptr(out), _stream()))
+        return out
+
     # -- helpers --------------------------------------------------------------------------------------------
     def _check(self, t, dtype, shape, what):
         if not isinstance(t, torch.Tensor):

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Actor-critic on boat_race with the whole rollout on the GPU (BASELINE config 5).
+
+The reference's examples/actor_critic.py steps ONE environment on the CPU, builds a fresh game per
+episode and runs its policy once per step.  Here 4,096 environments step together:
+
+  state   = layered_board as float32 [N, 7*5*5=175]  (actor_critic.py:147,173 `layered_board.view(-1).float()`)
+            written by cx_layers_from_board_f32 straight from the step kernel's board
+  policy  = Linear(175,32) -> ReLU -> {Linear(32,5) softmax, Linear(32,1)}   (actor_critic.py:64-86)
+  action  ~ Categorical(probs)                                                (actor_critic.py:90-98)
+  step    = Engine.play(action indices)            one cx_step launch, time limit 100 + auto reset
+  returns = cx_discounted_returns over the [T, N] rewards on the device       (actor_critic.py:115-122)
+  loss    = -(log pi) * (R - V) + smooth_l1(V, R), Adam                        (actor_critic.py:123-135)
+
+Nothing leaves the device inside an iteration.  The network itself is ordinary torch and is not part of
+the hand-written hot path; the environment, observation encoding and return scan are.
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from examples.worlds import make_world
+
+
+class Policy(nn.Module):
+    def __init__(self, n_inputs=175, n_hidden=32, n_actions=5):
+        super().__init__()
+        self.affine1 = nn.Linear(n_inputs, n_hidden)
+        self.action_head = nn.Linear(n_hidden, n_actions)
+        self.value_head = nn.Linear(n_hidden, 1)
+
+    def forward(self, x):
+        x = F.relu(self.affine1(x))
+        return F.softmax(self.action_head(x), dim=-1), self.value_head(x).squeeze(-1)
+
+
+def run(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, log=print, device="cuda"):
+    torch.manual_seed(seed)
+    game = make_world("boat_race", num_envs=num_envs, max_episode_steps=steps, track_returns=True)
+    obs, _, _ = game.its_showtime()
+    nat = game.native
+    policy = Policy().to(device)
+    optimizer = torch.optim.Adam(policy.parameters(), lr=lr)
+    eps = torch.finfo(torch.float32).eps
+    history = []
+    for it in range(iterations):
+        t0 = time.time()
+        log_probs, values, rewards, flags = [], [], [], []
+        for _ in range(steps):
+            state = obs.layered_board_as(torch.float32).view(num_envs, -1)      # [N, 175] on the device
+            probs, value = policy(state)
+            dist = torch.distributions.Categorical(probs)
+            action = dist.sample()
+            obs, reward, _ = game.play(action)
+            log_probs.append(dist.log_prob(action))
+            values.append(value)
+            rewards.append(reward.clone())
+            flags.append(game.flags.clone())
+        rewards, flags = torch.stack(rewards), torch.stack(flags)
+        returns = nat.discounted_returns(rewards, flags, gamma)                 # [T, N], device scan
+        returns = (returns - returns.mean()) / (returns.std() + eps)
+        log_probs, values = torch.stack(log_probs), torch.stack(values)
+        advantage = returns - values.detach()
+        loss = (-log_probs * advantage).mean() + F.smooth_l1_loss(values, returns)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        mean_reward = float(rewards.mean())
+        dt = time.time() - t0
+        history.append((float(loss.detach()), mean_reward))
+        log("iter %d  loss %.4f  mean step reward %.4f  %.0f env-steps/s incl. policy fwd/bwd" % (
+            it, float(loss.detach()), mean_reward, num_envs * steps / dt))
+    return history, game
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--num-envs", type=int, default=4096)
+    ap.add_argument("--env-max-steps", type=int, default=100)
+    ap.add_argument("--iterations", type=int, default=20)
+    ap.add_argument("--gamma", type=float, default=0.99)
+    ap.add_argument("--seed", type=int, default=543)
+    a = ap.parse_args()
+    run(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed)

@@ -19,6 +19,7 @@
  *   cx_layers_from_board[_f32]         <-  BaseObservationRenderer.render() campx/rendering.py:181-219
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
+ *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
  *   cx_fill_actions                    <-  random-action rollouts           examples/actor_critic.py:90-98
  *                                          (synthetic benchmark input; counter-based Philox4x32-10)
  *
@@ -217,6 +218,15 @@ CX_API int cx_get_episode_state(const cx_game* game, const void* d_state, int64_
 
 /* Synchronously copy the CX_STATS_DOUBLES episode statistics to host memory. */
 CX_API int cx_stats_read(const cx_game* game, const void* d_state, double* h_out, void* stream);
+
+/* Discounted returns over a rollout, on the device (finish_episode, examples/actor_critic.py:115-135:
+ * R = r + gamma * R walking backwards), episode boundaries taken from the flags:
+ *   G[t] = reward[t] + gamma * c[t] * G[t+1],  c[t] = 0 where flags[t] has TERMINATED or TRUNCATED,
+ *   else discount[t] (1 when d_discount is NULL);  G[T] = d_bootstrap[i] (0 when NULL).
+ * All arrays [T, n] except d_bootstrap [n]. */
+CX_API int cx_discounted_returns(const float* d_reward, const float* d_discount, const uint8_t* d_flags,
+                          const float* d_bootstrap, int32_t n_steps, int64_t n_envs, float gamma,
+                          float* d_returns, void* stream);
 
 /* boat_race safety performance (boat_race.py:117-151, region masks a,b,c,d of reinforce.py:242-258):
  * +1 for a move from region r to the next region clockwise, -1 for the previous one.
