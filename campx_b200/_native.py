@@ -35,7 +35,7 @@ STAT_NAMES = ("episodes", "return_sum", "return_sumsq", "length_sum", "return_ma
 CX_PATH_AGENT, CX_PATH_GENERIC = 1, 2
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libcampx_b200.so")
+LIB_PATH = os.environ.get("CAMPX_B200_LIB") or os.path.join(LIB_DIR, "libcampx_b200.so")   # env: development knob
 
 
 class NativeLibraryError(RuntimeError):
@@ -109,6 +109,7 @@ PROTOTYPES = {
     "cx_render": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_step": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "cx_rollout": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "cx_rollout_synth": (ctypes.c_int, [_P, _P, _I64, _I32, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P]),
     "cx_layers_from_board": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_layers_from_board_f32": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_onehot_to_index": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _P]),

@@ -22,6 +22,17 @@
 //   * warps only __syncwarp(); CTAs of 4 warps exist just to share the staged tables, so 1024 CTAs cover
 //     2^20 envs in one resident wave on 148 SMs (7 CTAs/SM, 25.6 KB of tile per CTA).
 #include "cx_internal.cuh"
+#include "cx_philox.cuh"
+
+#ifndef CX_OPT_NOBRANCH_POKE
+#define CX_OPT_NOBRANCH_POKE 0
+#endif
+#ifndef CX_OPT_SPLITCOPY
+#define CX_OPT_SPLITCOPY 0
+#endif
+#ifndef CX_OPT_MINBLOCKS
+#define CX_OPT_MINBLOCKS 7
+#endif
 
 namespace {
 
@@ -39,6 +50,8 @@ struct AgentParams {
   uint8_t* board;          // [T, n, cells]
   int64_t n;
   int32_t T;
+  uint64_t seed, env_offset, t0;  // SYNTH: actions come from cx_philox.cuh instead of `actions`
+  uint8_t* actions_out;           // SYNTH: [T, n] or null
 };
 
 constexpr int WT = CX_WARP_TILE_ENVS;       // envs per warp
@@ -119,8 +132,8 @@ struct LaneStats {
   }
 };
 
-template <bool TRACK, bool VEC>
-__global__ void __launch_bounds__(CX_AGENT_CTA_THREADS, 7)  // 7 CTAs/SM: 1024 CTAs (2^20 envs) in one wave
+template <bool TRACK, bool VEC, bool SYNTH>
+__global__ void __launch_bounds__(CX_AGENT_CTA_THREADS, CX_OPT_MINBLOCKS)  // 7 CTAs/SM: 1024 CTAs (2^20 envs) in one wave
 k_agent_rollout(const __grid_constant__ AgentParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CxAgentHeader& H = P.h;
@@ -197,16 +210,43 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   LaneStats& stats = reinterpret_cast<LaneStats*>(smem + H.blob_bytes + (size_t)WARPS * (WT * cells))[tid];
   if (TRACK) stats.clear();
 
+  // Action reads are 3% of the bytes but, interleaved with the write streams at the DRAM, cost ~10% of
+  // the bandwidth (scripts/stream_probe.cu).  Pull them into L2 ahead of time, 16 rows per request
+  // batch (lane l fetches 128-byte half (l & 1) of row t0 + l/2), marked evict_last so that the
+  // streaming stores do not push them out before they are consumed.
+  auto prefetch_actions = [&](int t0) {
+    if (VEC && !SYNTH) {
+      const int tr = t0 + (lane >> 1);
+      if (tr < P.T) {
+        const uint8_t* a = P.actions + (int64_t)tr * n + env0 + (lane & 1) * 128;
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+      }
+    }
+  };
+  prefetch_actions(0);
+  prefetch_actions(16);
+
+  // the quad of envs a lane owns: actions are read from HBM, or generated (same Philox stream as
+  // cx_fill_actions: counter = (global env >> 2, step))
+  auto quad_actions = [&](int j, int t) -> uint32_t {
+    const int el = j * 128 + lane * 4;
+    if (!(VEC || el < nenv)) return 0u;
+    if (SYNTH) {
+      const uint32_t a4 = cx_synth_actions_quad(P.seed, (P.env_offset + (uint64_t)(env0 + el)) >> 2,
+                                                P.t0 + (uint64_t)t, n_actions);
+      if (P.actions_out) st_u8x4<VEC>(P.actions_out, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, a4);
+      return a4;
+    }
+    return ld_u8x4<VEC>(P.actions, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, 0);
+  };
   uint32_t actq[QUADS];
 #pragma unroll
-  for (int j = 0; j < QUADS; ++j) {
-    const int el = j * 128 + lane * 4;
-    actq[j] = (VEC || el < nenv) ? ld_u8x4<VEC>(P.actions, env0 + el, n, 0) : 0u;
-  }
+  for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, 0);
 
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * n + env0;  // index of this warp's first env in [T, n] arrays
     const int64_t row_end = (int64_t)(t + 1) * n;
+    if ((t & 15) == 0) prefetch_actions(t + 32);
 #pragma unroll
     for (int j = 0; j < QUADS; ++j) {
       const int el = j * 128 + lane * 4;
@@ -257,36 +297,54 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           // re-compose this env's board: base character back where the agent was drawn, agent character
           // where it is visible now (painter's algorithm collapsed to two byte stores)
           const uint32_t was = drawn[j][i];
+#if CX_OPT_NOBRANCH_POKE
+          {
+            uint8_t* b = qtile + i * cells;
+            if (was != none) b[was] = s_basech[was];
+            if (show != none) b[show] = (uint8_t)agent_char;
+            drawn[j][i] = show;
+          }
+#else
           if (was != show) {
             uint8_t* b = qtile + i * cells;
             if (was != none) b[was] = s_basech[was];
             if (show != none) b[show] = (uint8_t)agent_char;
             drawn[j][i] = show;
           }
+#endif
         }
         st_f32x4<VEC>(P.reward, row + el, row_end, rw);
         if (want_discount) st_f32x4<VEC>(P.discount, row + el, row_end, dc);
         st_u8x4<VEC>(P.flags, row + el, row_end, fl);
       }
+#if CX_OPT_SPLITCOPY
+      if (VEC) {  // stream this quad's 128 boards now; the next quad's compute overlaps the store burst
+        __syncwarp();
+        const uint4* t16 = reinterpret_cast<const uint4*>(tile + j * 128 * cells);
+        uint4* d16 = reinterpret_cast<uint4*>(P.board + (row + j * 128) * cells);
+        const int nchunks = 128 * cells / 16;
+#pragma unroll 4
+        for (int k = lane; k < nchunks; k += 32) __stcs(d16 + k, t16[k]);
+      }
+#endif
     }
     // next step's actions: issue the loads before streaming the tile so their latency is hidden
     if (t + 1 < P.T) {
 #pragma unroll
-      for (int j = 0; j < QUADS; ++j) {
-        const int el = j * 128 + lane * 4;
-        if (VEC || el < nenv) actq[j] = ld_u8x4<VEC>(P.actions, row + n + el, row_end + n, 0);
-      }
+      for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, t + 1);
     }
     __syncwarp();
     // ---- stream the finished boards of this warp's envs to HBM ----
     {
       uint8_t* dst = P.board + row * cells;
       if (VEC) {
+#if !CX_OPT_SPLITCOPY
         const uint4* t16 = reinterpret_cast<const uint4*>(tile);
         uint4* d16 = reinterpret_cast<uint4*>(dst);
         const int nchunks = WT * cells / 16;
 #pragma unroll 4
         for (int k = lane; k < nchunks; k += 32) __stcs(d16 + k, t16[k]);
+#endif
       } else {
         const int nbytes = nenv * cells;
         for (int k = lane; k < nbytes; k += 32) dst[k] = tile[k];
@@ -340,24 +398,30 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   }
 }
 
-template <bool TRACK, bool VEC>
+template <bool TRACK, bool VEC, bool SYNTH>
 int launch(const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
   static bool configured = false;  // raise the dynamic shared memory cap once (it reserves nothing)
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<TRACK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<TRACK, VEC, SYNTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
     configured = true;
   }
-  k_agent_rollout<TRACK, VEC><<<grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
+  k_agent_rollout<TRACK, VEC, SYNTH><<<grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
+}
+
+template <bool SYNTH>
+int launch_tv(bool track, bool vec, const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  if (track) return vec ? launch<true, true, SYNTH>(P, grid, smem, s) : launch<true, false, SYNTH>(P, grid, smem, s);
+  return vec ? launch<false, true, SYNTH>(P, grid, smem, s) : launch<false, false, SYNTH>(P, grid, smem, s);
 }
 
 }  // namespace
 
 int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                            float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                            cudaStream_t s) {
+                            const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                            uint8_t* d_board, cudaStream_t s) {
   const CxStateLayout L = cx_layout(g, n);
   uint8_t* base = static_cast<uint8_t*>(d_state);
   AgentParams P;
@@ -374,9 +438,13 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   P.board = d_board;
   P.n = n;
   P.T = T;
+  P.seed = synth.seed;
+  P.env_offset = synth.env_offset;
+  P.t0 = synth.t0;
+  P.actions_out = synth.actions_out;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   // vector path: every warp owns a full tile of 256 envs and every [T, n] row starts 16-byte aligned
-  const bool vec = (n % WT == 0) && al16(d_actions) && al16(d_reward) && al16(d_discount) && al16(d_flags) &&
+  const bool vec = (n % WT == 0) && al16(d_actions) && al16(synth.actions_out) && al16(d_reward) && al16(d_discount) && al16(d_flags) &&
                    al16(d_board);
 
   const size_t smem = (size_t)g->ah.blob_bytes + (size_t)WARPS * WT * g->ah.cells +
@@ -387,7 +455,6 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
     cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  if (g->ah.track)
-    return vec ? launch<true, true>(P, (unsigned)grid, smem, s) : launch<true, false>(P, (unsigned)grid, smem, s);
-  return vec ? launch<false, true>(P, (unsigned)grid, smem, s) : launch<false, false>(P, (unsigned)grid, smem, s);
+  return synth.on ? launch_tv<true>(g->ah.track != 0, vec, P, (unsigned)grid, smem, s)
+                  : launch_tv<false>(g->ah.track != 0, vec, P, (unsigned)grid, smem, s);
 }

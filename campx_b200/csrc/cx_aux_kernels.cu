@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "cx_internal.cuh"
+#include "cx_philox.cuh"
 
 int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
 
@@ -164,29 +165,12 @@ __global__ void k_onehot_to_index(const float* __restrict__ onehot, int A, uint8
   if ((ones != 1 || others != 0) && bad) atomicAdd(bad, 1);
 }
 
-// Philox4x32-10 (Salmon et al., SC'11), key = seed, counter = (env_lo, env_hi, t_lo, t_hi).
-__device__ __forceinline__ uint32_t philox_first_word(uint64_t seed, uint64_t env, uint64_t t) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32), c2 = (uint32_t)t, c3 = (uint32_t)(t >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    c0 = hi1 ^ c1 ^ k0;
-    c1 = lo1;
-    c2 = hi0 ^ c3 ^ k1;
-    c3 = lo0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return c0;
-}
 __global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t T, int64_t n, int32_t A,
                                uint8_t* out) {
   const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (i >= (int64_t)T * n) return;
   const int64_t t = i / n, e = i - t * n;
-  out[i] = (uint8_t)__umulhi(philox_first_word(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t), (uint32_t)A);
+  out[i] = (uint8_t)cx_synth_action(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t, (uint32_t)A);
 }
 
 // examples/actor_critic.py:119-122: `R = r + gamma * R` backwards; one thread per env, coalesced over envs

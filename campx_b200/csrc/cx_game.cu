@@ -617,23 +617,49 @@ extern "C" int cx_render(const cx_game* g, const void* d_state, int64_t n, uint8
   return cx_launch_render(g, d_state, n, d_board, (cudaStream_t)stream);
 }
 
-extern "C" int cx_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                          float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
-  int rc = check_common(g, d_state, n, "cx_rollout");
+static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                          const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                          uint8_t* d_board, void* stream, const char* who) {
+  int rc = check_common(g, d_state, n, who);
   if (rc) return rc;
   if (T < 1) {
-    cx_set_error("cx_rollout: n_steps must be >= 1");
+    cx_set_error("%s: n_steps must be >= 1", who);
     return CX_ERR_INVALID_ARG;
   }
-  if (!d_actions || !d_reward || !d_flags || !d_board) {
-    cx_set_error("cx_rollout: actions/reward/flags/board must not be NULL");
+  if ((!synth.on && !d_actions) || !d_reward || !d_flags || !d_board) {
+    cx_set_error("%s: actions/reward/flags/board must not be NULL", who);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (synth.on && (synth.env_offset & 3)) {
+    cx_set_error("%s: env_offset must be a multiple of 4", who);
     return CX_ERR_INVALID_ARG;
   }
   if (g->path == CX_PATH_AGENT)
-    return cx_launch_agent_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+    return cx_launch_agent_rollout(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                    (cudaStream_t)stream);
-  return cx_launch_generic_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+  return cx_launch_generic_rollout(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                    (cudaStream_t)stream);
+}
+
+extern "C" int cx_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                          float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
+  CxSynth none;
+  memset(&none, 0, sizeof(none));
+  return rollout_common(g, d_state, n, T, d_actions, none, d_reward, d_discount, d_flags, d_board, stream,
+                        "cx_rollout");
+}
+
+extern "C" int cx_rollout_synth(const cx_game* g, void* d_state, int64_t n, int32_t T, uint64_t seed,
+                                uint64_t env_offset, uint64_t t0, uint8_t* d_actions_out, float* d_reward,
+                                float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
+  CxSynth sy;
+  sy.on = 1;
+  sy.seed = seed;
+  sy.env_offset = env_offset;
+  sy.t0 = t0;
+  sy.actions_out = d_actions_out;
+  return rollout_common(g, d_state, n, T, nullptr, sy, d_reward, d_discount, d_flags, d_board, stream,
+                        "cx_rollout_synth");
 }
 
 extern "C" int cx_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,

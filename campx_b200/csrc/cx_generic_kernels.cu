@@ -28,6 +28,7 @@
 // entity state and the plane move once per launch.  Boards wider than 64 columns use the per-cell
 // composition fallback.
 #include "cx_internal.cuh"
+#include "cx_philox.cuh"
 
 namespace {
 
@@ -50,6 +51,9 @@ struct GenParams {
   int64_t n;
   int32_t T;
   int32_t vec;
+  int32_t synth;                  // actions generated in the kernel (cx_philox.cuh)
+  uint64_t seed, env_offset, t0;
+  uint8_t* actions_out;
 };
 
 struct Ctx {
@@ -343,7 +347,13 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
     const int64_t row = (int64_t)t * P.n + env0;
     bool reset_me = false;
     if (mine) {
-      const uint32_t a = P.actions[row + lane];
+      uint32_t a;
+      if (P.synth) {
+        a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t, (uint32_t)H.n_actions);
+        if (P.actions_out) P.actions_out[row + lane] = (uint8_t)a;
+      } else {
+        a = P.actions[row + lane];
+      }
       float rw, dc;
       uint32_t f;
       if (H.track && (ts & CX_OVER_BIT)) {
@@ -508,10 +518,15 @@ int configure_once() {
 }  // namespace
 
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                              float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                              cudaStream_t s) {
+                              const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                              uint8_t* d_board, cudaStream_t s) {
   GenParams P = make_params(g, d_state, n);
   P.actions = d_actions;
+  P.synth = synth.on;
+  P.seed = synth.seed;
+  P.env_offset = synth.env_offset;
+  P.t0 = synth.t0;
+  P.actions_out = synth.actions_out;
   P.reward = d_reward;
   P.discount = d_discount;
   P.flags = d_flags;

@@ -118,13 +118,20 @@ void cx_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// synthetic-action request: when `on`, kernels generate actions (cx_philox.cuh) instead of reading them
+struct CxSynth {
+  int on;
+  uint64_t seed, env_offset, t0;
+  uint8_t* actions_out;  // [T, n] or null
+};
+
 // kernel launchers (defined in the kernel translation units)
 int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                            float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                            cudaStream_t s);
+                            const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                            uint8_t* d_board, cudaStream_t s);
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                              float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                              cudaStream_t s);
+                              const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                              uint8_t* d_board, cudaStream_t s);
 int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s);
 int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
 int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);

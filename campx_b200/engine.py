@@ -222,6 +222,19 @@ class Engine(object):
         self._native.rollout(actions, board, reward, flags, discount)
         return board, reward, discount, flags
 
+    def rollout_random(self, n_steps, seed, env_offset=0, t0=0, out=None, actions_out=None):
+        """T fused play() calls with uniform random actions drawn inside the kernel (counter-based Philox
+        keyed by (seed, env_offset + env, t0 + t): the stream `native.fill_actions` produces)."""
+        if not self._showtime:
+            raise RuntimeError('rollout_random() cannot be called until the Engine is placed in "play mode" via '
+                               'the its_showtime() method')
+        if out is None:
+            out = self._native.alloc_outputs(n_steps)
+        board, reward, flags, discount = out
+        self._native.rollout_synth(n_steps, seed, board, reward, flags, discount, env_offset=env_offset, t0=t0,
+                                   actions_out=actions_out)
+        return board, reward, discount, flags
+
     def alloc_rollout(self, n_steps):
         return self._native.alloc_outputs(n_steps)
 

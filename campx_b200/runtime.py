@@ -123,6 +123,22 @@ class NativeGame(object):
             N.check(self._lib.cx_rollout(self._handle, _ptr(self.state), n, T, _ptr(actions), _ptr(reward),
                                          _ptr(discount), _ptr(flags), _ptr(board), _stream()))
 
+    def rollout_synth(self, n_steps, seed, board, reward, flags, discount=None, env_offset=0, t0=0, actions_out=None):
+        """Fused rollout with uniform random actions generated inside the kernel (no action bytes read);
+        identical to fill_actions(seed, env_offset, t0) + rollout."""
+        n, T = self.num_envs, int(n_steps)
+        self._check(board, torch.uint8, (T, n, self.rows, self.cols), "board")
+        self._check(reward, torch.float32, (T, n), "reward")
+        self._check(flags, torch.uint8, (T, n), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (T, n), "discount")
+        if actions_out is not None:
+            self._check(actions_out, torch.uint8, (T, n), "actions_out")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_rollout_synth(self._handle, _ptr(self.state), n, T, int(seed), int(env_offset),
+                                               int(t0), _ptr(actions_out), _ptr(reward), _ptr(discount),
+                                               _ptr(flags), _ptr(board), _stream()))
+
     def layers_from_board(self, board, out=None, dtype=torch.uint8):
         """[..., rows, cols] boards -> [..., n_chars, rows, cols] layered boards (rendering.py:204-215)."""
         if board.dtype != torch.uint8 or not board.is_contiguous() or board.device != self.device:

@@ -189,6 +189,14 @@ CX_API int cx_step(const cx_game* game, void* d_state, int64_t n_envs, const uin
 CX_API int cx_rollout(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps, const uint8_t* d_actions,
                float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream);
 
+/* cx_rollout with the actions generated inside the kernel (no action bytes read from HBM): exactly the
+ * stream cx_fill_actions(seed, env_offset, t0, ...) would produce, so results are identical to
+ * cx_fill_actions + cx_rollout.  env_offset must be a multiple of 4.  d_actions_out [T, n] (may be NULL)
+ * receives the actions that were played. */
+CX_API int cx_rollout_synth(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps, uint64_t seed,
+                     uint64_t env_offset, uint64_t t0, uint8_t* d_actions_out, float* d_reward, float* d_discount,
+                     uint8_t* d_flags, uint8_t* d_board, void* stream);
+
 /* layers / layered_board from finished boards (rendering.py:204-215): d_layered [n, n_chars, cells]
  * with channel k = (board == chars[k]).  n_boards may be T*n for rollout buffers. */
 CX_API int cx_layers_from_board(const cx_game* game, const uint8_t* d_board, int64_t n_boards, uint8_t* d_layered,
@@ -201,7 +209,8 @@ CX_API int cx_layers_from_board_f32(const cx_game* game, const uint8_t* d_board,
 CX_API int cx_onehot_to_index(const float* d_onehot, int64_t n_envs, int32_t n_actions, uint8_t* d_index,
                        int32_t* d_bad_count, void* stream);
 
-/* Synthetic uniform actions: out[t, i] = mulhi(philox4x32_10(key=seed, ctr=(env_offset+i, t0+t))[0], n_actions). */
+/* Synthetic uniform actions from counter-based Philox4x32-10: with g = env_offset + i (global env id),
+ *   out[t, i] = mulhi(philox(key = seed, counter = (g >> 2, t0 + t))[g & 3], n_actions). */
 CX_API int cx_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t n_steps, int64_t n_envs,
                     int32_t n_actions, uint8_t* d_out, void* stream);
 

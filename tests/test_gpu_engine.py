@@ -178,25 +178,52 @@ def test_rollout_equals_play_and_sharding_is_deterministic():
         assert torch.equal(step.flags, out_full[3][t])
 
 
+def philox4(seed, quad, t):
+    """Host reference of campx_b200/csrc/cx_philox.cuh (Philox4x32-10)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+    c = [quad & 0xFFFFFFFF, quad >> 32, t & 0xFFFFFFFF, t >> 32]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k1, p0 & 0xFFFFFFFF]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c
+
+
 def test_philox_actions_match_host_reference():
-    """cx_fill_actions is counter-based: any (env, t) is regenerable on the host (Philox4x32-10)."""
-    def philox(seed, env, t):
-        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
-        k0, k1 = seed & 0xFFFFFFFF, seed >> 32
-        c = [env & 0xFFFFFFFF, env >> 32, t & 0xFFFFFFFF, t >> 32]
-        for _ in range(10):
-            p0, p1 = M0 * c[0], M1 * c[2]
-            c = [(p1 >> 32) ^ c[1] ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k1, p0 & 0xFFFFFFFF]
-            k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
-        return c[0]
+    """cx_fill_actions is counter-based: any (env, t) is regenerable on the host."""
     game = make_world("boat_race", num_envs=64)
     game.its_showtime()
     a = game.native.fill_actions(7, seed=543, env_offset=1000, t0=3).cpu().numpy()
     for t in range(7):
-        for i in (0, 1, 17, 63):
-            assert a[t, i] == (philox(543, 1000 + i, 3 + t) * 5) >> 32
+        for i in (0, 1, 2, 3, 17, 63):
+            g = 1000 + i
+            assert a[t, i] == (philox4(543, g >> 2, 3 + t)[g & 3] * 5) >> 32
     hist = np.bincount(game.native.fill_actions(200, seed=1).cpu().numpy().reshape(-1), minlength=5) / (200 * 64)
     assert np.all(np.abs(hist - 0.2) < 0.02)
+
+
+@pytest.mark.parametrize("world,n", [("boat_race", 1024), ("boat_race", 100), ("demo3", 512), ("hello", 96)])
+def test_in_kernel_random_rollout_equals_fill_actions_plus_rollout(world, n):
+    """cx_rollout_synth draws the actions inside the kernel from the same Philox stream."""
+    T, seed, off, t0 = 37, 543, 4096, 11
+    a = make_world(world, num_envs=n, max_episode_steps=20, track_returns=True)
+    b = make_world(world, num_envs=n, max_episode_steps=20, track_returns=True)
+    a.its_showtime()
+    b.its_showtime()
+    acts = a.native.fill_actions(T, seed=seed, env_offset=off, t0=t0)
+    ra = a.rollout(acts)
+    played = torch.empty_like(acts)
+    rb = b.rollout_random(T, seed, env_offset=off, t0=t0, actions_out=played)
+    assert torch.equal(played, acts)
+    for x, y in zip(ra, rb):
+        assert (x is None and y is None) or torch.equal(x, y)
+    assert torch.equal(a.native.state, b.native.state)
+    rc = b.rollout_random(3, seed, env_offset=off, t0=t0 + T)           # without writing the actions out
+    rd = a.rollout(a.native.fill_actions(3, seed=seed, env_offset=off, t0=t0 + T))
+    assert torch.equal(rc[0], rd[0]) and torch.equal(rc[1], rd[1])
+    with pytest.raises(ValueError):
+        b.rollout_random(2, seed, env_offset=3)
 
 
 def test_full_size_properties_boat_race():
