@@ -24,14 +24,11 @@
 #include "cx_internal.cuh"
 #include "cx_philox.cuh"
 
-#ifndef CX_OPT_NOBRANCH_POKE
-#define CX_OPT_NOBRANCH_POKE 0
-#endif
-#ifndef CX_OPT_SPLITCOPY
-#define CX_OPT_SPLITCOPY 0
-#endif
 #ifndef CX_OPT_MINBLOCKS
 #define CX_OPT_MINBLOCKS 7
+#endif
+#ifndef CX_OPT_TMA
+#define CX_OPT_TMA 1   // board tiles leave shared memory as one cp.async.bulk (UBLKCP) per warp and step
 #endif
 
 namespace {
@@ -99,6 +96,23 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// ---- bulk asynchronous copy shared -> global (TMA engine, no tensor map: the tile is a flat byte range) ----
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the source bytes of every committed bulk store have been read: the tile may be modified again
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (the TMA engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // atomic max on a double that is only ever raised (stats slots start at -inf)
 __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
@@ -176,7 +190,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 
   // ---- load env state into registers; paint the agents into the tile ----
   uint32_t cellv[QUADS][4];   // agent cell
-  uint32_t drawn[QUADS][4];   // cell where the agent is currently drawn in the tile (none: nowhere)
+  uint32_t drawnq[QUADS];     // per env one byte: cell where the agent is currently drawn in the tile (none: nowhere)
   uint32_t ts[QUADS][4];
   float rt[QUADS][4];
 #pragma unroll
@@ -190,6 +204,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
       ts[j][0] = tv.x & 0xFFFF; ts[j][1] = tv.x >> 16; ts[j][2] = tv.y & 0xFFFF; ts[j][3] = tv.y >> 16;
       rt[j][0] = rv.x; rt[j][1] = rv.y; rt[j][2] = rv.z; rt[j][3] = rv.w;
     }
+    drawnq[j] = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const bool valid = VEC || el + i < nenv;
@@ -198,12 +213,12 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
         rt[j][i] = valid ? P.ret[env0 + el + i] : 0.0f;
       }
       cellv[j][i] = min((cq >> (8 * i)) & 0xFF, none);
-      drawn[j][i] = none;
+      uint32_t sh = none;
       if (valid) {
-        const uint32_t sh = s_shown[cellv[j][i]];
+        sh = s_shown[cellv[j][i]];
         if (sh != none) tile[(el + i) * cells + sh] = (uint8_t)agent_char;
-        drawn[j][i] = sh;
       }
+      drawnq[j] |= sh << (8 * i);
     }
   }
 
@@ -243,22 +258,29 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 #pragma unroll
   for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, 0);
 
+  constexpr bool TMA = VEC && (CX_OPT_TMA != 0);
+  const uint64_t l2pol = l2_evict_first_policy();
+
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * n + env0;  // index of this warp's first env in [T, n] arrays
     const int64_t row_end = (int64_t)(t + 1) * n;
     if ((t & 15) == 0) prefetch_actions(t + 32);
+    // ---- phase A (registers and tables only): the step of every env this lane owns ----
+    uint32_t shwq[QUADS];  // per env one byte: where the agent is drawn after this step
 #pragma unroll
     for (int j = 0; j < QUADS; ++j) {
       const int el = j * 128 + lane * 4;
+      shwq[j] = drawnq[j];
       if (VEC || el < nenv) {
         float rw[4], dc[4];
-        uint32_t fl = 0;
-        uint8_t* qtile = tile + el * cells;
+        uint32_t fl = 0, shw = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          const uint32_t was = (drawnq[j] >> (8 * i)) & 0xFF;
           if (!VEC && el + i >= nenv) {  // tail quad on the scalar path: env does not exist
             rw[i] = 0.0f;
             dc[i] = 0.0f;
+            shw |= was << (8 * i);
             continue;
           }
           // one table lookup = action dispatch + toroidal move + wall gate + entry rewards + directives
@@ -268,7 +290,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           float r = s_tr[idx];
           if (want_discount) dc[i] = s_td[a];
           if (TRACK && (ts[j][i] & CX_OVER_BIT)) {  // auto_reset == 0 and the episode ended: frozen env
-            e = cellv[j][i] | (drawn[j][i] << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+            e = cellv[j][i] | (was << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
             r = 0.0f;
             dc[i] = 0.0f;
           }
@@ -293,63 +315,69 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           }
           rw[i] = r;
           fl |= f << (8 * i);
+          shw |= show << (8 * i);
           cellv[j][i] = p;
-          // re-compose this env's board: base character back where the agent was drawn, agent character
-          // where it is visible now (painter's algorithm collapsed to two byte stores)
-          const uint32_t was = drawn[j][i];
-#if CX_OPT_NOBRANCH_POKE
-          {
-            uint8_t* b = qtile + i * cells;
-            if (was != none) b[was] = s_basech[was];
-            if (show != none) b[show] = (uint8_t)agent_char;
-            drawn[j][i] = show;
-          }
-#else
-          if (was != show) {
-            uint8_t* b = qtile + i * cells;
-            if (was != none) b[was] = s_basech[was];
-            if (show != none) b[show] = (uint8_t)agent_char;
-            drawn[j][i] = show;
-          }
-#endif
         }
+        shwq[j] = shw;
         st_f32x4<VEC>(P.reward, row + el, row_end, rw);
         if (want_discount) st_f32x4<VEC>(P.discount, row + el, row_end, dc);
         st_u8x4<VEC>(P.flags, row + el, row_end, fl);
       }
-#if CX_OPT_SPLITCOPY
-      if (VEC) {  // stream this quad's 128 boards now; the next quad's compute overlaps the store burst
-        __syncwarp();
-        const uint4* t16 = reinterpret_cast<const uint4*>(tile + j * 128 * cells);
-        uint4* d16 = reinterpret_cast<uint4*>(P.board + (row + j * 128) * cells);
-        const int nchunks = 128 * cells / 16;
-#pragma unroll 4
-        for (int k = lane; k < nchunks; k += 32) __stcs(d16 + k, t16[k]);
-      }
-#endif
     }
-    // next step's actions: issue the loads before streaming the tile so their latency is hidden
+    // next step's actions: issue the loads before touching the tile so their latency is hidden
     if (t + 1 < P.T) {
 #pragma unroll
       for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, t + 1);
     }
-    __syncwarp();
+    if (TMA) {  // the previous step's bulk store must have read the tile before it is modified
+      if (lane == 0) bulk_wait_read();
+      __syncwarp();
+    }
+    // ---- phase B: re-compose the boards: base character back where the agent was drawn, agent character
+    // where it is visible now (painter's algorithm collapsed to two byte stores per env that changed) ----
+#pragma unroll
+    for (int j = 0; j < QUADS; ++j) {
+      const uint32_t diff = drawnq[j] ^ shwq[j];
+      if (diff) {
+        uint8_t* qtile = tile + (j * 128 + lane * 4) * cells;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((diff >> (8 * i)) & 0xFF) {
+            const uint32_t was = (drawnq[j] >> (8 * i)) & 0xFF, show = (shwq[j] >> (8 * i)) & 0xFF;
+            uint8_t* b = qtile + i * cells;
+            if (was != none) b[was] = s_basech[was];
+            if (show != none) b[show] = (uint8_t)agent_char;
+          }
+        }
+        drawnq[j] = shwq[j];
+      }
+    }
     // ---- stream the finished boards of this warp's envs to HBM ----
-    {
-      uint8_t* dst = P.board + row * cells;
+    uint8_t* dst = P.board + row * cells;
+    if (TMA) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store_s2g(dst, tile, (uint32_t)(WT * cells), l2pol);
+        bulk_commit();
+      }
+    } else {
+      __syncwarp();
       if (VEC) {
-#if !CX_OPT_SPLITCOPY
         const uint4* t16 = reinterpret_cast<const uint4*>(tile);
         uint4* d16 = reinterpret_cast<uint4*>(dst);
         const int nchunks = WT * cells / 16;
 #pragma unroll 4
         for (int k = lane; k < nchunks; k += 32) __stcs(d16 + k, t16[k]);
-#endif
       } else {
         const int nbytes = nenv * cells;
         for (int k = lane; k < nbytes; k += 32) dst[k] = tile[k];
       }
+      __syncwarp();
     }
+  }
+  if (TMA) {  // shared memory must outlive the last bulk read
+    if (lane == 0) bulk_wait_read();
     __syncwarp();
   }
 
