@@ -27,6 +27,9 @@
 #ifndef CX_OPT_MINBLOCKS
 #define CX_OPT_MINBLOCKS 7
 #endif
+#ifndef CX_OPT_PDL
+#define CX_OPT_PDL 1   // programmatic dependent launch: the next launch's prologue overlaps this launch's tail
+#endif
 #ifndef CX_OPT_TMA
 #define CX_OPT_TMA 1   // board tiles leave shared memory as one cp.async.bulk (UBLKCP) per warp and step
 #endif
@@ -154,6 +157,11 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cells = H.cells;
 
+#if CX_OPT_PDL
+  // Let the next launch in the stream become resident as our CTAs retire and run its prologue (tables and
+  // tile staging touch only immutable data); it blocks at griddepcontrol.wait until this grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
   // ---- stage the static tables (transition table, rewards, base board, tile pattern) ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.blob);
@@ -188,6 +196,9 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   }
   __syncwarp();
 
+#if CX_OPT_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything earlier in the stream is complete and visible
+#endif
   // ---- load env state into registers; paint the agents into the tile ----
   uint32_t cellv[QUADS][4];   // agent cell
   uint32_t drawnq[QUADS];     // per env one byte: cell where the agent is currently drawn in the tile (none: nowhere)
@@ -434,8 +445,22 @@ int launch(const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
                                     227 * 1024));
     configured = true;
   }
+#if CX_OPT_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CX_AGENT_CTA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout<TRACK, VEC, SYNTH>, P));
+#else
   k_agent_rollout<TRACK, VEC, SYNTH><<<grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
+#endif
   return CX_OK;
 }
 

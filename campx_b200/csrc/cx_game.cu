@@ -450,7 +450,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
   H->n_dyn = n_dyn;
   H->has_dynbd = any_stamp;
   H->needs_prev = needs_prev;
-  H->off_masks = B->reserve((size_t)E * H->mask_words * 4);
+  H->off_masks = B->reserve(((size_t)E * H->mask_words + 1) * 4);  // +1: the composer's funnel shift reads one word ahead
   for (int z = 0; z < E; ++z) {
     uint32_t* w = (uint32_t*)&B->bytes[H->off_masks + (size_t)z * H->mask_words * 4];
     const uint8_t* m = d->masks + (size_t)z * cells;
@@ -480,14 +480,69 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
           if (m[c]) rb[z * R + c / C] |= 1ull << (c % C);
     }
   }
-  // envs per warp: small tiles keep ~30 warps per SM resident (two byte tiles per env in shared memory)
-  // while the (env,row) composition tasks still fill the 32 lanes
-  int tile = cells >= 128 ? 8 : (cells >= 32 ? 16 : 32);
+  // Mask entities (static / rolling drapes) are composed from linear bitsets.  A rolling mask, and a static
+  // mask with a visible one-cell entity above it in z-order (whose cell is punched out of the mask), need a
+  // per-env copy in shared memory.
+  int n_lin = 0;
+  bool wide_roll = false;
+  for (int z = 0; z < E; ++z) {
+    CxGenEntity& g = H->ent[z];
+    g.lin_slot = 0xFF;
+    if (g.kind != CX_KIND_STATIC && g.kind != CX_KIND_ROLL) continue;
+    bool per_env = g.kind == CX_KIND_ROLL;
+    if (g.kind == CX_KIND_ROLL && C > 64) wide_roll = true;
+    for (int y = z + 1; y < E; ++y)
+      if ((H->ent[y].kind == CX_KIND_CELL || H->ent[y].kind == CX_KIND_SPRITE) && H->ent[y].visible) per_env = true;
+    if (per_env) g.lin_slot = (uint8_t)(n_lin < 255 ? n_lin : 254), ++n_lin;
+  }
+  H->n_lin = n_lin;
+  for (int i = 0; i < CX_MAX_LIN; ++i) H->off_colroll[i] = -1;
+  if (H->fast_compose) {
+    // A roll by (dr, dc) is a column roll inside every board row followed by a rotation of the linear
+    // bitset by dr * cols bits.  Tabulating the column rolls leaves the kernel only the rotation.
+    const int lw = H->mask_words + 1;
+    for (int z = 0; z < E; ++z) {
+      const CxGenEntity& g = H->ent[z];
+      if (g.kind != CX_KIND_ROLL || g.lin_slot >= CX_MAX_LIN || (size_t)C * lw * 4 > 16 * 1024) continue;
+      const int32_t off = B->reserve((size_t)C * lw * 4);
+      H->off_colroll[g.lin_slot] = off;
+      const uint8_t* m = d->masks + (size_t)z * cells;
+      for (int dc = 0; dc < C; ++dc) {
+        uint32_t* w = (uint32_t*)&B->bytes[off + (size_t)dc * lw * 4];
+        for (int r = 0; r < R; ++r)
+          for (int c = 0; c < C; ++c)
+            if (m[r * C + (c - dc + C) % C]) w[(r * C + c) >> 5] |= 1u << ((r * C + c) & 31);
+      }
+    }
+  }
+  H->n_masks = H->n_points = 0;
+  for (int z = 0; z < E; ++z) {
+    const CxGenEntity& g = H->ent[z];
+    if (g.kind == CX_KIND_STATIC || g.kind == CX_KIND_ROLL) {
+      H->mask_prog[H->n_masks++] = (uint32_t)z | ((uint32_t)g.ch << 8) | ((uint32_t)g.lin_slot << 16) | ((uint32_t)g.kind << 24);
+    } else if (g.visible) {
+      uint32_t holes = 0;
+      for (int y = 0; y < z; ++y)
+        if ((H->ent[y].kind == CX_KIND_STATIC || H->ent[y].kind == CX_KIND_ROLL) && H->ent[y].lin_slot != 0xFF &&
+            H->ent[y].lin_slot < 32)
+          holes |= 1u << H->ent[y].lin_slot;
+      H->point_holes[H->n_points] = holes;
+      H->point_prog[H->n_points++] =
+          (uint32_t)z | ((uint32_t)g.ch << 8) | ((uint32_t)g.dyn_slot << 16) | ((uint32_t)(g.stamps ? 1 : 0) << 24);
+    }
+  }
+  H->fast_compose = (n_lin <= CX_MAX_LIN && !wide_roll && cells >= 16) ? 1 : 0;
+  if (const char* dbg = getenv("CX_GEN_SLOW")) {  // development knob: force the per-cell composer
+    if (atoi(dbg)) H->fast_compose = 0;
+  }
+  // envs per warp: one plane tile of at most 8 KB per warp keeps >= 20 warps per SM resident
+  int tile = 32;
+  while (tile > 1 && (size_t)tile * cells > 8 * 1024) tile >>= 1;
   if (const char* dbg = getenv("CX_GEN_TILE")) {  // development knob
     const int v = atoi(dbg);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) tile = v;
   }
-  while (tile > 1 && (size_t)2 * tile * cells > 96 * 1024) tile >>= 1;
+  while (tile > 1 && (size_t)tile * cells > 96 * 1024) tile >>= 1;
   H->tile_envs = tile;
   B->pad();
   H->blob_bytes = (int32_t)B->bytes.size();

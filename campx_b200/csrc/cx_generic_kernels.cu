@@ -13,20 +13,25 @@
 //                              has its canvas zeroed at every render
 //   plot directives            campx/plot.py:161-257, engine.py:285-290
 //
-// B200 mapping.  One WARP owns `tile_envs` (8..32) consecutive envs for all T fused steps,
-// and keeps two byte tiles in shared memory: the per-env BACKDROP PLANE (static scenery + quirk-Q1
-// sprite stamps; loaded once per launch, written back once) and the composed BOARD.  Warps never wait
-// on a block barrier after the tables are staged.  A step is
-//   phase 1  lane = env: entity state update in update order (a few bytes in shared memory), stamps
-//            into the plane tile;
-//   phase 2a whole warp: board tile = plane tile (128-bit shared-memory copies);
-//   phase 2b one lane per (env, board row): each entity's row as a 64-bit bitset (static rows from a
-//            table, rolled rows by a 64-bit rotate, one-cell entities by a shift), z-order resolved with
-//            bit masks front to back, visible bits written as bytes into the board tile;
-//   phase 2c whole warp: stream the board tile to HBM with LDS.128 -> STG.128 (st.global.cs).
+// B200 mapping.  One WARP owns `tile_envs` (8..32) consecutive envs for all T fused steps and keeps
+// their BACKDROP PLANES (static scenery + quirk-Q1 sprite stamps; loaded once per launch, written back
+// once) as one byte tile in shared memory.  Warps never wait on a block barrier after the tables are
+// staged.  A step is
+//   phase 1   lane = env: entity state update in update order (a few bytes in shared memory), stamps
+//             into the plane tile;
+//   phase 1b  whole warp: the masks that differ per env (rolled drapes; static drapes with a one-cell
+//             entity above them) are rebuilt as LINEAR bitsets (bit = cell index) in shared memory: a
+//             roll is a 64-bit rotate per board row, re-packed 32 cells per lane;
+//   phase 1c  lane = env: cells of one-cell entities are punched out of the masks below them and their
+//             characters poked into the plane tile (un-poked after the step), so that ...
+//   phase 2   ... composing is only "plane bytes, overlaid by each mask entity in z-order": one lane per
+//             16-byte chunk of the board tile: LDS.128 of the plane, per mask entity a 16-bit slice of its
+//             bitset (funnel shift), expanded to byte masks (multiply trick) and merged with LOP3, then
+//             STG.128 (st.global.cs) straight from registers.  Chunks that straddle two envs (cells is
+//             not a multiple of 16) take a second pass with two slices per mask.
 // Per env-step HBM traffic is the observation contract only (board + reward + flags + discount + action);
-// entity state and the plane move once per launch.  Boards wider than 64 columns use the per-cell
-// composition fallback.
+// entity state and the plane move once per launch.  Games with more than CX_MAX_LIN per-env masks, rolling
+// drapes wider than 64 columns, or unaligned buffers use the per-cell painter's algorithm instead.
 #include "cx_internal.cuh"
 #include "cx_philox.cuh"
 
@@ -64,6 +69,15 @@ struct Ctx {
   const uint16_t* rc;
   const uint64_t* rowbits;
   const uint8_t* chidx;  // [256] char code -> game char index (0xFF: not a game char)
+  const uint8_t* smem;   // staged tables blob
+};
+
+// per-warp view of the shared-memory working set
+struct WarpMem {
+  uint8_t* plane;              // [G][cells] backdrop planes, tile-contiguous like the board rows in HBM
+  uint32_t* lin;               // [G][n_lin][mask_words + 1] per-env mask bitsets (last word stays 0)
+  uint16_t (*dyn)[CX_MAX_DYN]; // [G] entity state
+  uint16_t (*prev)[CX_MAX_DYN];
 };
 
 __device__ __forceinline__ bool mask_bit(const Ctx& X, int z, int cell) {
@@ -238,6 +252,7 @@ __device__ __forceinline__ void setup_ctx(Ctx& X, const GenParams& P, uint8_t* s
   X.rc = reinterpret_cast<const uint16_t*>(smem + P.h.off_rc);
   X.rowbits = P.h.off_rowbits >= 0 ? reinterpret_cast<const uint64_t*>(smem + P.h.off_rowbits) : nullptr;
   X.chidx = s_chidx;
+  X.smem = smem;
 }
 
 __device__ __forceinline__ void stage_tables(const GenParams& P, uint8_t* smem, uint8_t* s_chidx) {
@@ -252,46 +267,198 @@ __device__ __forceinline__ void stage_tables(const GenParams& P, uint8_t* smem, 
   }
 }
 
-// Compose the boards of one warp's envs from `plane` into `out` (both shared memory, [G][cells]).
-__device__ __forceinline__ void compose_warp(const Ctx& X, const uint16_t (*dyn)[CX_MAX_DYN], const uint8_t* plane,
-                                             uint8_t* out, int nenv, int tile_bytes16, int lane) {
+// x / d by multiplication with ceil(2^32 / d): exact while x * d < 2^32 (tiles are < 2^17 bytes, d <= 4096)
+__device__ __forceinline__ uint32_t div_inverse(uint32_t d) { return d == 1u ? 0u : 0xFFFFFFFFu / d + 1u; }
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t inv) { return inv ? __umulhi(x, inv) : x; }
+
+// phase 1b: rebuild the per-env linear bitsets (32 cells per lane and task)
+__device__ __forceinline__ void build_linear_masks(const Ctx& X, const WarpMem& W, int nenv, int lane) {
   const CxGenHeader& H = *X.H;
-  const int cells = H.cells;
-  {  // 2a: board = backdrop plane
-    const uint4* s16 = reinterpret_cast<const uint4*>(plane);
-    uint4* d16 = reinterpret_cast<uint4*>(out);
-    for (int k = lane; k < tile_bytes16; k += 32) d16[k] = s16[k];
-  }
-  __syncwarp();
-  if (X.rowbits) {  // 2b: one lane per (env, row); z-order resolved on 64-bit row bitsets, front to back
-    const int R = H.rows, C = H.cols;
-    const uint32_t inv_r = 0xFFFFFFFFu / (uint32_t)R + 1u;  // exact for task < 2^16
-    for (int task = lane; task < nenv * R; task += 32) {
-      const int e = (int)__umulhi((uint32_t)task, inv_r), r = task - e * R;
-      uint8_t* row = out + e * cells + r * C;
-      uint64_t covered = 0ull;
-      for (int z = H.n_ent - 1; z >= 0; --z) {
-        const uint64_t bits = entity_row(X, dyn[e], z, r);
-        uint64_t vis = bits & ~covered;
-        covered |= bits;
-        const uint8_t ch = H.ent[z].ch;
-        uint32_t lo = (uint32_t)vis, hi = (uint32_t)(vis >> 32);
-        while (lo) {
-          const int c = __ffs(lo) - 1;
-          lo &= lo - 1;
-          row[c] = ch;
-        }
-        while (hi) {
-          const int c = __ffs(hi) - 1;
-          hi &= hi - 1;
-          row[32 + c] = ch;
+  if (H.n_lin == 0) return;
+  const int mw = H.mask_words, lw = mw + 1, R = H.rows, C = H.cols;
+  const uint32_t inv_mw = div_inverse((uint32_t)mw);
+  const uint64_t full = C >= 64 ? ~0ull : ((1ull << C) - 1ull);
+  for (int i = 0; i < H.n_masks; ++i) {
+    const uint32_t prog = H.mask_prog[i];
+    const uint32_t z = prog & 0xFF, ls = (prog >> 16) & 0xFF, kind = prog >> 24;
+    if (ls == 0xFF) continue;
+    const uint32_t slot = H.ent[z].dyn_slot;
+    const uint64_t* rows = X.rowbits + z * R;
+    const int32_t off_cr = kind == CX_KIND_ROLL ? H.off_colroll[ls] : -1;
+    const uint32_t* colroll = reinterpret_cast<const uint32_t*>(X.smem + (off_cr >= 0 ? off_cr : 0));
+    for (int task = lane; task < nenv * mw; task += 32) {
+      const int e = (int)fast_div((uint32_t)task, inv_mw), j = task - e * mw;
+      uint32_t w;
+      if (kind == CX_KIND_STATIC) {
+        w = X.masks[z * mw + j];
+      } else if (off_cr >= 0) {
+        // rolled mask = (static mask rolled by dc columns: tabulated) rotated by dr * cols bits
+        const uint32_t s = W.dyn[e][slot];
+        const uint32_t* src = colroll + (s & 255u) * lw;
+        int S = 32 * j - (int)(s >> 8) * C;          // first source bit of this word
+        if (S < 0) S += H.cells;
+        w = __funnelshift_r(src[S >> 5], src[(S >> 5) + 1], S & 31);
+        const int n1 = H.cells - S;                  // bits left before the bitset wraps around
+        if (n1 < 32) w = (w & ((1u << n1) - 1u)) | (src[0] << n1);
+      } else {  // rolled mask (np.roll: content moves down/right by the accumulated offset): gather cells
+                // 32j .. 32j+31 from the rotated board rows
+        const uint32_t s = W.dyn[e][slot], k = s & 255u;
+        const uint32_t rcv = X.rc[32 * j];
+        int r = (int)(rcv >> 8), c = (int)(rcv & 255), got = 0;
+        int sr = r - (int)(s >> 8);
+        if (sr < 0) sr += R;
+        w = 0;
+        while (got < 32 && r < R) {
+          const uint64_t x = rows[sr];
+          const uint64_t bits = (k ? ((x << k) | (x >> (C - k))) & full : x) >> c;
+          w |= (uint32_t)(bits << got);
+          got += C - c;
+          c = 0;
+          ++r;
+          if (++sr == R) sr = 0;
         }
       }
+      W.lin[(e * H.n_lin + ls) * lw + j] = w;
     }
-  } else {  // wide boards: per-cell painter's algorithm, whole warp over the tile
+  }
+}
+
+// phase 1c (lane = env): one-cell entities.  Their cells are punched out of every per-env mask BELOW them
+// in z-order and their characters poked into the plane in z-order, so that the composer only deals with
+// masks.  Returns the plane bytes that were overwritten (one per dynamic slot) for unpoke_points().
+__device__ __forceinline__ uint64_t poke_points(const Ctx& X, const WarpMem& W, int e) {
+  const CxGenHeader& H = *X.H;
+  const int lw = H.mask_words + 1;
+  uint8_t* plane = W.plane + e * H.cells;
+  uint32_t* lin = W.lin + e * H.n_lin * lw;
+  uint64_t saved = 0;
+  for (int i = 0; i < H.n_points; ++i) {
+    const uint32_t prog = H.point_prog[i], slot = (prog >> 16) & 0xFF;
+    const uint32_t s = W.dyn[e][slot];
+    if (s == CX_EMPTY_CELL16) continue;
+    for (uint32_t holes = H.point_holes[i]; holes; holes &= holes - 1)
+      lin[(__ffs(holes) - 1) * lw + (s >> 5)] &= ~(1u << (s & 31));
+    if (!(prog >> 24)) {  // stamping sprites are in the plane for good (quirk Q1)
+      saved |= (uint64_t)plane[s] << (8 * slot);
+      plane[s] = (uint8_t)(prog >> 8);
+    }
+  }
+  return saved;
+}
+__device__ __forceinline__ void unpoke_points(const Ctx& X, const WarpMem& W, int e, uint64_t saved) {
+  const CxGenHeader& H = *X.H;
+  uint8_t* plane = W.plane + e * H.cells;
+  for (int i = H.n_points - 1; i >= 0; --i) {  // reverse order: restores what was under stacked entities
+    const uint32_t prog = H.point_prog[i], slot = (prog >> 16) & 0xFF;
+    if (prog >> 24) continue;
+    const uint32_t s = W.dyn[e][slot];
+    if (s != CX_EMPTY_CELL16) plane[s] = (uint8_t)(saved >> (8 * slot));
+  }
+}
+
+// 4 mask bits -> 4 byte masks (0x00 / 0xFF): the multiply moves bit i to the top of byte i (no carries),
+// the byte permute replicates each byte's top bit
+// (prmt selector nibble 8|i = "sign of byte i"; __byte_perm masks that bit off, hence the inline PTX)
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, 0, 0xBA98;" : "=r"(m) : "r"(nib * 0x10204080u));
+  return m;
+}
+
+__device__ __forceinline__ void overlay16(uint4& v, uint32_t slice, uint32_t ch4) {
+  if (slice) {
+    uint32_t m;
+    m = expand4(slice & 15u);         v.x = (v.x & ~m) | (ch4 & m);
+    m = expand4((slice >> 4) & 15u);  v.y = (v.y & ~m) | (ch4 & m);
+    m = expand4((slice >> 8) & 15u);  v.z = (v.z & ~m) | (ch4 & m);
+    m = expand4(slice >> 12);         v.w = (v.w & ~m) | (ch4 & m);
+  }
+}
+
+// bits [o, o+16) of a linear bitset (one word of slack behind the last is readable)
+__device__ __forceinline__ uint32_t slice16(const uint32_t* bits, uint32_t o) {
+  const uint32_t j = o >> 5;
+  return __funnelshift_r(bits[j], bits[j + 1], o & 31u) & 0xFFFFu;
+}
+
+// phase 2: compose this warp's board tile chunk by chunk and stream it to `dst` (16-byte aligned)
+__device__ __forceinline__ void compose_stream(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t cells = H.cells, mw = H.mask_words, lw = mw + 1, env_words = H.n_lin * lw;
+  const uint32_t inv_cells = div_inverse(cells);
+  const int nchunks = nenv * (int)cells / 16, n_masks = H.n_masks;
+  const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
+  uint4* d16 = reinterpret_cast<uint4*>(dst);
+  // pass A: chunks inside one env.  The first four mask entities' programs live in registers.
+  constexpr int HOIST = 4;
+  uint32_t prog[HOIST];
+#pragma unroll
+  for (int i = 0; i < HOIST; ++i) prog[i] = i < n_masks ? H.mask_prog[i] : 0u;
+  for (int k = lane; k < nchunks; k += 32) {
+    const uint32_t b = 16u * k, e = fast_div(b, inv_cells), o = b - e * cells;
+    if (o + 16u > cells) continue;  // straddles two envs: pass B
+    uint4 v = p16[k];
+    const uint32_t* lin_e = W.lin + e * env_words;
+#pragma unroll
+    for (int i = 0; i < HOIST; ++i) {
+      if (i < n_masks) {
+        const uint32_t ls = (prog[i] >> 16) & 0xFF;
+        const uint32_t* bits = ls == 0xFF ? X.masks + (prog[i] & 0xFF) * mw : lin_e + ls * lw;
+        overlay16(v, slice16(bits, o), ((prog[i] >> 8) & 0xFF) * 0x01010101u);
+      }
+    }
+    for (int i = HOIST; i < n_masks; ++i) {
+      const uint32_t pg = H.mask_prog[i], ls = (pg >> 16) & 0xFF;
+      const uint32_t* bits = ls == 0xFF ? X.masks + (pg & 0xFF) * mw : lin_e + ls * lw;
+      overlay16(v, slice16(bits, o), ((pg >> 8) & 0xFF) * 0x01010101u);
+    }
+    __stcs(d16 + k, v);
+  }
+  // pass B: the chunk across the boundary between env i-1 and env i (lane i), if there is one
+  if ((cells & 15u) != 0) {
+    for (int i = lane + 1; i < nenv; i += 32) {
+      const uint32_t b = (uint32_t)i * cells;
+      if ((b & 15u) == 0) continue;
+      const uint32_t k = b >> 4, cnt = b - 16u * k;       // cnt cells of env i-1, 16-cnt cells of env i
+      const uint32_t o = cells - cnt, lo_mask = (1u << cnt) - 1u;
+      uint4 v = p16[k];
+      for (int m = 0; m < n_masks; ++m) {
+        const uint32_t prog = H.mask_prog[m], ls = (prog >> 16) & 0xFF;
+        uint32_t sl;
+        if (ls == 0xFF) {
+          const uint32_t* bits = X.masks + (prog & 0xFF) * mw;
+          sl = (slice16(bits, o) & lo_mask) | ((bits[0] << cnt) & 0xFFFFu);
+        } else {
+          const uint32_t* b0 = W.lin + (i - 1) * env_words + ls * lw;
+          sl = (slice16(b0, o) & lo_mask) | ((b0[env_words] << cnt) & 0xFFFFu);
+        }
+        overlay16(v, sl, ((prog >> 8) & 0xFF) * 0x01010101u);
+      }
+      __stcs(d16 + k, v);
+    }
+  }
+}
+
+// Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
+// per-cell painter's algorithm with byte stores (any geometry, any alignment).
+__device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, bool fast,
+                                             int lane) {
+  const CxGenHeader& H = *X.H;
+  if (fast) {
+    build_linear_masks(X, W, nenv, lane);
+    __syncwarp();
+    uint64_t saved = 0;
+    if (lane < nenv) saved = poke_points(X, W, lane);
+    __syncwarp();
+    compose_stream(X, W, nenv, dst, lane);
+    __syncwarp();
+    if (lane < nenv) unpoke_points(X, W, lane, saved);
+  } else {
+    const int cells = H.cells;
+    const uint32_t inv_cells = div_inverse((uint32_t)cells);
     for (int b = lane; b < nenv * cells; b += 32) {
-      const int e = b / cells, cell = b - e * cells;
-      out[b] = overlay(X, dyn[e], cell, plane[b]);
+      const int e = (int)fast_div((uint32_t)b, inv_cells), cell = b - e * cells;
+      dst[b] = overlay(X, W.dyn[e], cell, W.plane[b]);
     }
   }
   __syncwarp();
@@ -301,6 +468,25 @@ struct WarpTile {
   uint16_t dyn[GMAX][CX_MAX_DYN];
   uint16_t prev[GMAX][CX_MAX_DYN];
 };
+
+// dynamic shared memory: [tables blob][per warp: plane tile (16-byte multiple) | per-env mask bitsets]
+__device__ __forceinline__ size_t warp_mem_bytes(const CxGenHeader& H) {
+  const size_t tile = ((size_t)H.tile_envs * H.cells + 15) / 16 * 16;
+  const size_t lin = ((size_t)H.tile_envs * H.n_lin * (H.mask_words + 1) * 4 + 15) / 16 * 16;
+  return tile + lin;
+}
+
+__device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem, WarpTile* wt, int warp, int lane) {
+  WarpMem W;
+  const size_t tile = ((size_t)H.tile_envs * H.cells + 15) / 16 * 16;
+  W.plane = smem + H.blob_bytes + (size_t)warp * warp_mem_bytes(H);
+  W.lin = reinterpret_cast<uint32_t*>(W.plane + tile);
+  W.dyn = wt[warp].dyn;
+  W.prev = wt[warp].prev;
+  const int nwords = H.tile_envs * H.n_lin * (H.mask_words + 1);
+  for (int i = lane; i < nwords; i += 32) W.lin[i] = 0u;  // incl. the slack word behind every bitset
+  return W;
+}
 
 __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -317,10 +503,10 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
   if (env0 >= P.n) return;
   const int nenv = (int)min((int64_t)G, P.n - env0);
-  const int tile_bytes16 = (G * cells + 15) / 16;
-  uint8_t* plane = smem + H.blob_bytes + (size_t)warp * 2 * tile_bytes16 * 16;
-  uint8_t* out = plane + tile_bytes16 * 16;
-  uint16_t (*dyn)[CX_MAX_DYN] = s_w[warp].dyn;
+  const WarpMem W = warp_mem(H, smem, s_w, warp, lane);
+  uint8_t* plane = W.plane;
+  uint16_t (*dyn)[CX_MAX_DYN] = W.dyn;
+  const bool fast = P.vec && H.fast_compose;
   const bool mine = lane < nenv;
   const int64_t env = env0 + lane;
   uint32_t ts = 0;
@@ -333,9 +519,16 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
     }
   }
   // backdrop plane of the tile: per-env plane from HBM (quirk Q1 games) or the static scenery
-  for (int b = lane; b < nenv * cells; b += 32) {
-    const int e = b / cells;
-    plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
+  if (H.has_dynbd && P.vec) {
+    const uint4* s16 = reinterpret_cast<const uint4*>(P.dynbd + env0 * cells);
+    uint4* d16 = reinterpret_cast<uint4*>(plane);
+    for (int k = lane; k < nenv * cells / 16; k += 32) d16[k] = s16[k];
+  } else {
+    const uint32_t inv_cells = div_inverse((uint32_t)cells);
+    for (int b = lane; b < nenv * cells; b += 32) {
+      const int e = (int)fast_div((uint32_t)b, inv_cells);
+      plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
+    }
   }
   __syncwarp();
 
@@ -361,7 +554,7 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
         dc = 0.0f;
         f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
       } else {
-        generic_env_step(X, a, dyn[lane], s_w[warp].prev[lane], plane + lane * cells, rw, f, dc);
+        generic_env_step(X, a, dyn[lane], W.prev[lane], plane + lane * cells, rw, f, dc);
       }
       if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
         const uint32_t steps = ts + 1u;
@@ -390,19 +583,8 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
     }
     __syncwarp();  // entity state and backdrop stamps of the warp's envs are visible
 
-    compose_warp(X, dyn, plane, out, nenv, tile_bytes16, lane);
-
-    // ---- 2c: stream the boards out ----
-    uint8_t* dst = P.board + row * cells;
-    const int nbytes = nenv * cells;
-    if (P.vec) {
-      const uint4* s16 = reinterpret_cast<const uint4*>(out);
-      uint4* d16 = reinterpret_cast<uint4*>(dst);
-#pragma unroll 4
-      for (int k = lane; k < nbytes / 16; k += 32) __stcs(d16 + k, s16[k]);
-    } else {
-      for (int b = lane; b < nbytes; b += 32) dst[b] = out[b];
-    }
+    // ---- phases 1b, 1c, 2: compose the boards and stream them out ----
+    compose_warp(X, W, nenv, P.board + row * cells, fast, lane);
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
@@ -410,11 +592,19 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
       if (reset_me)
         for (int z = 0; z < H.n_ent; ++z)
           if (H.ent[z].dyn_slot != 0xFF) dyn[lane][H.ent[z].dyn_slot] = H.ent[z].init_state;
-      while (rmask) {  // the plane of each finished env goes back to the its_showtime backdrop
-        const int e = __ffs(rmask) - 1;
-        rmask &= rmask - 1;
-        uint8_t* pl = plane + e * cells;
-        for (int b = lane; b < cells; b += 32) pl[b] = X.backdrop[b];
+      if (H.has_dynbd) {
+        while (rmask) {  // the plane of each finished env goes back to the its_showtime backdrop
+          const int e = __ffs(rmask) - 1;
+          rmask &= rmask - 1;
+          uint8_t* pl = plane + e * cells;
+          if ((cells & 3) == 0) {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(X.backdrop);
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(pl);
+            for (int b = lane; b < cells / 4; b += 32) d32[b] = s32[b];
+          } else {
+            for (int b = lane; b < cells; b += 32) pl[b] = X.backdrop[b];
+          }
+        }
       }
     }
     __syncwarp();
@@ -427,8 +617,15 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
       P.ret[env] = rt;
     }
   }
-  if (H.has_dynbd)
-    for (int b = lane; b < nenv * cells; b += 32) P.dynbd[env0 * cells + b] = plane[b];
+  if (H.has_dynbd) {
+    if (P.vec) {
+      const uint4* s16 = reinterpret_cast<const uint4*>(plane);
+      uint4* d16 = reinterpret_cast<uint4*>(P.dynbd + env0 * cells);
+      for (int k = lane; k < nenv * cells / 16; k += 32) d16[k] = s16[k];
+    } else {
+      for (int b = lane; b < nenv * cells; b += 32) P.dynbd[env0 * cells + b] = plane[b];
+    }
+  }
   if (H.track) {
     const double cnt = warp_sum((double)ep_cnt), len = warp_sum((double)ep_len);
     const double sum = warp_sum(ep_sum), sumsq = warp_sum(ep_sumsq);
@@ -462,18 +659,16 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
   if (env0 >= P.n) return;
   const int nenv = (int)min((int64_t)G, P.n - env0);
-  const int tile_bytes16 = (G * cells + 15) / 16;
-  uint8_t* plane = smem + H.blob_bytes + (size_t)warp * 2 * tile_bytes16 * 16;
-  uint8_t* out = plane + tile_bytes16 * 16;
+  const WarpMem W = warp_mem(H, smem, s_w, warp, lane);
   if (lane < nenv)
-    for (int d = 0; d < H.n_dyn; ++d) s_w[warp].dyn[lane][d] = P.dyn[(int64_t)d * P.n + env0 + lane];
+    for (int d = 0; d < H.n_dyn; ++d) W.dyn[lane][d] = P.dyn[(int64_t)d * P.n + env0 + lane];
+  const uint32_t inv_cells = div_inverse((uint32_t)cells);
   for (int b = lane; b < nenv * cells; b += 32) {
-    const int e = b / cells;
-    plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
+    const int e = (int)fast_div((uint32_t)b, inv_cells);
+    W.plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
   }
   __syncwarp();
-  compose_warp(X, s_w[warp].dyn, plane, out, nenv, tile_bytes16, lane);
-  for (int b = lane; b < nenv * cells; b += 32) P.board[env0 * cells + b] = out[b];
+  compose_warp(X, W, nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
@@ -492,17 +687,25 @@ GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
   return P;
 }
 
-size_t gen_tile_bytes(const cx_game* g) {
-  return ((size_t)g->gh.tile_envs * g->gh.cells + 15) / 16 * 16;
+size_t gen_warp_bytes(const cx_game* g) {
+  const size_t tile = ((size_t)g->gh.tile_envs * g->gh.cells + 15) / 16 * 16;
+  const size_t lin = ((size_t)g->gh.tile_envs * g->gh.n_lin * (g->gh.mask_words + 1) * 4 + 15) / 16 * 16;
+  return tile + lin;
 }
 // warps per CTA: share the staged tables between warps while keeping a CTA below ~100 KB of shared memory
 int gen_warps_per_cta(const cx_game* g) {
   int w = NT / 32;
-  while (w > 1 && (size_t)g->gh.blob_bytes + (size_t)w * 2 * gen_tile_bytes(g) > 100 * 1024) w >>= 1;
+  while (w > 1 && (size_t)g->gh.blob_bytes + (size_t)w * gen_warp_bytes(g) > 100 * 1024) w >>= 1;
   return w;
 }
 size_t gen_smem_bytes(const cx_game* g, int wpc) {
-  return (size_t)g->gh.blob_bytes + (size_t)wpc * 2 * gen_tile_bytes(g);
+  return (size_t)g->gh.blob_bytes + (size_t)wpc * gen_warp_bytes(g);
+}
+// 16-byte chunks: every tile and every [T, n] board row starts 16-byte aligned and holds whole chunks
+bool gen_vec_ok(const cx_game* g, int64_t n, const void* d_board) {
+  const int G = g->gh.tile_envs;
+  return ((int64_t)G * g->gh.cells % 16 == 0) && (n % G == 0) && ((n * g->gh.cells) % 16 == 0) &&
+         (reinterpret_cast<uintptr_t>(d_board) & 15) == 0;
 }
 
 int configure_once() {
@@ -533,9 +736,7 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   P.board = d_board;
   P.T = T;
   const int G = g->gh.tile_envs;
-  // vector stores need every tile and every [T, n] row to start 16-byte aligned and hold whole chunks
-  P.vec = ((int64_t)G * g->gh.cells % 16 == 0) && (n % G == 0) && ((n * g->gh.cells) % 16 == 0) &&
-          (reinterpret_cast<uintptr_t>(d_board) & 15) == 0;
+  P.vec = gen_vec_ok(g, n, d_board);
   const int wpc = gen_warps_per_cta(g);
   const int64_t warps = (n + G - 1) / G;
   const int64_t grid = (warps + wpc - 1) / wpc;
@@ -553,6 +754,7 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
 int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s) {
   GenParams P = make_params(g, const_cast<void*>(d_state), n);
   P.board = d_board;
+  P.vec = gen_vec_ok(g, n, d_board);
   const int G = g->gh.tile_envs;
   const int wpc = gen_warps_per_cta(g);
   const int64_t warps = (n + G - 1) / G;

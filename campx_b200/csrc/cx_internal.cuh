@@ -20,6 +20,7 @@
 #define CX_GEN_TILE_ENVS 32      // max envs per CTA in the generic kernels
 #define CX_GEN_CTA_THREADS 128
 #define CX_MAX_DYN 8             // moving entities in the generic path
+#define CX_MAX_LIN 4             // per-env mask bitsets the fast composer keeps in shared memory
 
 // ---- per-action engine directives, identical for both paths (plot.py:161-257, engine.py:285-290) ----
 struct CxActionTable {
@@ -56,7 +57,9 @@ struct CxGenEntity {
   uint8_t ch, kind, visible, group;
   uint8_t chidx, dyn_slot, stamps, watch;  // watch: z-index or 0xFF
   uint32_t blockers;
-  uint8_t reward_actions, rank, pad0, pad1;
+  uint8_t reward_actions, rank;
+  uint8_t lin_slot;         // mask entities: index of the per-env linear bitset (0xFF: the static mask is used as is)
+  uint8_t pad1;
   int8_t dr[CX_MAX_ACTIONS], dc[CX_MAX_ACTIONS];
   float step_reward[CX_MAX_ACTIONS];
   uint16_t init_state;      // cell / linear offset after its_showtime
@@ -78,7 +81,16 @@ struct CxGenHeader {
   int32_t off_entry;        // f32 [n_ent][n_actions][n_chars]
   int32_t off_rc;           // u16 [cells]  (row << 8 | col)
   int32_t off_rowbits;      // u64 [n_ent][rows]  static masks as one bitset per board row (cols <= 64), else -1
-  int32_t tile_envs;        // envs per CTA (power of two <= 32, sized so that two board tiles fit shared memory)
+  int32_t tile_envs;        // envs per warp (power of two <= 32; the warp's backdrop-plane tile lives in shared memory)
+  int32_t n_lin;            // per-env linear bitsets: rolling masks, and static masks with a visible point entity above
+  int32_t fast_compose;     // the bitset composer applies (else: per-cell painter's algorithm)
+  // the composer's view of the z-order, so that its loops touch one word per entity:
+  int32_t n_masks, n_points;
+  uint32_t mask_prog[CX_MAX_ENTITIES];   // mask entities back to front: z | ch << 8 | lin_slot << 16 | kind << 24
+  uint32_t point_prog[CX_MAX_DYN];       // visible one-cell entities back to front: z | ch << 8 | dyn_slot << 16 | stamps << 24
+  uint32_t point_holes[CX_MAX_DYN];      // bit s: per-env mask bitset s lies below the point entity (its cell is punched out)
+  int32_t off_colroll[CX_MAX_LIN];       // per lin slot of a rolling drape: u32 [cols][mask_words + 1], the static mask
+                                         // rolled right by dc columns, as linear bitsets; -1: not tabulated
   int32_t blob_bytes;
   CxActionTable act;
 };
