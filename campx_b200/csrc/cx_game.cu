@@ -496,6 +496,10 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     if (per_env) g.lin_slot = (uint8_t)(n_lin < 255 ? n_lin : 254), ++n_lin;
   }
   H->n_lin = n_lin;
+  H->fast_compose = (n_lin <= CX_MAX_LIN && !wide_roll && cells >= 16) ? 1 : 0;
+  if (const char* dbg = getenv("CX_GEN_SLOW")) {  // development knob: force the per-cell composer
+    if (atoi(dbg)) H->fast_compose = 0;
+  }
   for (int i = 0; i < CX_MAX_LIN; ++i) H->off_colroll[i] = -1;
   if (H->fast_compose) {
     // A roll by (dr, dc) is a column roll inside every board row followed by a rotation of the linear
@@ -530,10 +534,6 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
       H->point_prog[H->n_points++] =
           (uint32_t)z | ((uint32_t)g.ch << 8) | ((uint32_t)g.dyn_slot << 16) | ((uint32_t)(g.stamps ? 1 : 0) << 24);
     }
-  }
-  H->fast_compose = (n_lin <= CX_MAX_LIN && !wide_roll && cells >= 16) ? 1 : 0;
-  if (const char* dbg = getenv("CX_GEN_SLOW")) {  // development knob: force the per-cell composer
-    if (atoi(dbg)) H->fast_compose = 0;
   }
   // envs per warp: one plane tile of at most 8 KB per warp keeps >= 20 warps per SM resident
   int tile = 32;

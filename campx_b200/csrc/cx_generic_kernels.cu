@@ -365,14 +365,13 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
   return m;
 }
 
+// branch-free on purpose: the chunk loop is straight-line code, so two chunks per lane interleave (ILP)
 __device__ __forceinline__ void overlay16(uint4& v, uint32_t slice, uint32_t ch4) {
-  if (slice) {
-    uint32_t m;
-    m = expand4(slice & 15u);         v.x = (v.x & ~m) | (ch4 & m);
-    m = expand4((slice >> 4) & 15u);  v.y = (v.y & ~m) | (ch4 & m);
-    m = expand4((slice >> 8) & 15u);  v.z = (v.z & ~m) | (ch4 & m);
-    m = expand4(slice >> 12);         v.w = (v.w & ~m) | (ch4 & m);
-  }
+  uint32_t m;
+  m = expand4(slice & 15u);         v.x = (v.x & ~m) | (ch4 & m);
+  m = expand4((slice >> 4) & 15u);  v.y = (v.y & ~m) | (ch4 & m);
+  m = expand4((slice >> 8) & 15u);  v.z = (v.z & ~m) | (ch4 & m);
+  m = expand4(slice >> 12);         v.w = (v.w & ~m) | (ch4 & m);
 }
 
 // bits [o, o+16) of a linear bitset (one word of slack behind the last is readable)
@@ -394,17 +393,25 @@ __device__ __forceinline__ void compose_stream(const Ctx& X, const WarpMem& W, i
   uint32_t prog[HOIST];
 #pragma unroll
   for (int i = 0; i < HOIST; ++i) prog[i] = i < n_masks ? H.mask_prog[i] : 0u;
+  uint32_t ch4[HOIST], lsw[HOIST];
+  const uint32_t* sbits[HOIST];
+#pragma unroll
+  for (int i = 0; i < HOIST; ++i) {
+    const uint32_t ls = (prog[i] >> 16) & 0xFF;
+    ch4[i] = ((prog[i] >> 8) & 0xFF) * 0x01010101u;
+    lsw[i] = ls * lw;
+    sbits[i] = ls == 0xFF ? X.masks + (prog[i] & 0xFF) * mw : nullptr;  // shared static mask, or per-env bitset
+  }
+#pragma unroll 2
   for (int k = lane; k < nchunks; k += 32) {
     const uint32_t b = 16u * k, e = fast_div(b, inv_cells), o = b - e * cells;
-    if (o + 16u > cells) continue;  // straddles two envs: pass B
     uint4 v = p16[k];
     const uint32_t* lin_e = W.lin + e * env_words;
 #pragma unroll
     for (int i = 0; i < HOIST; ++i) {
       if (i < n_masks) {
-        const uint32_t ls = (prog[i] >> 16) & 0xFF;
-        const uint32_t* bits = ls == 0xFF ? X.masks + (prog[i] & 0xFF) * mw : lin_e + ls * lw;
-        overlay16(v, slice16(bits, o), ((prog[i] >> 8) & 0xFF) * 0x01010101u);
+        const uint32_t* bits = sbits[i] ? sbits[i] : lin_e + lsw[i];
+        overlay16(v, slice16(bits, o), ch4[i]);
       }
     }
     for (int i = HOIST; i < n_masks; ++i) {
@@ -412,7 +419,7 @@ __device__ __forceinline__ void compose_stream(const Ctx& X, const WarpMem& W, i
       const uint32_t* bits = ls == 0xFF ? X.masks + (pg & 0xFF) * mw : lin_e + ls * lw;
       overlay16(v, slice16(bits, o), ((pg >> 8) & 0xFF) * 0x01010101u);
     }
-    __stcs(d16 + k, v);
+    if (o + 16u <= cells) __stcs(d16 + k, v);  // else: the chunk straddles two envs -> pass B
   }
   // pass B: the chunk across the boundary between env i-1 and env i (lane i), if there is one
   if ((cells & 15u) != 0) {
