@@ -30,6 +30,9 @@
 #ifndef CX_OPT_PDL
 #define CX_OPT_PDL 1   // programmatic dependent launch: the next launch's prologue overlaps this launch's tail
 #endif
+#ifndef CX_OPT_ACT2
+#define CX_OPT_ACT2 1  // action loads run two steps ahead of their use
+#endif
 #ifndef CX_OPT_TMA
 #define CX_OPT_TMA 1   // board tiles leave shared memory as one cp.async.bulk (UBLKCP) per warp and step
 #endif
@@ -265,9 +268,14 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
     }
     return ld_u8x4<VEC>(P.actions, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, 0);
   };
-  uint32_t actq[QUADS];
+  // actions are fetched two steps ahead: a load issued in step t is consumed in step t+2, so its latency
+  // (microseconds behind the write streams) never stalls the warp
+  uint32_t actq[QUADS], actn[QUADS];
 #pragma unroll
-  for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, 0);
+  for (int j = 0; j < QUADS; ++j) {
+    actq[j] = quad_actions(j, 0);
+    actn[j] = (CX_OPT_ACT2 && P.T > 1) ? quad_actions(j, 1) : 0u;
+  }
 
   constexpr bool TMA = VEC && (CX_OPT_TMA != 0);
   const uint64_t l2pol = l2_evict_first_policy();
@@ -335,10 +343,14 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
         st_u8x4<VEC>(P.flags, row + el, row_end, fl);
       }
     }
-    // next step's actions: issue the loads before touching the tile so their latency is hidden
-    if (t + 1 < P.T) {
 #pragma unroll
-      for (int j = 0; j < QUADS; ++j) actq[j] = quad_actions(j, t + 1);
+    for (int j = 0; j < QUADS; ++j) {
+#if CX_OPT_ACT2
+      actq[j] = actn[j];
+      if (t + 2 < P.T) actn[j] = quad_actions(j, t + 2);
+#else
+      if (t + 1 < P.T) actq[j] = quad_actions(j, t + 1);
+#endif
     }
     if (TMA) {  // the previous step's bulk store must have read the tile before it is modified
       if (lane == 0) bulk_wait_read();
