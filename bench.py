@@ -90,6 +90,18 @@ def cpu_reference_rate(steps, warm, budget_s, cores=None):
     return total / slowest, cores, sample, slowest
 
 
+def workload_config(envs, world, chunk):
+    """`config` of the JSON line; identical for both arms (the reference arm times a bounded sample of it)."""
+    per_step = 1 + 4 + 1 + 25
+    return {"workload": "boat_race 5x5 (examples/worlds.py == reference examples/boat_race.py), "
+                        "2^20 envs per GPU, uniform random actions, episode limit 100 + auto reset",
+            "envs_per_gpu": envs, "total_envs": world * envs, "fused_steps_per_launch": chunk,
+            "observation_contract": "board u8[25] + reward f32 + flags u8 per env-step",
+            "l2_policy": "outputs larger than L2: each launch writes %.0f MB, two alternating output "
+                         "buffers" % (envs * chunk * (per_step - 1) / 1e6),
+            "parallelism": "env-sharded x%d, no step-path collective" % world}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -100,8 +112,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": elapsed * 1e3 / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "boat_race 5x5, uniform random actions, episode limit 100 (CPU sample of the "
-                               "2^20-env/GPU workload)", "envs_per_gpu": args.envs},
+        "config": workload_config(args.envs, max(1, args.gpus), max(1, args.chunk)),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -310,13 +321,7 @@ def run_ours(args):
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": max(W, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "boat_race 5x5 (examples/worlds.py == reference examples/boat_race.py), "
-                                   "2^20 envs per GPU, uniform random actions, episode limit 100 + auto reset",
-                       "envs_per_gpu": n, "total_envs": world * n, "fused_steps_per_launch": T,
-                       "observation_contract": "board u8[25] + reward f32 + flags u8 per env-step",
-                       "l2_policy": "outputs larger than L2: each launch writes %.0f MB, two alternating output "
-                                    "buffers" % (n * T * (per_step - 1) / 1e6),
-                       "parallelism": "env-sharded x%d, no step-path collective" % world},
+            "config": workload_config(n, world, T),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "return_stats": summary,
         }
@@ -328,6 +333,9 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; stdout carries ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)

@@ -110,6 +110,7 @@ PROTOTYPES = {
     "cx_step": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "cx_rollout": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "cx_rollout_synth": (ctypes.c_int, [_P, _P, _I64, _I32, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P]),
+    "cx_rollout_observations": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "cx_layers_from_board": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_layers_from_board_f32": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_onehot_to_index": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _P]),

@@ -1,0 +1,262 @@
+// Single-agent fast path with the FULL observation: fused T-step Engine.play() that writes, per env-step,
+// the board AND the layered board (campx/rendering.py:181-219: layers[ch] = board == ord(ch), stacked in
+// canonical channel order) -- the tensor the reference's RL loops feed to the policy
+// (examples/actor_critic.py:147,173: state = board.layered_board.view(-1).float()).
+//
+// Why a second kernel: deriving the layers from a finished board (cx_layers_from_board) re-reads the board
+// from HBM and costs a second launch; here they leave the SM together.  Algorithmic bytes per env-step
+// (boat_race): action 1 + reward 4 + flags 1 + board 25 + layered 7*25 = 206 B.
+//
+// B200 mapping.  The layered board of a single-agent game is, like its board, a static image plus the
+// agent: moving the agent from cell `was` to cell `show` changes four bytes
+//     layer[agent][was] = 0, layer[base(was)][was] = 1, layer[base(show)][show] = 0, layer[agent][show] = 1
+// so one WARP keeps the boards (32 x cells bytes) and layered boards (32 x chars x cells bytes) of 32
+// consecutive envs in shared memory for all T steps, lane = env, pokes 2 + 4 bytes per env-step and hands
+// both tiles to the TMA engine: two cp.async.bulk (UBLKCP) stores per warp and step, 800 B + 5600 B for
+// boat_race, contiguous in HBM because the outputs are env-major.  Rewards / flags / actions are one
+// 128 B / 32 B / 32 B transaction per warp.  The step itself is the same (action, cell) table lookup as
+// k_agent_rollout (cx_agent_kernels.cu), so the two kernels cannot disagree on the game rules.
+#include "cx_agent_common.cuh"
+
+namespace {
+
+struct ObsParams {
+  CxAgentHeader h;
+  const uint8_t* blob;
+  uint8_t* cell;
+  uint16_t* tstep;
+  float* ret;
+  double* stats;
+  const uint8_t* actions;  // [T, n]
+  float* reward;           // [T, n]
+  float* discount;         // [T, n] or null
+  uint8_t* flags;          // [T, n]
+  uint8_t* board;          // [T, n, cells]
+  uint8_t* layered;        // [T, n, chars, cells]
+  int64_t n;
+  int32_t T;
+};
+
+constexpr int OBS_WARPS = 4;
+constexpr int OBS_THREADS = OBS_WARPS * 32;
+constexpr int OBS_TILE = 32;  // envs per warp: lane = env
+
+template <bool TRACK>
+__global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_constant__ ObsParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const CxAgentHeader& H = P.h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cells = H.cells, lay_bytes = H.n_chars * H.cells;
+
+  asm volatile("griddepcontrol.launch_dependents;");
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < H.blob_bytes_ext / 16; i += OBS_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();  // the only block barrier
+
+  const int64_t env0 = ((int64_t)blockIdx.x * OBS_WARPS + warp) * OBS_TILE;
+  if (env0 >= P.n) return;
+  const int64_t n = P.n, env = env0 + lane;
+
+  const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
+  const float* __restrict__ s_tr = reinterpret_cast<const float*>(smem + H.off_tr);
+  const float* __restrict__ s_td = reinterpret_cast<const float*>(smem + H.off_td);
+  const uint8_t* __restrict__ s_basech = smem + H.off_basech;
+  const uint8_t* __restrict__ s_shown = smem + H.off_shown;
+  const uint8_t* __restrict__ s_basek = smem + H.off_basek;
+  const uint8_t* __restrict__ s_baselay = smem + H.off_baselay;
+  const uint32_t stride = H.stride, n_actions = H.n_actions, agent_char = H.agent_char, agent_k = H.agent_k;
+  const uint32_t none = cells;
+  const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
+  const bool auto_reset = H.auto_reset != 0, want_discount = P.discount != nullptr;
+
+  // per warp: [board tile 32*cells][layered tile 32*chars*cells], both multiples of 16 bytes
+  uint8_t* wbase = smem + H.blob_bytes_ext + (size_t)warp * OBS_TILE * (cells + lay_bytes);
+  uint8_t* btile = wbase;
+  uint8_t* ltile = wbase + OBS_TILE * cells;
+  for (int k = lane; k < OBS_TILE * cells; k += 32) btile[k] = s_basech[k % cells];
+  for (int k = lane; k < OBS_TILE * lay_bytes; k += 32) ltile[k] = s_baselay[k % lay_bytes];
+  __syncwarp();
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  uint8_t* myb = btile + lane * cells;
+  uint8_t* myl = ltile + lane * lay_bytes;
+  auto draw = [&](uint32_t c) {  // paint the agent at visible cell c
+    myb[c] = (uint8_t)agent_char;
+    const uint32_t k = s_basek[c];
+    if (k != 0xFF) myl[k * cells + c] = 0;
+    myl[agent_k * cells + c] = 1;
+  };
+  auto erase = [&](uint32_t c) {  // back to the static scene at cell c
+    myb[c] = s_basech[c];
+    myl[agent_k * cells + c] = 0;
+    const uint32_t k = s_basek[c];
+    if (k != 0xFF) myl[k * cells + c] = 1;
+  };
+
+  uint32_t cell = min((uint32_t)P.cell[env], none);
+  uint32_t drawn = s_shown[cell];
+  if (drawn != none) draw(drawn);
+  uint32_t ts = 0;
+  float rt = 0.0f;
+  if (TRACK) {
+    ts = P.tstep[env];
+    rt = P.ret[env];
+  }
+  LaneStats& stats =
+      reinterpret_cast<LaneStats*>(smem + H.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * (cells + lay_bytes))[tid];
+  if (TRACK) stats.clear();
+
+  const uint64_t l2pol = l2_evict_first_policy();
+  uint32_t act = P.actions[env], act_next = P.T > 1 ? P.actions[n + env] : 0u;
+
+  for (int t = 0; t < P.T; ++t) {
+    const int64_t row = (int64_t)t * n + env0;
+    // ---- phase A: the env's step (same table as k_agent_rollout) ----
+    const uint32_t a = min(act, n_actions);
+    const uint32_t idx = a * stride + cell;
+    uint32_t e = s_tt[idx];
+    float r = s_tr[idx];
+    float dc = want_discount ? s_td[a] : 1.0f;
+    if (TRACK && (ts & CX_OVER_BIT)) {
+      e = cell | (drawn << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+      r = 0.0f;
+      dc = 0.0f;
+    }
+    uint32_t p = e & 0xFF;
+    const uint32_t show = (e >> 8) & 0xFF;
+    uint32_t f = e >> 16;
+    if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
+      const uint32_t steps = ts + 1u;
+      rt += r;
+      if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
+      ts = steps;
+      if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
+        stats.episode(rt, steps);
+        if (auto_reset) {
+          p = H.init_cell;
+          ts = 0;
+          rt = 0.0f;
+        } else {
+          ts |= CX_OVER_BIT;
+        }
+      }
+    }
+    cell = p;
+    __stcs(P.reward + row + lane, r);
+    if (want_discount) __stcs(P.discount + row + lane, dc);
+    P.flags[row + lane] = (uint8_t)f;
+    act = act_next;
+    if (t + 2 < P.T) act_next = P.actions[(int64_t)(t + 2) * n + env];
+
+    // ---- phase B: re-compose both tiles (2 + 4 byte stores when the agent moved) and hand them to TMA ----
+    if (lane == 0) bulk_wait_read();  // the previous step's bulk stores have read the tiles
+    __syncwarp();
+    if (drawn != show) {
+      if (drawn != none) erase(drawn);
+      if (show != none) draw(show);
+      drawn = show;
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store_s2g(P.board + row * cells, btile, (uint32_t)(OBS_TILE * cells), l2pol);
+      bulk_store_s2g(P.layered + row * lay_bytes, ltile, (uint32_t)(OBS_TILE * lay_bytes), l2pol);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read();
+  __syncwarp();
+
+  P.cell[env] = (uint8_t)cell;
+  if (TRACK) {
+    P.tstep[env] = (uint16_t)ts;
+    P.ret[env] = rt;
+    const double cnt = warp_sum((double)stats.cnt), len = warp_sum((double)stats.len);
+    const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
+    const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
+    if (lane == 0) {
+      if (cnt > 0.0) {
+        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
+        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+      }
+      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)OBS_TILE * (double)P.T);
+    }
+  }
+}
+
+size_t obs_smem_bytes(const cx_game* g) {
+  const size_t per_env = (size_t)g->ah.cells * (1 + g->ah.n_chars);
+  return (size_t)g->ah.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env +
+         (g->ah.track ? OBS_THREADS * sizeof(LaneStats) : 0);
+}
+
+template <bool TRACK>
+int launch_obs(const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_obs<TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(OBS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout_obs<TRACK>, P));
+  return CX_OK;
+}
+
+}  // namespace
+
+// The fused kernel needs whole warps of 32 envs, bulk-store alignment (every [T, n, ...] row 16-byte aligned)
+// and both tiles of a CTA in shared memory; everything else goes through cx_rollout + cx_layers_from_board.
+bool cx_agent_obs_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_reward,
+                          const void* d_discount, const void* d_flags, const void* d_board, const void* d_layered) {
+  if (g->path != CX_PATH_AGENT) return false;
+  if (n % OBS_TILE != 0) return false;
+  if (obs_smem_bytes(g) > 200 * 1024) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  (void)d_actions; (void)d_reward; (void)d_discount; (void)d_flags;  // element-wise accesses: no alignment need
+  return al16(d_board) && al16(d_layered);
+}
+
+int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                                float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                                uint8_t* d_layered, cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  uint8_t* base = static_cast<uint8_t*>(d_state);
+  ObsParams P;
+  P.h = g->ah;
+  P.blob = g->d_blob;
+  P.cell = base + L.off_dyn;
+  P.tstep = reinterpret_cast<uint16_t*>(base + L.off_tstep);
+  P.ret = reinterpret_cast<float*>(base + L.off_ret);
+  P.stats = reinterpret_cast<double*>(base + L.off_stats);
+  P.actions = d_actions;
+  P.reward = d_reward;
+  P.discount = d_discount;
+  P.flags = d_flags;
+  P.board = d_board;
+  P.layered = d_layered;
+  P.n = n;
+  P.T = T;
+  const int64_t grid = (n / OBS_TILE + OBS_WARPS - 1) / OBS_WARPS;
+  if (grid > 0x7fffffff) {
+    cx_set_error("cx_rollout_observations: too many environments for one launch");
+    return CX_ERR_INVALID_ARG;
+  }
+  return g->ah.track ? launch_obs<true>(P, (unsigned)grid, obs_smem_bytes(g), s)
+                     : launch_obs<false>(P, (unsigned)grid, obs_smem_bytes(g), s);
+}

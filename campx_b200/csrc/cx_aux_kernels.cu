@@ -109,39 +109,108 @@ __global__ void k_get_episode(const uint16_t* tstep, const float* ret, int32_t* 
 struct CharTable {
   uint8_t ch[CX_MAX_CHARS];
 };
-__global__ void k_layers_u8(const uint8_t* __restrict__ board, uint8_t* __restrict__ out, CharTable ct, int L,
-                            int cells, int64_t n_boards) {
-  const int64_t total = n_boards * L * cells;
-  const int64_t i4 = ((int64_t)blockIdx.x * TB + threadIdx.x) * 4;
-  if (i4 >= total) return;
+// layers / layered_board from finished boards (campx/rendering.py:204-215: layers[ch] = board == ord(ch)).
+// One CTA stages EB boards in shared memory (coalesced 16-byte loads), then every thread produces 16 output
+// BYTES per iteration (u8: 16 cells of one or two channels; f32: 4 cells) and stores them with one STG.128:
+// the (board, channel, cell) coordinates of the first element come from two integer divisions, the rest is
+// incremental.  HBM traffic = cells bytes read + chars * cells * sizeof(OutT) bytes written per board.
+template <typename OutT>
+__global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board, OutT* __restrict__ out, CharTable ct,
+                                               int L, int cells, int EB, int64_t n_boards) {
+  extern __shared__ __align__(16) uint8_t s_board[];
+  __shared__ uint8_t s_ch[CX_MAX_CHARS];
+  constexpr int PER = 16 / (int)sizeof(OutT);   // elements per thread and iteration
+  const int64_t b0 = (int64_t)blockIdx.x * EB;
+  const int nb = (int)min((int64_t)EB, n_boards - b0);
+  const int tile_bytes = nb * cells;
+  const uint8_t* src = board + b0 * cells;
+  if (threadIdx.x < CX_MAX_CHARS) s_ch[threadIdx.x] = ct.ch[threadIdx.x];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint4* s16 = reinterpret_cast<const uint4*>(src);
+    uint4* d16 = reinterpret_cast<uint4*>(s_board);
+    for (int i = threadIdx.x; i < tile_bytes / 16; i += TB) d16[i] = __ldcs(s16 + i);
+    for (int i = (tile_bytes & ~15) + threadIdx.x; i < tile_bytes; i += TB) s_board[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < tile_bytes; i += TB) s_board[i] = src[i];
+  }
+  __syncthreads();
   const int per = L * cells;
-  uint32_t word = 0;
+  const int total = nb * per;                   // output elements of this CTA (< 2^31: EB * per <= 2^23)
+  OutT* dst = out + b0 * per;
+  const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  for (int o = threadIdx.x * PER; o < total; o += TB * PER) {
+    int e = o / per;
+    const int rem = o - e * per;
+    int k = rem / cells, c = rem - k * cells;
+    const uint8_t* brow = s_board + e * cells;
+    uint32_t chk = s_ch[k];
+    if (sizeof(OutT) == 1) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int64_t i = i4 + b;
-    if (i < total) {
-      const int64_t e = i / per;
-      const int rem = (int)(i - e * per);
-      const int k = rem / cells, c = rem - k * cells;
-      word |= (uint32_t)(board[e * cells + c] == ct.ch[k]) << (8 * b);
+      for (int j = 0; j < 16; ++j) {
+        if (o + j < total) w[j >> 2] |= (uint32_t)(brow[c] == chk) << (8 * (j & 3));
+        if (++c == cells) {
+          c = 0;
+          if (++k == L) {
+            k = 0;
+            brow += cells;
+          }
+          chk = s_ch[k];
+        }
+      }
+      uint8_t* d8 = reinterpret_cast<uint8_t*>(dst) + o;
+      if (vec && o + 16 <= total) {
+        __stcs(reinterpret_cast<uint4*>(d8), make_uint4(w[0], w[1], w[2], w[3]));
+      } else {
+        for (int j = 0; j < 16 && o + j < total; ++j) d8[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+      }
+    } else {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (o + j < total) v[j] = brow[c] == chk ? 1.0f : 0.0f;
+        if (++c == cells) {
+          c = 0;
+          if (++k == L) {
+            k = 0;
+            brow += cells;
+          }
+          chk = s_ch[k];
+        }
+      }
+      float* df = reinterpret_cast<float*>(dst) + o;
+      if (vec && o + 4 <= total) {
+        __stcs(reinterpret_cast<float4*>(df), make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+        for (int j = 0; j < 4 && o + j < total; ++j) df[j] = v[j];
+      }
     }
   }
-  if (i4 + 3 < total && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-    *reinterpret_cast<uint32_t*>(out + i4) = word;
-  } else {
-    for (int b = 0; b < 4 && i4 + b < total; ++b) out[i4 + b] = (uint8_t)(word >> (8 * b));
-  }
 }
-__global__ void k_layers_f32(const uint8_t* __restrict__ board, float* __restrict__ out, CharTable ct, int L,
-                             int cells, int64_t n_boards) {
-  const int64_t total = n_boards * L * cells;
-  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
-  if (i >= total) return;
-  const int per = L * cells;
-  const int64_t e = i / per;
-  const int rem = (int)(i - e * per);
-  const int k = rem / cells, c = rem - k * cells;
-  out[i] = board[e * cells + c] == ct.ch[k] ? 1.0f : 0.0f;
+
+// boards per CTA: a multiple of 16 (so that every CTA's input and output tiles start 16-byte aligned) with at
+// most 64 KB of boards in shared memory
+inline int layers_boards_per_cta(int cells) { return cells <= 512 ? 64 : (cells <= 1024 ? 32 : 16); }
+
+template <typename OutT>
+int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, OutT* d_out, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  CharTable ct;
+  memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
+  const int cells = g->info.cells, EB = layers_boards_per_cta(cells);
+  const int64_t grid = (n_boards + EB - 1) / EB;
+  if (grid > 0x7fffffff) {
+    cx_set_error("cx_layers_from_board: too many boards for one launch");
+    return CX_ERR_INVALID_ARG;
+  }
+  const size_t smem = ((size_t)EB * cells + 15) / 16 * 16;
+  k_layers<OutT><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, g->info.n_chars, cells, EB, n_boards);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
 }
 
 __global__ void k_onehot_to_index(const float* __restrict__ onehot, int A, uint8_t* __restrict__ idx,
@@ -295,13 +364,7 @@ extern "C" int cx_layers_from_board(const cx_game* g, const uint8_t* d_board, in
     cx_set_error("cx_layers_from_board: bad argument");
     return CX_ERR_INVALID_ARG;
   }
-  CharTable ct;
-  memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
-  const int64_t total = n_boards * g->info.n_chars * g->info.cells;
-  k_layers_u8<<<blocks_for((total + 3) / 4), TB, 0, (cudaStream_t)stream>>>(d_board, d_layered, ct, g->info.n_chars,
-                                                                            g->info.cells, n_boards);
-  CX_CUDA_OK(cudaGetLastError());
-  return CX_OK;
+  return launch_layers<uint8_t>(g, d_board, n_boards, d_layered, (cudaStream_t)stream);
 }
 
 extern "C" int cx_layers_from_board_f32(const cx_game* g, const uint8_t* d_board, int64_t n_boards, float* d_layered,
@@ -310,13 +373,7 @@ extern "C" int cx_layers_from_board_f32(const cx_game* g, const uint8_t* d_board
     cx_set_error("cx_layers_from_board_f32: bad argument");
     return CX_ERR_INVALID_ARG;
   }
-  CharTable ct;
-  memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
-  const int64_t total = n_boards * g->info.n_chars * g->info.cells;
-  k_layers_f32<<<blocks_for(total), TB, 0, (cudaStream_t)stream>>>(d_board, d_layered, ct, g->info.n_chars,
-                                                                   g->info.cells, n_boards);
-  CX_CUDA_OK(cudaGetLastError());
-  return CX_OK;
+  return launch_layers<float>(g, d_board, n_boards, d_layered, (cudaStream_t)stream);
 }
 
 extern "C" int cx_onehot_to_index(const float* d_onehot, int64_t n, int32_t A, uint8_t* d_index, int32_t* d_bad,

@@ -380,6 +380,21 @@ static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* or
     for (int j = 0; j < 16; ++j) B->bytes[H->off_pat + o * 16 + j] = basech[(o + j) % cells];
   B->pad();
   H->blob_bytes = (int32_t)B->bytes.size();
+  // extension for the observation kernel: which layered-board channel each static cell belongs to
+  const int L = d->n_chars;
+  H->agent_k = char_index(d, ag.character);
+  H->off_basek = B->reserve(S);
+  for (int c = 0; c <= cells; ++c) {
+    const int k = c < cells ? char_index(d, basech[c]) : -1;
+    B->bytes[H->off_basek + c] = (uint8_t)(k < 0 ? 0xFF : k);
+  }
+  H->off_baselay = B->reserve((size_t)L * cells);
+  for (int c = 0; c < cells; ++c) {
+    const int k = char_index(d, basech[c]);
+    if (k >= 0) B->bytes[H->off_baselay + (size_t)k * cells + c] = 1;
+  }
+  B->pad();
+  H->blob_bytes_ext = (int32_t)B->bytes.size();
 }
 
 static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHeader* H, Blob* B) {
@@ -715,6 +730,26 @@ extern "C" int cx_rollout_synth(const cx_game* g, void* d_state, int64_t n, int3
   sy.actions_out = d_actions_out;
   return rollout_common(g, d_state, n, T, nullptr, sy, d_reward, d_discount, d_flags, d_board, stream,
                         "cx_rollout_synth");
+}
+
+extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                                       float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                                       uint8_t* d_layered, void* stream) {
+  if (!d_layered) {
+    cx_set_error("cx_rollout_observations: layered must not be NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (g && d_actions && d_reward && d_flags && d_board && T >= 1 &&
+      cx_agent_obs_applies(g, n, d_actions, d_reward, d_discount, d_flags, d_board, d_layered)) {
+    int rc = check_common(g, d_state, n, "cx_rollout_observations");
+    if (rc) return rc;
+    return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+                                       d_layered, (cudaStream_t)stream);
+  }
+  // any other game or geometry: the step kernel, then the layers from the finished boards
+  int rc = cx_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board, stream);
+  if (rc) return rc;
+  return cx_layers_from_board(g, d_board, (int64_t)T * n, d_layered, stream);
 }
 
 extern "C" int cx_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,

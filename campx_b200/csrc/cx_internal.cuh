@@ -48,7 +48,12 @@ struct CxAgentHeader {
   int32_t off_basech;       // u8  [cells+1]  board character without the agent
   int32_t off_shown;        // u8  [cells+1]  cell where an agent standing on c is drawn (cells: occluded/none)
   int32_t off_pat;          // u8  [cells][16]  base board bytes starting at phase o (wraps): tile fill pattern
-  int32_t blob_bytes;
+  int32_t blob_bytes;       // what k_agent_rollout stages (its shared-memory budget is exact: 7 CTAs per SM)
+  // extension staged only by the observation kernel (k_agent_rollout_obs): layered-board tables
+  int32_t agent_k;          // channel of the agent character in the canonical order
+  int32_t off_basek;        // u8  [cells+1]  channel of basech[c] (0xFF: not a game character)
+  int32_t off_baselay;      // u8  [n_chars][cells]  layered board of the static scene (no agent)
+  int32_t blob_bytes_ext;   // blob_bytes + the extension
   CxActionTable act;        // host copy
 };
 
@@ -141,6 +146,11 @@ struct CxSynth {
 int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                             const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                             uint8_t* d_board, cudaStream_t s);
+int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                                float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                                uint8_t* d_layered, cudaStream_t s);
+bool cx_agent_obs_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_reward,
+                          const void* d_discount, const void* d_flags, const void* d_board, const void* d_layered);
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                               uint8_t* d_board, cudaStream_t s);

@@ -222,6 +222,27 @@ class Engine(object):
         self._native.rollout(actions, board, reward, flags, discount)
         return board, reward, discount, flags
 
+    def rollout_observations(self, actions, out=None, layered=None):
+        """`rollout()` that also returns the layered board of every step (the full reference Observation).
+
+        Returns (boards [T,N,R,C] uint8, layered [T,N,L,R,C] uint8, rewards, discounts or None, flags).  For
+        single-agent worlds (boat_race, Demo 1-5) boards and layers come out of ONE kernel; other worlds
+        derive the layers from the finished boards.  `layered.view(T, N, -1).float()` is the reference's
+        policy input (examples/actor_critic.py:147,173)."""
+        if not self._showtime:
+            raise RuntimeError('rollout_observations() cannot be called until the Engine is placed in "play mode" '
+                               'via the its_showtime() method')
+        nat = self._native
+        T = actions.shape[0]
+        if out is None:
+            out = nat.alloc_outputs(T)
+        board, reward, flags, discount = out
+        if layered is None:
+            layered = torch.empty((T, self._num_envs, nat.n_chars, self._rows, self._cols), dtype=torch.uint8,
+                                  device=nat.device)
+        nat.rollout_observations(actions, board, layered, reward, flags, discount)
+        return board, layered, reward, discount, flags
+
     def rollout_random(self, n_steps, seed, env_offset=0, t0=0, out=None, actions_out=None):
         """T fused play() calls with uniform random actions drawn inside the kernel (counter-based Philox
         keyed by (seed, env_offset + env, t0 + t): the stream `native.fill_actions` produces)."""

@@ -123,6 +123,24 @@ class NativeGame(object):
             N.check(self._lib.cx_rollout(self._handle, _ptr(self.state), n, T, _ptr(actions), _ptr(reward),
                                          _ptr(discount), _ptr(flags), _ptr(board), _stream()))
 
+    def rollout_observations(self, actions, board, layered, reward, flags, discount=None):
+        """Fused rollout that writes the layered board [T, n, n_chars, rows, cols] next to every board."""
+        n = self.num_envs
+        if actions.dim() != 2:
+            raise ValueError("rollout actions must be [T, num_envs]")
+        T = actions.shape[0]
+        self._check(actions, torch.uint8, (T, n), "actions")
+        self._check(board, torch.uint8, (T, n, self.rows, self.cols), "board")
+        self._check(layered, torch.uint8, (T, n, self.n_chars, self.rows, self.cols), "layered")
+        self._check(reward, torch.float32, (T, n), "reward")
+        self._check(flags, torch.uint8, (T, n), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (T, n), "discount")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_rollout_observations(self._handle, _ptr(self.state), n, T, _ptr(actions),
+                                                      _ptr(reward), _ptr(discount), _ptr(flags), _ptr(board),
+                                                      _ptr(layered), _stream()))
+
     def rollout_synth(self, n_steps, seed, board, reward, flags, discount=None, env_offset=0, t0=0, actions_out=None):
         """Fused rollout with uniform random actions generated inside the kernel (no action bytes read);
         identical to fill_actions(seed, env_offset, t0) + rollout."""

@@ -17,6 +17,8 @@
  *                                          _apply_and_clear_plot :211-293, Plot directives
  *                                          campx/plot.py:121-257)
  *   cx_layers_from_board[_f32]         <-  BaseObservationRenderer.render() campx/rendering.py:181-219
+ *   cx_rollout_observations            <-  Engine.play() returning the full Observation(board, layers,
+ *                                          layered_board)                   campx/rendering.py:29,181-219
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
  *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
@@ -196,6 +198,16 @@ CX_API int cx_rollout(const cx_game* game, void* d_state, int64_t n_envs, int32_
 CX_API int cx_rollout_synth(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps, uint64_t seed,
                      uint64_t env_offset, uint64_t t0, uint8_t* d_actions_out, float* d_reward, float* d_discount,
                      uint8_t* d_flags, uint8_t* d_board, void* stream);
+
+/* cx_rollout that also writes the layered board of every env-step (the whole Observation of
+ * campx/rendering.py:29,181-219; what examples/actor_critic.py:147,173 feeds the policy):
+ *   d_layered [T, n, n_chars, rows*cols] uint8, channel k = (board == chars[k]).
+ * Single-agent games with n a multiple of 32 and 16-byte aligned board/layered buffers run one fused kernel
+ * (no board re-read); everything else runs cx_rollout followed by cx_layers_from_board.  Results are
+ * identical either way. */
+CX_API int cx_rollout_observations(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps,
+                            const uint8_t* d_actions, float* d_reward, float* d_discount, uint8_t* d_flags,
+                            uint8_t* d_board, uint8_t* d_layered, void* stream);
 
 /* layers / layered_board from finished boards (rendering.py:204-215): d_layered [n, n_chars, cells]
  * with channel k = (board == chars[k]).  n_boards may be T*n for rollout buffers. */

@@ -9,6 +9,6 @@ i=0
 for knobs in "$@"; do
   i=$((i+1))
   nvcc $FLAGS $knobs -c cx_agent_kernels.cu -o build/var/agent_$i.o
-  nvcc -shared $ARCH -o ../lib/variants/v$i.so build/cx_game.o build/var/agent_$i.o build/cx_generic_kernels.o build/cx_aux_kernels.o -Xcompiler -fPIC -cudart static
+  nvcc -shared $ARCH -o ../lib/variants/v$i.so build/cx_game.o build/var/agent_$i.o build/cx_agent_obs_kernels.o build/cx_generic_kernels.o build/cx_aux_kernels.o -Xcompiler -fPIC -cudart static
   echo "v$i: $knobs"
 done

@@ -65,3 +65,84 @@ def test_batched_actor_critic_example_runs_on_device():
     assert -1.0 <= history[0][1] <= 2.0
     st = game.episode_stats()
     assert st["episodes"] == 2 * 512 and st["env_steps"] == 2 * 20 * 512
+
+
+def test_vector_env_adapter_matches_oracle():
+    """gym-style reset()/step() over the batched engine: observations in the reference's
+    policy-input encoding, termination/truncation flags and masked resets, env for env against the oracle."""
+    import numpy as np
+    from campx_b200.vector_env import VectorEnv
+    from oracle import campx_oracle as O
+    n, T, limit = 64, 30, 12
+    env = VectorEnv(make_world("boat_race", num_envs=n, max_episode_steps=limit), observation="features")
+    obs = env.reset()
+    assert obs.shape == (n, 175) and obs.dtype == torch.float32 and env.single_observation_shape == (175,)
+    first = O.World("boat_race").first[0]
+    # canonical channel order: sorted by code point; permute the oracle's layers accordingly
+    chars = env.engine.characters
+    enc = lambda o: np.stack([np.asarray(o.layers[c]) for c in chars]).reshape(-1).astype(np.float32)
+    assert np.array_equal(obs[0].cpu().numpy(), enc(first))
+    rng = np.random.Generator(np.random.PCG64(5))
+    acts = rng.integers(0, 5, size=(T, n)).astype(np.uint8)
+    oracles = [O.rollout("boat_race", acts[:, i], rebuild_on_done=True, max_episode_steps=limit) for i in range(n)]
+    for t in range(T):
+        a = torch.from_numpy(acts[t]).cuda()
+        if t % 2:
+            a = torch.nn.functional.one_hot(a.long(), 5).float()
+        obs, reward, terminated, truncated, info = env.step(a)
+        o_np, r_np = obs.cpu().numpy(), reward.cpu().numpy()
+        tr_np, te_np = truncated.cpu().numpy(), terminated.cpu().numpy()
+        for i in range(n):
+            o, rew, dsc, term, trunc, eng = next(oracles[i])
+            assert np.array_equal(o_np[i], enc(o)) and float(rew) == float(r_np[i])
+            assert bool(tr_np[i]) == trunc and bool(te_np[i]) == term
+        assert bool((info["discount"] == 1.0).all()) and not bool(info["reward_is_none"].any())
+    # masked reset: only the selected envs go back to the first frame
+    before = env._encode(env.engine._observation(env.engine._out_board)).clone()
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    obs = env.reset(mask)
+    assert np.array_equal(obs[0].cpu().numpy(), enc(first))
+    assert torch.equal(obs[~mask], before[~mask])
+    # board and layered kinds
+    env2 = VectorEnv(make_world("hello", num_envs=8, max_episode_steps=5), observation="layered")
+    assert env2.reset().shape == (8, 7, 13, 36)
+    o2, r2, te2, tr2, info2 = env2.step(torch.full((8,), 4, dtype=torch.uint8, device="cuda"))   # quit
+    assert bool(te2.all()) and bool(info2["reward_is_none"].all()) and bool((info2["discount"] == 0).all())
+
+
+@pytest.mark.parametrize("world,n,kw", [
+    ("boat_race", 4096, dict(max_episode_steps=10, track_returns=True)),     # fused kernel, time limit + stats
+    ("boat_race", 64, dict()),                                               # fused kernel, no tracking
+    ("demo1", 96, dict(max_episode_steps=7)),                                # agent walks over backdrop '#'
+    ("demo3", 32, dict(max_episode_steps=9, auto_reset=False)),              # frozen envs after the limit
+    ("demo4", 50, dict(max_episode_steps=10)),                               # n % 32 != 0: two-kernel route
+    ("hello", 16, dict(max_episode_steps=6)),                                # generic path: two-kernel route
+])
+def test_rollout_observations_equals_rollout_plus_layers(world, n, kw):
+    """cx_rollout_observations: boards, layered boards, rewards, flags and the state afterwards are identical to
+    cx_rollout + cx_layers_from_board, and the layered boards equal the oracle's Observation.layered_board."""
+    T = 23
+    a = make_world(world, num_envs=n, **kw)
+    b = make_world(world, num_envs=n, **kw)
+    a.its_showtime()
+    b.its_showtime()
+    acts = a.native.fill_actions(T, seed=77)
+    for chunk in (acts[:9], acts[9:]):                                       # two launches: state carries over
+        boards, layered, rewards, discounts, flags = a.rollout_observations(chunk.contiguous())
+        boards2, rewards2, discounts2, flags2 = b.rollout(chunk.contiguous())
+        assert torch.equal(boards, boards2) and torch.equal(rewards, rewards2) and torch.equal(flags, flags2)
+        assert (discounts is None and discounts2 is None) or torch.equal(discounts, discounts2)
+        assert torch.equal(layered, b.native.layers_from_board(boards2))
+    assert torch.equal(a.native.state, b.native.state)
+    # against the oracle (last chunk), channel by channel in canonical order
+    chars = a.characters
+    an, ln = acts.cpu().numpy(), layered.cpu().numpy()
+    limit = kw.get("max_episode_steps", 0)
+    if kw.get("auto_reset", True):
+        for i in (0, n // 2, n - 1):
+            # (oracle observations alias live renderer buffers, like the reference's: compare step by step)
+            for t, frame in enumerate(O.rollout(world, an[:, i], rebuild_on_done=True, max_episode_steps=limit)):
+                if t >= 9:
+                    want = np.stack([np.asarray(frame[0].layers[c]) for c in chars]).astype(np.uint8)
+                    assert np.array_equal(ln[t - 9, i], want), (world, i, t)

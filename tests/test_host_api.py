@@ -180,3 +180,22 @@ def test_shadow_clone_keeps_canvas_backdrop_aliasing(golden_dir):
         sh.play(0)
         boards.append(sh.board.reshape(-1).tolist())
     assert boards == want[1:]
+
+
+def test_vector_env_argument_validation():
+    """campx_b200.vector_env: host-side checks that need no GPU."""
+    from campx_b200.vector_env import VectorEnv
+    from examples.worlds import make_world
+    with pytest.raises(ValueError):
+        VectorEnv(make_world("boat_race", num_envs=8), observation="pixels")
+    with pytest.raises(ValueError):
+        VectorEnv(make_world("boat_race"))                                   # one unbatched env
+    with pytest.raises(ValueError):
+        VectorEnv(make_world("boat_race", num_envs=8, auto_reset=False))
+    env = VectorEnv(make_world("boat_race", num_envs=8), observation="features")
+    assert env.num_envs == 8 and env.num_actions == 5
+    with pytest.raises(RuntimeError):
+        env.step(None)                                                       # reset() first
+    with pytest.raises(RuntimeError):
+        env.single_observation_shape                                         # characters known after reset()
+    assert VectorEnv(make_world("hello", num_envs=2)).single_observation_shape == (13, 36)
