@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=32, help="env-batch steps fused per kernel launch")
     ap.add_argument("--e2e-steps", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--obs-reps", type=int, default=8,
+                    help="launches of the secondary board+layered-board measurement (0: skip it)")
     return ap.parse_args()
 
 
@@ -306,6 +308,35 @@ def run_ours(args):
            "d2h_bytes_per_step": n * (cells + 4 + 1), "steps": E,
            "what": "Engine.play(): pinned-host uint8 actions -> H2D -> cx_step -> D2H of board, reward, flags"}
 
+    # ---- secondary contract (BASELINE config 5's policy input): board + layered board per env-step ----
+    obs_extra = None
+    try:
+        if args.obs_reps <= 0:
+            raise RuntimeError("skipped (--obs-reps 0)")
+        To = 16
+        del outs
+        torch.cuda.empty_cache()
+        o_outs = [game.alloc_rollout(To) for _ in range(2)]
+        o_lay = [torch.empty((To, n, nat.n_chars, 5, 5), dtype=torch.uint8, device=dev) for _ in range(2)]
+        for i in range(3):
+            game.rollout_observations(actions[i % n_act][:To], o_outs[i % 2], o_lay[i % 2])
+        torch.cuda.synchronize()
+        reps = args.obs_reps
+        e0.record()
+        for i in range(reps):
+            game.rollout_observations(actions[i % n_act][:To], o_outs[i % 2], o_lay[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        oms = e0.elapsed_time(e1) / reps
+        ob = 1 + 4 + 1 + cells * (1 + nat.n_chars)
+        obs_extra = {"kernel": "k_agent_rollout_obs<TRACK=true>", "alg_bytes_per_env_step": ob,
+                     "env_steps_per_sec": n * To / (oms * 1e-3), "achieved_gbs": n * To * ob / (oms * 1e-3) / 1e9,
+                     "frac_of_measured_peak": n * To * ob / (oms * 1e-3) / 1e9 / peak, "avg_launch_ms": oms,
+                     "fused_steps_per_launch": To, "what": "board u8[25] + layered board u8[7,25] + reward + flags"}
+        del o_outs, o_lay
+    except Exception as exc:                                     # secondary number: never fail the bench line
+        obs_extra = {"error": repr(exc)}
+
     # ---- episode-return statistics: the one collective of the design (not on the step path) ----
     stats = nat.stats_tensor.clone()
     cxdist.all_reduce_stats(stats)
@@ -323,7 +354,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(n, world, T),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clocks, "return_stats": summary,
+            "clocks": clocks, "return_stats": summary, "observation_contract_kernel": obs_extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

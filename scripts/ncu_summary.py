@@ -2,7 +2,9 @@
 import collections, csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-rep = os.path.join(ROOT, "gpurun_out", "%s_agent_rollout.ncu-rep" % tag)
+kname = sys.argv[2] if len(sys.argv) > 2 else "agent_rollout"     # agent_rollout | agent_obs | generic_rollout
+title = sys.argv[3] if len(sys.argv) > 3 else "kernel k_agent_rollout (bench.py workload)"
+rep = os.path.join(ROOT, "gpurun_out", "%s_%s.ncu-rep" % (tag, kname))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -17,7 +19,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "lts__t_bytes.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__shared_mem_per_block_dynamic",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
-lines = ["# ncu --set full, kernel k_agent_rollout (bench.py workload), %s" % tag, ""]
+lines = ["# ncu --set full, %s, %s" % (title, tag), ""]
 traffic = {}
 for r in rows[2:]:
     name = r[hdr.index("Kernel Name")]
@@ -59,7 +61,10 @@ lines.append(", ".join("%s %.1f%%" % (k[6:], 100 * v / ts) for k, v in sorted(ag
 proof = [o for o in ops if o in ("STG", "LDS", "LDG", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA")]
 lines.append("")
 lines.append("memory/tensor opcodes present: %s (no tensor-core opcodes: nothing on this path is a contraction)" % ", ".join(sorted(proof)))
-open(os.path.join(out_dir, "%s_ncu_agent_rollout.md" % tag), "w").write("\n".join(lines) + "\n")
+open(os.path.join(out_dir, "%s_ncu_%s.md" % (tag, kname)), "w").write("\n".join(lines) + "\n")
+if kname != "agent_rollout":
+    print("\n".join(lines))
+    sys.exit(0)
 
 # launch list (gpu__time_duration per launch of the bench command)
 ll = os.path.join(ROOT, "gpurun_out", "%s_launches.csv" % tag)
