@@ -30,6 +30,9 @@
 #ifndef CX_OPT_PDL
 #define CX_OPT_PDL 1   // programmatic dependent launch: the next launch's prologue overlaps this launch's tail
 #endif
+#ifndef CX_OPT_PF
+#define CX_OPT_PF 2    // L2 prefetch of action rows: 0 none, 1 plain, 2 evict_last
+#endif
 #ifndef CX_OPT_ACT2
 #define CX_OPT_ACT2 1  // action loads run two steps ahead of their use
 #endif
@@ -157,12 +160,20 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
       const int tr = t0 + (lane >> 1);
       if (tr < P.T) {
         const uint8_t* a = P.actions + (int64_t)tr * n + env0 + (lane & 1) * 128;
+#if CX_OPT_PF >= 2
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
+#elif CX_OPT_PF == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
       }
     }
   };
+#if CX_OPT_PF == 3
+  for (int t0 = 0; t0 < P.T; t0 += 16) prefetch_actions(t0);
+#else
   prefetch_actions(0);
   prefetch_actions(16);
+#endif
 
   // the quad of envs a lane owns: actions are read from HBM, or generated (same Philox stream as
   // cx_fill_actions: counter = (global env >> 2, step))
@@ -192,7 +203,9 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * n + env0;  // index of this warp's first env in [T, n] arrays
     const int64_t row_end = (int64_t)(t + 1) * n;
+#if CX_OPT_PF != 3
     if ((t & 15) == 0) prefetch_actions(t + 32);
+#endif
     // ---- phase A (registers and tables only): the step of every env this lane owns ----
     uint32_t shwq[QUADS];  // per env one byte: where the agent is drawn after this step
 #pragma unroll

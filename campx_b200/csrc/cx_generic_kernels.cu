@@ -37,6 +37,10 @@
 
 namespace {
 
+#ifndef CX_GEN_UNROLL
+#define CX_GEN_UNROLL 2   // chunks of the composer loop in flight per lane (ILP)
+#endif
+constexpr int kChunkUnroll = CX_GEN_UNROLL;
 constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
 
@@ -402,7 +406,7 @@ __device__ __forceinline__ void compose_stream(const Ctx& X, const WarpMem& W, i
     lsw[i] = ls * lw;
     sbits[i] = ls == 0xFF ? X.masks + (prog[i] & 0xFF) * mw : nullptr;  // shared static mask, or per-env bitset
   }
-#pragma unroll 2
+#pragma unroll kChunkUnroll
   for (int k = lane; k < nchunks; k += 32) {
     const uint32_t b = 16u * k, e = fast_div(b, inv_cells), o = b - e * cells;
     uint4 v = p16[k];

@@ -176,3 +176,50 @@ def test_invisible_sprite_is_never_painted_or_stamped():
             o, rew, dsc = oracles[i].play(int(acts[t, i]))
             assert np.array_equal(b[t, i], np.asarray(o.board).astype(np.uint8)), (i, t)
     assert not (b == ord('1')).any() and (b == ord('2')).any()
+
+
+def _random_art(rng, rows, cols, p_wall, p_star):
+    cells = rng.random((rows, cols))
+    art = np.full((rows, cols), ' ', dtype='<U1')
+    art[cells < p_wall] = '#'
+    art[(cells >= p_wall) & (cells < p_wall + p_star)] = '*'
+    r, c = int(rng.integers(0, rows)), int(rng.integers(0, cols))
+    art[r, c] = 'A'
+    return [''.join(row) for row in art]
+
+
+@pytest.mark.parametrize("rows,cols,seed", [(3, 3, 1), (4, 7, 2), (5, 5, 3), (8, 12, 4), (6, 16, 5), (10, 12, 6), (9, 20, 7)])
+def test_random_wall_and_treasure_worlds(rows, cols, seed):
+    """Randomly generated boards (walls, first-entry treasures, open toroidal edges) of several sizes:
+    <= 96 cells run on the single-agent fast path, larger ones on the generic kernels.  User-level Walker
+    class vs the oracle's restatement of the Demo 3 agent, frame by frame."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    art = _random_art(rng, rows, cols, 0.25, 0.2)
+    game = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
+                                               '#': things.FixedDrape, '*': things.FixedDrape},
+                             z_order='*A#', num_envs=64)
+    factory = lambda: O.ascii_art_to_game(
+        art, ' ', drapes={'A': (O.AgentDrape, (), dict(variant='demo3')), '#': O.FixedDrape, '*': O.FixedDrape},
+        z_order='*A#')
+    compare(game, factory, lambda a: [int(v) for v in onehot(a)], n=64, T=60, seed=seed)
+    assert game.native.info.path == (1 if rows * cols <= 96 else 2)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_arrow_ring_worlds(seed):
+    """boat_race-style worlds with random arrow bonuses and tolls (float32 reward sums in update order)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    bonus = {ch: [float(v) for v in rng.integers(0, 4, size=5)] for ch in '^>v<'}
+    toll = float(rng.choice([-0.25, 0.0, 0.5]))
+    game = ascii_art_to_game(
+        RING_ART, ' ',
+        drapes={'A': Partial(Walker, walls='#', strict=True), '#': things.FixedDrape,
+                **{ch: Partial(Arrow, bonus=torch.FloatTensor(bonus[ch]), toll=toll) for ch in '^>v<'}},
+        z_order='^>v<A#', update_schedule='A^>v<#', num_envs=48)
+    hover = lambda d: (O.DirectionalHoverRewardDrape, (), dict(dctns=d, base_reward=toll))
+    factory = lambda: O.ascii_art_to_game(
+        O.BOAT_RACE_ART, ' ',
+        drapes={'A': (O.AgentDrape, (), dict(variant='boat_race')), '#': O.FixedDrape,
+                **{ch: hover(bonus[ch]) for ch in '^>v<'}},
+        z_order='^>v<A#', update_schedule='A^>v<#')
+    compare(game, factory, onehot, n=48, T=60, seed=seed)
