@@ -173,7 +173,11 @@ class Engine(object):
         if self._verify:
             self._verify_against_shadow()
         nat = self._native
-        self._out_board, self._out_reward, self._out_flags, self._out_discount = nat.alloc_outputs()
+        # two sets of output buffers, used alternately: the tensors a play() returns stay valid until the play()
+        # AFTER the next one, so a caller can copy step t to the host on a side stream while step t+1 runs
+        self._out_sets = [nat.alloc_outputs(), nat.alloc_outputs()] if self._batched else [nat.alloc_outputs()]
+        self._out_index = 0
+        self._out_board, self._out_reward, self._out_flags, self._out_discount = self._out_sets[0]
         self._ones = None
         nat.render(self._out_board)
         self._game_over = False
@@ -193,6 +197,8 @@ class Engine(object):
             raise RuntimeError('play() was called after the episode handled by this Engine has terminated')
         nat = self._native
         idx = self._action_indices(actions)
+        self._out_index = (self._out_index + 1) % len(self._out_sets)
+        self._out_board, self._out_reward, self._out_flags, self._out_discount = self._out_sets[self._out_index]
         nat.step(idx, self._out_board, self._out_reward, self._out_flags, self._out_discount)
         obs = self._observation(self._out_board)
         if not self._batched:
