@@ -80,6 +80,105 @@ def run(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, l
     return history, game
 
 
+class GraphedRollout(object):
+    """One T-step rollout (observation encoding -> policy -> sample -> Engine.play, T times) captured ONCE as a
+    CUDA graph and replayed per iteration: ~8 kernel launches per env-batch step collapse into one graph
+    launch, which is what a launch-bound inner loop at 4,096 environments needs on a B200.
+
+    The rollout runs under no_grad into static buffers (states, actions, rewards, flags); the learner then
+    re-evaluates the policy on all T*N states in one batched forward pass (the usual A2C/PPO split).
+    """
+
+    def __init__(self, game, policy, steps):
+        self.game, self.policy, self.T = game, policy, int(steps)
+        nat = game.native
+        n, dev = game.num_envs, nat.device
+        self.feat = nat.n_chars * nat.cells
+        self.states = torch.empty((self.T, n, self.feat), dtype=torch.float32, device=dev)
+        self.actions = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
+        self.rewards = torch.empty((self.T, n), dtype=torch.float32, device=dev)
+        self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
+        self.all_envs = torch.ones(n, dtype=torch.uint8, device=dev)
+        self.board = game.reset(self.all_envs).board.clone()   # board the next rollout starts from
+        self.graph = None
+
+    def _body(self):
+        nat, game, n = self.game.native, self.game, self.game.num_envs
+        board = self.board
+        with torch.no_grad():
+            for t in range(self.T):
+                nat.layers_from_board(board, out=self.states[t].view(n, nat.n_chars, nat.rows, nat.cols),
+                                      dtype=torch.float32)
+                probs, _ = self.policy(self.states[t])
+                action = torch.multinomial(probs, 1).squeeze(1)
+                self.actions[t].copy_(action)
+                obs, reward, _ = game.play(self.actions[t])
+                self.rewards[t].copy_(reward)
+                self.flags[t].copy_(game.flags)
+                board = obs.board
+            # a fresh episode for every env, like the reference's make_game() per episode (actor_critic.py:146):
+            # the next rollout's first state is the its_showtime frame (a masked reset keeps the statistics)
+            self.board.copy_(game.reset(self.all_envs).board)
+
+    def capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up off the capture (lazy kernel configuration)
+            self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        return self
+
+    def run(self):
+        if self.graph is None:
+            self._body()
+        else:
+            self.graph.replay()
+        return self.states, self.actions, self.rewards, self.flags
+
+
+def run_graphed(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, log=print, device="cuda",
+                use_graph=True):
+    """Same learner as run(), rollout replayed from a CUDA graph.  Returns (history, game, rollout)."""
+    torch.manual_seed(seed)
+    game = make_world("boat_race", num_envs=num_envs, max_episode_steps=steps, track_returns=True)
+    game.its_showtime()
+    nat = game.native
+    policy = Policy(nat.n_chars * nat.cells).to(device)
+    optimizer = torch.optim.Adam(policy.parameters(), lr=lr)
+    eps = torch.finfo(torch.float32).eps
+    roll = GraphedRollout(game, policy, steps)
+    if use_graph:
+        roll.capture()
+    history = []
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for it in range(iterations):
+        e0.record()
+        states, actions, rewards, flags = roll.run()
+        e1.record()
+        returns = nat.discounted_returns(rewards, flags, gamma)
+        returns = (returns - returns.mean()) / (returns.std() + eps)
+        probs, values = policy(states.view(-1, states.shape[-1]))                  # one batched forward pass
+        log_probs = torch.log(probs.gather(1, actions.view(-1, 1).long()).squeeze(1)).view_as(returns)
+        values = values.view_as(returns)
+        advantage = returns - values.detach()
+        loss = (-log_probs * advantage).mean() + F.smooth_l1_loss(values, returns)
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        e2.record()
+        torch.cuda.synchronize()
+        mean_reward = float(rewards.mean())
+        history.append((float(loss.detach()), mean_reward))
+        log("iter %d  loss %.4f  mean step reward %.4f  rollout %.3e env-steps/s, whole iteration %.3e env-steps/s" % (
+            it, float(loss.detach()), mean_reward, num_envs * steps / (e0.elapsed_time(e1) * 1e-3),
+            num_envs * steps / (e0.elapsed_time(e2) * 1e-3)))
+    return history, game, roll
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--num-envs", type=int, default=4096)
@@ -87,5 +186,11 @@ if __name__ == "__main__":
     ap.add_argument("--iterations", type=int, default=20)
     ap.add_argument("--gamma", type=float, default=0.99)
     ap.add_argument("--seed", type=int, default=543)
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager-batched", "stepwise"],
+                    help="graph: rollout replayed from a CUDA graph; eager-batched: same code without the graph; "
+                         "stepwise: the reference's loop structure (policy forward kept for autograd every step)")
     a = ap.parse_args()
-    run(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed)
+    if a.mode == "stepwise":
+        run(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed)
+    else:
+        run_graphed(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed, use_graph=a.mode == "graph")

@@ -146,3 +146,25 @@ def test_rollout_observations_equals_rollout_plus_layers(world, n, kw):
                 if t >= 9:
                     want = np.stack([np.asarray(frame[0].layers[c]) for c in chars]).astype(np.uint8)
                     assert np.array_equal(ln[t - 9, i], want), (world, i, t)
+
+
+def test_cuda_graph_rollout_is_bit_exact_and_learns_on_device():
+    """The T-step (encode -> policy -> sample -> play) loop captured as a CUDA graph: replaying the recorded
+    actions through a fresh engine's fused rollout reproduces the graph's rewards, flags and states."""
+    from examples.actor_critic_batched import run_graphed
+    n, T = 512, 20
+    history, game, roll = run_graphed(num_envs=n, steps=T, iterations=3, log=lambda *_: None)
+    assert len(history) == 3 and all(np.isfinite(h[0]) for h in history)
+    assert roll.graph is not None
+    # iteration k continued from the state iteration k-1 left behind; replay all three from a fresh start
+    fresh = make_world("boat_race", num_envs=n, max_episode_steps=T, track_returns=True)
+    fresh.its_showtime()
+    # the graph's last iteration: recorded actions -> same rewards/flags when re-played after the same prefix
+    # (the prefix is unknown here, but episodes restart every T steps, so every iteration starts from its_showtime)
+    boards, layered, rewards, _, flags = fresh.rollout_observations(roll.actions.clone())
+    assert torch.equal(rewards, roll.rewards) and torch.equal(flags, roll.flags)
+    # the states the policy saw at step t are the layered boards after step t-1 (first: the its_showtime frame)
+    assert torch.equal(roll.states[1:], layered[:-1].view(T - 1, n, -1).float())
+    first = fresh.reset().layered_board.view(n, -1).float()
+    assert torch.equal(roll.states[0], first)
+    assert game.episode_stats()["env_steps"] >= 3 * n * T
