@@ -110,21 +110,52 @@ struct CharTable {
   uint8_t ch[CX_MAX_CHARS];
 };
 // layers / layered_board from finished boards (campx/rendering.py:204-215: layers[ch] = board == ord(ch)).
-// One CTA stages EB boards in shared memory (coalesced 16-byte loads), then every thread produces 16 output
-// BYTES per iteration (u8: 16 cells of one or two channels; f32: 4 cells) and stores them with one STG.128:
-// the (board, channel, cell) coordinates of the first element come from two integer divisions, the rest is
-// incremental.  HBM traffic = cells bytes read + chars * cells * sizeof(OutT) bytes written per board.
+// One CTA stages EB boards in shared memory (coalesced 16-byte loads).  The output is produced four cells at
+// a time: an unaligned 4-byte window of the board row (two LDS.32 + funnel shift) is compared against the
+// channel's character with one SIMD byte compare (__vcmpeq4), and because a 4-cell output word may run over
+// the end of a (board, channel) row, every word is the OR of two such segments.  The (board, channel, cell)
+// coordinates are divided out once per thread and iteration (16 cells) and advanced incrementally.
+// HBM traffic = cells bytes read + chars * cells * sizeof(OutT) bytes written per board.
+struct LayerCursor {
+  int e, k, c;  // board in the tile, channel, cell
+};
+
+// 0/1 bytes of the 4 output cells that start at cursor `cur`; advances the cursor by 4 cells (cells >= 4)
+__device__ __forceinline__ uint32_t layer_word(const uint8_t* s_board, const uint32_t* s_ch4, int L, int cells,
+                                               LayerCursor& cur) {
+  auto window = [&](int byte_off) -> uint32_t {  // 4 board bytes starting at any byte offset of the tile
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s_board) + (byte_off >> 2);
+    return __funnelshift_r(w[0], w[1], (byte_off & 3) * 8);
+  };
+  const int row = cur.e * cells;
+  const int l1 = min(4, cells - cur.c);                       // cells left in this (board, channel) row
+  uint32_t m = __vcmpeq4(window(row + cur.c), s_ch4[cur.k]) & 0x01010101u;
+  cur.c += 4;
+  if (cur.c >= cells) {                                       // the word runs into the next row
+    cur.c -= cells;
+    if (++cur.k == L) {
+      cur.k = 0;
+      ++cur.e;
+    }
+    if (l1 < 4) {
+      const uint32_t keep = (1u << (8 * l1)) - 1u;
+      const uint32_t m2 = __vcmpeq4(window(cur.e * cells), s_ch4[cur.k]) & 0x01010101u;
+      m = (m & keep) | (m2 << (8 * l1));
+    }
+  }
+  return m;
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board, OutT* __restrict__ out, CharTable ct,
                                                int L, int cells, int EB, int64_t n_boards) {
-  extern __shared__ __align__(16) uint8_t s_board[];
-  __shared__ uint8_t s_ch[CX_MAX_CHARS];
-  constexpr int PER = 16 / (int)sizeof(OutT);   // elements per thread and iteration
+  extern __shared__ __align__(16) uint8_t s_board[];          // EB * cells bytes + 32 bytes of slack
+  __shared__ uint32_t s_ch4[CX_MAX_CHARS];
   const int64_t b0 = (int64_t)blockIdx.x * EB;
   const int nb = (int)min((int64_t)EB, n_boards - b0);
   const int tile_bytes = nb * cells;
   const uint8_t* src = board + b0 * cells;
-  if (threadIdx.x < CX_MAX_CHARS) s_ch[threadIdx.x] = ct.ch[threadIdx.x];
+  if (threadIdx.x < CX_MAX_CHARS) s_ch4[threadIdx.x] = ct.ch[threadIdx.x] * 0x01010101u;
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const uint4* s16 = reinterpret_cast<const uint4*>(src);
     uint4* d16 = reinterpret_cast<uint4*>(s_board);
@@ -133,31 +164,22 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
   } else {
     for (int i = threadIdx.x; i < tile_bytes; i += TB) s_board[i] = src[i];
   }
+  if (threadIdx.x < 32) s_board[tile_bytes + threadIdx.x] = 0;  // the 4-byte windows may read past the last board
   __syncthreads();
   const int per = L * cells;
-  const int total = nb * per;                   // output elements of this CTA (< 2^31: EB * per <= 2^23)
+  const int total = nb * per;                   // output elements of this CTA (< 2^31)
   OutT* dst = out + b0 * per;
   const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-  for (int o = threadIdx.x * PER; o < total; o += TB * PER) {
-    int e = o / per;
-    const int rem = o - e * per;
-    int k = rem / cells, c = rem - k * cells;
-    const uint8_t* brow = s_board + e * cells;
-    uint32_t chk = s_ch[k];
-    if (sizeof(OutT) == 1) {
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
+  for (int o = threadIdx.x * 16; o < total; o += TB * 16) {   // 16 cells per thread and iteration
+    LayerCursor cur;
+    cur.e = o / per;
+    const int rem = o - cur.e * per;
+    cur.k = rem / cells;
+    cur.c = rem - cur.k * cells;
+    uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (o + j < total) w[j >> 2] |= (uint32_t)(brow[c] == chk) << (8 * (j & 3));
-        if (++c == cells) {
-          c = 0;
-          if (++k == L) {
-            k = 0;
-            brow += cells;
-          }
-          chk = s_ch[k];
-        }
-      }
+    for (int j = 0; j < 4; ++j) w[j] = layer_word(s_board, s_ch4, L, cells, cur);
+    if (sizeof(OutT) == 1) {
       uint8_t* d8 = reinterpret_cast<uint8_t*>(dst) + o;
       if (vec && o + 16 <= total) {
         __stcs(reinterpret_cast<uint4*>(d8), make_uint4(w[0], w[1], w[2], w[3]));
@@ -165,38 +187,47 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
         for (int j = 0; j < 16 && o + j < total; ++j) d8[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
       }
     } else {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (o + j < total) v[j] = brow[c] == chk ? 1.0f : 0.0f;
-        if (++c == cells) {
-          c = 0;
-          if (++k == L) {
-            k = 0;
-            brow += cells;
-          }
-          chk = s_ch[k];
-        }
-      }
       float* df = reinterpret_cast<float*>(dst) + o;
-      if (vec && o + 4 <= total) {
-        __stcs(reinterpret_cast<float4*>(df), make_float4(v[0], v[1], v[2], v[3]));
+      if (vec && o + 16 <= total) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          __stcs(reinterpret_cast<float4*>(df) + j,
+                 make_float4((float)(w[j] & 1u), (float)((w[j] >> 8) & 1u), (float)((w[j] >> 16) & 1u),
+                             (float)(w[j] >> 24)));
       } else {
-        for (int j = 0; j < 4 && o + j < total; ++j) df[j] = v[j];
+        for (int j = 0; j < 16 && o + j < total; ++j) df[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 1u);
       }
     }
   }
 }
 
+// boards narrower than 4 cells: one element per thread (never on a hot path)
+template <typename OutT>
+__global__ void k_layers_tiny(const uint8_t* __restrict__ board, OutT* __restrict__ out, CharTable ct, int L, int cells,
+                              int64_t n_boards) {
+  const int64_t total = n_boards * L * cells;
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= total) return;
+  const int per = L * cells;
+  const int64_t e = i / per;
+  const int rem = (int)(i - e * per);
+  const int k = rem / cells, c = rem - k * cells;
+  out[i] = (OutT)(board[e * cells + c] == ct.ch[k] ? 1 : 0);
+}
+
 // boards per CTA: a multiple of 16 (so that every CTA's input and output tiles start 16-byte aligned) with at
-// most 64 KB of boards in shared memory
-inline int layers_boards_per_cta(int cells) { return cells <= 512 ? 64 : (cells <= 1024 ? 32 : 16); }
+// most 64 KB of boards in shared memory (cells <= 4096)
+inline int layers_boards_per_cta(int cells) {
+  int eb = (32 * 1024 / cells) / 16 * 16;   // <= 32 KB of boards per CTA (64 KB for the largest boards) ...
+  if (eb > 256) eb = 256;                   // ... in fat CTAs: the per-CTA set-up is amortised over >= 40 KB of output
+  return eb < 16 ? 16 : eb;
+}
 
 template <typename OutT>
 int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, OutT* d_out, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
     configured = true;
   }
   CharTable ct;
@@ -207,7 +238,13 @@ int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, Ou
     cx_set_error("cx_layers_from_board: too many boards for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  const size_t smem = ((size_t)EB * cells + 15) / 16 * 16;
+  if (cells < 4) {
+    const int64_t total = n_boards * g->info.n_chars * cells;
+    k_layers_tiny<OutT><<<blocks_for(total), TB, 0, s>>>(d_board, d_out, ct, g->info.n_chars, cells, n_boards);
+    CX_CUDA_OK(cudaGetLastError());
+    return CX_OK;
+  }
+  const size_t smem = ((size_t)EB * cells + 15) / 16 * 16 + 32;
   k_layers<OutT><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, g->info.n_chars, cells, EB, n_boards);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
