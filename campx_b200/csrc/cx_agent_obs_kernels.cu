@@ -16,7 +16,13 @@
 // boat_race, contiguous in HBM because the outputs are env-major.  Rewards / flags / actions are one
 // 128 B / 32 B / 32 B transaction per warp.  The step itself is the same (action, cell) table lookup as
 // k_agent_rollout (cx_agent_kernels.cu), so the two kernels cannot disagree on the game rules.
+//
+// The same kernel, with the layered board switched off, is the step kernel of single-agent games whose boards
+// are too large for k_agent_rollout's 256-env warp tiles (97..254 cells): at >= 100 bytes per env-step a
+// lane-per-env warp saturates HBM as well.  It also takes ragged batches (N not a multiple of 32) and
+// unaligned buffers (coalesced byte stores instead of the bulk stores) and in-kernel Philox actions.
 #include "cx_agent_common.cuh"
+#include "cx_philox.cuh"
 
 namespace {
 
@@ -32,9 +38,13 @@ struct ObsParams {
   float* discount;         // [T, n] or null
   uint8_t* flags;          // [T, n]
   uint8_t* board;          // [T, n, cells]
-  uint8_t* layered;        // [T, n, chars, cells]
+  uint8_t* layered;        // [T, n, chars, cells] or null
   int64_t n;
   int32_t T;
+  int32_t bulk;            // every [T, n, ...] row of board / layered starts 16-byte aligned: TMA bulk stores
+  int32_t synth;           // actions from cx_philox.cuh instead of `actions`
+  uint64_t seed, env_offset, t0;
+  uint8_t* actions_out;    // synth: [T, n] or null
 };
 
 constexpr int OBS_WARPS = 4;
@@ -59,6 +69,9 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   const int64_t env0 = ((int64_t)blockIdx.x * OBS_WARPS + warp) * OBS_TILE;
   if (env0 >= P.n) return;
   const int64_t n = P.n, env = env0 + lane;
+  const int nenv = (int)min((int64_t)OBS_TILE, n - env0);
+  const bool mine = lane < nenv;
+  const bool layers = P.layered != nullptr;
 
   const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
   const float* __restrict__ s_tr = reinterpret_cast<const float*>(smem + H.off_tr);
@@ -72,45 +85,62 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
   const bool auto_reset = H.auto_reset != 0, want_discount = P.discount != nullptr;
 
-  // per warp: [board tile 32*cells][layered tile 32*chars*cells], both multiples of 16 bytes
-  uint8_t* wbase = smem + H.blob_bytes_ext + (size_t)warp * OBS_TILE * (cells + lay_bytes);
+  // per warp: [board tile 32*cells][layered tile 32*chars*cells (if wanted)], both multiples of 16 bytes
+  const int per_env = cells + (layers ? lay_bytes : 0);
+  uint8_t* wbase = smem + H.blob_bytes_ext + (size_t)warp * OBS_TILE * per_env;
   uint8_t* btile = wbase;
   uint8_t* ltile = wbase + OBS_TILE * cells;
-  for (int k = lane; k < OBS_TILE * cells; k += 32) btile[k] = s_basech[k % cells];
-  for (int k = lane; k < OBS_TILE * lay_bytes; k += 32) ltile[k] = s_baselay[k % lay_bytes];
+  uint8_t* myb = btile + lane * cells;
+  uint8_t* myl = ltile + lane * lay_bytes;
+  for (int c = 0; c < cells; ++c) myb[c] = s_basech[c];       // every lane stages its own env's static scene
+  if (layers)
+    for (int j = 0; j < lay_bytes; ++j) myl[j] = s_baselay[j];
   __syncwarp();
 
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  uint8_t* myb = btile + lane * cells;
-  uint8_t* myl = ltile + lane * lay_bytes;
   auto draw = [&](uint32_t c) {  // paint the agent at visible cell c
     myb[c] = (uint8_t)agent_char;
-    const uint32_t k = s_basek[c];
-    if (k != 0xFF) myl[k * cells + c] = 0;
-    myl[agent_k * cells + c] = 1;
+    if (layers) {
+      const uint32_t k = s_basek[c];
+      if (k != 0xFF) myl[k * cells + c] = 0;
+      myl[agent_k * cells + c] = 1;
+    }
   };
   auto erase = [&](uint32_t c) {  // back to the static scene at cell c
     myb[c] = s_basech[c];
-    myl[agent_k * cells + c] = 0;
-    const uint32_t k = s_basek[c];
-    if (k != 0xFF) myl[k * cells + c] = 1;
+    if (layers) {
+      myl[agent_k * cells + c] = 0;
+      const uint32_t k = s_basek[c];
+      if (k != 0xFF) myl[k * cells + c] = 1;
+    }
   };
 
-  uint32_t cell = min((uint32_t)P.cell[env], none);
+  uint32_t cell = mine ? min((uint32_t)P.cell[env], none) : none;
   uint32_t drawn = s_shown[cell];
   if (drawn != none) draw(drawn);
   uint32_t ts = 0;
   float rt = 0.0f;
-  if (TRACK) {
+  if (TRACK && mine) {
     ts = P.tstep[env];
     rt = P.ret[env];
   }
   LaneStats& stats =
-      reinterpret_cast<LaneStats*>(smem + H.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * (cells + lay_bytes))[tid];
+      reinterpret_cast<LaneStats*>(smem + H.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env)[tid];
   if (TRACK) stats.clear();
 
+  // whole tiles over TMA when the rows are 16-byte aligned and the warp owns 32 envs; else byte stores
+  const bool bulk = P.bulk && nenv == OBS_TILE;
+  auto fetch_action = [&](int t) -> uint32_t {
+    if (!mine || t >= P.T) return 0u;
+    if (P.synth) {
+      const uint32_t a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t, n_actions);
+      if (P.actions_out) P.actions_out[(int64_t)t * n + env] = (uint8_t)a;
+      return a;
+    }
+    return P.actions[(int64_t)t * n + env];
+  };
   const uint64_t l2pol = l2_evict_first_policy();
-  uint32_t act = P.actions[env], act_next = P.T > 1 ? P.actions[n + env] : 0u;
+  uint32_t act = fetch_action(0), act_next = fetch_action(1);
 
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * n + env0;
@@ -126,9 +156,9 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
       dc = 0.0f;
     }
     uint32_t p = e & 0xFF;
-    const uint32_t show = (e >> 8) & 0xFF;
+    const uint32_t show = mine ? (e >> 8) & 0xFF : none;
     uint32_t f = e >> 16;
-    if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
+    if (TRACK && mine && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
       const uint32_t steps = ts + 1u;
       rt += r;
       if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
@@ -144,36 +174,54 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
         }
       }
     }
-    cell = p;
-    __stcs(P.reward + row + lane, r);
-    if (want_discount) __stcs(P.discount + row + lane, dc);
-    P.flags[row + lane] = (uint8_t)f;
+    if (mine) {
+      cell = p;
+      __stcs(P.reward + row + lane, r);
+      if (want_discount) __stcs(P.discount + row + lane, dc);
+      P.flags[row + lane] = (uint8_t)f;
+    }
     act = act_next;
-    if (t + 2 < P.T) act_next = P.actions[(int64_t)(t + 2) * n + env];
+    act_next = fetch_action(t + 2);
 
-    // ---- phase B: re-compose both tiles (2 + 4 byte stores when the agent moved) and hand them to TMA ----
-    if (lane == 0) bulk_wait_read();  // the previous step's bulk stores have read the tiles
-    __syncwarp();
+    // ---- phase B: re-compose the tiles (2 + 4 byte stores when the agent moved) and send them out ----
+    if (bulk) {
+      if (lane == 0) bulk_wait_read();  // the previous step's bulk stores have read the tiles
+      __syncwarp();
+    }
     if (drawn != show) {
       if (drawn != none) erase(drawn);
       if (show != none) draw(show);
       drawn = show;
     }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      bulk_store_s2g(P.board + row * cells, btile, (uint32_t)(OBS_TILE * cells), l2pol);
-      bulk_store_s2g(P.layered + row * lay_bytes, ltile, (uint32_t)(OBS_TILE * lay_bytes), l2pol);
-      bulk_commit();
+    uint8_t* bdst = P.board + row * cells;
+    if (bulk) {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store_s2g(bdst, btile, (uint32_t)(OBS_TILE * cells), l2pol);
+        if (layers) bulk_store_s2g(P.layered + row * lay_bytes, ltile, (uint32_t)(OBS_TILE * lay_bytes), l2pol);
+        bulk_commit();
+      }
+    } else {
+      __syncwarp();
+      for (int k = lane; k < nenv * cells; k += 32) bdst[k] = btile[k];
+      if (layers) {
+        uint8_t* ldst = P.layered + row * lay_bytes;
+        for (int k = lane; k < nenv * lay_bytes; k += 32) ldst[k] = ltile[k];
+      }
+      __syncwarp();
     }
   }
   if (lane == 0) bulk_wait_read();
   __syncwarp();
-
-  P.cell[env] = (uint8_t)cell;
-  if (TRACK) {
-    P.tstep[env] = (uint16_t)ts;
-    P.ret[env] = rt;
+  if (mine) {
+    P.cell[env] = (uint8_t)cell;
+    if (TRACK) {
+      P.tstep[env] = (uint16_t)ts;
+      P.ret[env] = rt;
+    }
+  }
+  if (TRACK) {  // all 32 lanes reduce (lanes without an env contribute empty statistics)
     const double cnt = warp_sum((double)stats.cnt), len = warp_sum((double)stats.len);
     const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
     const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
@@ -186,13 +234,13 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
         atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
         atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
-      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)OBS_TILE * (double)P.T);
+      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
 }
 
-size_t obs_smem_bytes(const cx_game* g) {
-  const size_t per_env = (size_t)g->ah.cells * (1 + g->ah.n_chars);
+size_t obs_smem_bytes(const cx_game* g, bool layers) {
+  const size_t per_env = (size_t)g->ah.cells * (1 + (layers ? g->ah.n_chars : 0));
   return (size_t)g->ah.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env +
          (g->ah.track ? OBS_THREADS * sizeof(LaneStats) : 0);
 }
@@ -220,21 +268,15 @@ int launch_obs(const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
 
 }  // namespace
 
-// The fused kernel needs whole warps of 32 envs, bulk-store alignment (every [T, n, ...] row 16-byte aligned)
-// and both tiles of a CTA in shared memory; everything else goes through cx_rollout + cx_layers_from_board.
-bool cx_agent_obs_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_reward,
-                          const void* d_discount, const void* d_flags, const void* d_board, const void* d_layered) {
-  if (g->path != CX_PATH_AGENT) return false;
-  if (n % OBS_TILE != 0) return false;
-  if (obs_smem_bytes(g) > 200 * 1024) return false;
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  (void)d_actions; (void)d_reward; (void)d_discount; (void)d_flags;  // element-wise accesses: no alignment need
-  return al16(d_board) && al16(d_layered);
+// Shared memory decides whether the lane-per-env kernel can hold a CTA's tiles (boards up to 254 cells always
+// fit without the layered tile; with it, up to about 1500 bytes of layered board per env).
+bool cx_agent_obs_applies(const cx_game* g, bool layers) {
+  return g->path == CX_PATH_AGENT && obs_smem_bytes(g, layers) <= 200 * 1024;
 }
 
 int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                                float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                                uint8_t* d_layered, cudaStream_t s) {
+                                const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                                uint8_t* d_board, uint8_t* d_layered, cudaStream_t s) {
   const CxStateLayout L = cx_layout(g, n);
   uint8_t* base = static_cast<uint8_t*>(d_state);
   ObsParams P;
@@ -252,11 +294,22 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
   P.layered = d_layered;
   P.n = n;
   P.T = T;
-  const int64_t grid = (n / OBS_TILE + OBS_WARPS - 1) / OBS_WARPS;
+  P.synth = synth.on;
+  P.seed = synth.seed;
+  P.env_offset = synth.env_offset;
+  P.t0 = synth.t0;
+  P.actions_out = synth.actions_out;
+  // bulk (TMA) stores: every [T, n, ...] row and every warp tile must start 16-byte aligned
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int64_t lay_bytes = (int64_t)g->ah.n_chars * g->ah.cells;
+  P.bulk = al16(d_board) && (n * g->ah.cells) % 16 == 0 &&
+           (!d_layered || (al16(d_layered) && (n * lay_bytes) % 16 == 0));
+  const int64_t warps = (n + OBS_TILE - 1) / OBS_TILE;
+  const int64_t grid = (warps + OBS_WARPS - 1) / OBS_WARPS;
   if (grid > 0x7fffffff) {
-    cx_set_error("cx_rollout_observations: too many environments for one launch");
+    cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  return g->ah.track ? launch_obs<true>(P, (unsigned)grid, obs_smem_bytes(g), s)
-                     : launch_obs<false>(P, (unsigned)grid, obs_smem_bytes(g), s);
+  const size_t smem = obs_smem_bytes(g, d_layered != nullptr);
+  return g->ah.track ? launch_obs<true>(P, (unsigned)grid, smem, s) : launch_obs<false>(P, (unsigned)grid, smem, s);
 }

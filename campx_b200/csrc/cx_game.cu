@@ -704,9 +704,13 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     cx_set_error("%s: env_offset must be a multiple of 4", who);
     return CX_ERR_INVALID_ARG;
   }
-  if (g->path == CX_PATH_AGENT)
+  if (g->path == CX_PATH_AGENT) {
+    if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS)  // large boards: lane-per-env kernel, board only
+      return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
+                                         nullptr, (cudaStream_t)stream);
     return cx_launch_agent_rollout(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                    (cudaStream_t)stream);
+  }
   return cx_launch_generic_rollout(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                    (cudaStream_t)stream);
 }
@@ -739,11 +743,12 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
     cx_set_error("cx_rollout_observations: layered must not be NULL");
     return CX_ERR_INVALID_ARG;
   }
-  if (g && d_actions && d_reward && d_flags && d_board && T >= 1 &&
-      cx_agent_obs_applies(g, n, d_actions, d_reward, d_discount, d_flags, d_board, d_layered)) {
+  if (g && d_actions && d_reward && d_flags && d_board && T >= 1 && cx_agent_obs_applies(g, true)) {
     int rc = check_common(g, d_state, n, "cx_rollout_observations");
     if (rc) return rc;
-    return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board,
+    CxSynth none;
+    memset(&none, 0, sizeof(none));
+    return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, none, d_reward, d_discount, d_flags, d_board,
                                        d_layered, (cudaStream_t)stream);
   }
   // any other game or geometry: the step kernel, then the layers from the finished boards

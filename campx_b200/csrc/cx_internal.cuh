@@ -13,7 +13,9 @@
 #define CX_EMPTY_CELL16 0xFFFFu  // generic path
 #define CX_OVER_BIT 0x8000u      // in the per-env step counter: episode ended and auto_reset == 0
 
-#define CX_AGENT_MAX_CELLS 96    // fast path: warp tile of 256 envs * cells bytes must fit shared memory
+#define CX_AGENT_TILE_MAX_CELLS 96  // k_agent_rollout: warp tile of 256 envs * cells bytes must fit shared memory
+#define CX_AGENT_MAX_CELLS 254      // single-agent path: cells and "no cell" must fit a byte; boards above
+                                    // CX_AGENT_TILE_MAX_CELLS run on the lane-per-env kernel (cx_agent_obs_kernels.cu)
 #define CX_WARP_TILE_ENVS 256    // envs owned by one warp in the agent kernels (32 lanes x 2 quads x 4)
 #define CX_AGENT_CTA_THREADS 128
 
@@ -147,10 +149,9 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
                             const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                             uint8_t* d_board, cudaStream_t s);
 int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
-                                float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
-                                uint8_t* d_layered, cudaStream_t s);
-bool cx_agent_obs_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_reward,
-                          const void* d_discount, const void* d_flags, const void* d_board, const void* d_layered);
+                                const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                                uint8_t* d_board, uint8_t* d_layered /* or null */, cudaStream_t s);
+bool cx_agent_obs_applies(const cx_game* g, bool layers);
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                               uint8_t* d_board, cudaStream_t s);

@@ -202,9 +202,9 @@ CX_API int cx_rollout_synth(const cx_game* game, void* d_state, int64_t n_envs, 
 /* cx_rollout that also writes the layered board of every env-step (the whole Observation of
  * campx/rendering.py:29,181-219; what examples/actor_critic.py:147,173 feeds the policy):
  *   d_layered [T, n, n_chars, rows*cols] uint8, channel k = (board == chars[k]).
- * Single-agent games with n a multiple of 32 and 16-byte aligned board/layered buffers run one fused kernel
- * (no board re-read); everything else runs cx_rollout followed by cx_layers_from_board.  Results are
- * identical either way. */
+ * Single-agent games run one fused kernel (no board re-read; whole tiles leave over TMA when the buffers and
+ * n * cells are 16-byte aligned); every other game runs cx_rollout followed by cx_layers_from_board.
+ * Results are identical either way. */
 CX_API int cx_rollout_observations(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps,
                             const uint8_t* d_actions, float* d_reward, float* d_discount, uint8_t* d_flags,
                             uint8_t* d_board, uint8_t* d_layered, void* stream);

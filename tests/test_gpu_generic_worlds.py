@@ -188,21 +188,41 @@ def _random_art(rng, rows, cols, p_wall, p_star):
     return [''.join(row) for row in art]
 
 
-@pytest.mark.parametrize("rows,cols,seed", [(3, 3, 1), (4, 7, 2), (5, 5, 3), (8, 12, 4), (6, 16, 5), (10, 12, 6), (9, 20, 7)])
-def test_random_wall_and_treasure_worlds(rows, cols, seed):
-    """Randomly generated boards (walls, first-entry treasures, open toroidal edges) of several sizes:
-    <= 96 cells run on the single-agent fast path, larger ones on the generic kernels.  User-level Walker
-    class vs the oracle's restatement of the Demo 3 agent, frame by frame."""
+@pytest.mark.parametrize("rows,cols,seed,n", [(3, 3, 1, 64), (4, 7, 2, 64), (5, 5, 3, 64), (8, 12, 4, 64), (6, 16, 5, 64),
+                                              (10, 12, 6, 64), (9, 20, 7, 64), (11, 13, 8, 50), (14, 18, 9, 33),
+                                              (13, 21, 10, 64), (16, 17, 11, 40)])
+def test_random_wall_and_treasure_worlds(rows, cols, seed, n):
+    """Randomly generated boards (walls, first-entry treasures, open toroidal edges) of several sizes and batch
+    sizes: <= 96 cells run on k_agent_rollout, 97..254 cells on the lane-per-env single-agent kernel (bulk
+    stores when n * cells is a multiple of 16, byte stores and ragged warps otherwise), larger boards on the
+    generic kernels.  User-level Walker class vs the oracle's restatement of the Demo 3 agent, frame by frame."""
     rng = np.random.Generator(np.random.PCG64(seed))
     art = _random_art(rng, rows, cols, 0.25, 0.2)
     game = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
                                                '#': things.FixedDrape, '*': things.FixedDrape},
-                             z_order='*A#', num_envs=64)
+                             z_order='*A#', num_envs=n)
     factory = lambda: O.ascii_art_to_game(
         art, ' ', drapes={'A': (O.AgentDrape, (), dict(variant='demo3')), '#': O.FixedDrape, '*': O.FixedDrape},
         z_order='*A#')
-    compare(game, factory, lambda a: [int(v) for v in onehot(a)], n=64, T=60, seed=seed)
-    assert game.native.info.path == (1 if rows * cols <= 96 else 2)
+    compare(game, factory, lambda a: [int(v) for v in onehot(a)], n=n, T=60, seed=seed)
+    assert game.native.info.path == (1 if rows * cols <= 254 else 2)
+    # the other entry points on the same world: fused observations and in-kernel random actions
+    a = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
+                                            '#': things.FixedDrape, '*': things.FixedDrape},
+                          z_order='*A#', num_envs=n, max_episode_steps=17, track_returns=True, verify=False)
+    b = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
+                                            '#': things.FixedDrape, '*': things.FixedDrape},
+                          z_order='*A#', num_envs=n, max_episode_steps=17, track_returns=True, verify=False)
+    a.its_showtime()
+    b.its_showtime()
+    acts = torch.empty((40, n), dtype=torch.uint8, device="cuda")
+    boards, rewards, discounts, flags = a.rollout_random(40, seed=5, env_offset=8, actions_out=acts)
+    assert torch.equal(acts, a.native.fill_actions(40, seed=5, env_offset=8))
+    boards2, layered2, rewards2, _, flags2 = b.rollout_observations(acts)
+    assert torch.equal(boards, boards2) and torch.equal(rewards, rewards2) and torch.equal(flags, flags2)
+    assert torch.equal(layered2, b.native.layers_from_board(boards2))
+    assert torch.equal(a.native.state, b.native.state)
+    assert int((flags == 2).sum()) == 2 * n                               # two time limits (17, 34) per env
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
