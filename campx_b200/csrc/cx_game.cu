@@ -495,6 +495,31 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
           if (m[c]) rb[z * R + c / C] |= 1ull << (c % C);
     }
   }
+  // direct composer eligibility (see CxGenHeader::direct)
+  bool direct_ok = cells >= 16 && E > 0;
+  {
+    bool ok = direct_ok;
+    if (const char* dbg = getenv("CX_GEN_DIRECT")) ok = ok && atoi(dbg) != 0;  // development knob
+    if (getenv("CX_GEN_SLOW") && atoi(getenv("CX_GEN_SLOW"))) ok = false;
+    size_t tab_bytes = 0;
+    const int xw = (cells + 16 + 31) / 32 + 1;
+    for (int z = 0; z < E; ++z) {
+      const CxGenEntity& g = H->ent[z];
+      if (g.kind == CX_KIND_STATIC) tab_bytes += (size_t)xw * 4;
+      if (g.kind == CX_KIND_ROLL) tab_bytes += (size_t)C * xw * 4;
+    }
+    if (tab_bytes > 48 * 1024) ok = false;
+    // every visible one-cell entity must be below all masks or above all masks
+    for (int z = 0; z < E && ok; ++z) {
+      const CxGenEntity& g = H->ent[z];
+      if (g.kind == CX_KIND_STATIC || g.kind == CX_KIND_ROLL || !g.visible) continue;
+      int below = 0, above = 0;
+      for (int y = 0; y < E; ++y)
+        if (H->ent[y].kind == CX_KIND_STATIC || H->ent[y].kind == CX_KIND_ROLL) (y < z ? below : above)++;
+      if (below && above) ok = false;
+    }
+    direct_ok = ok;
+  }
   // Mask entities (static / rolling drapes) are composed from linear bitsets.  A rolling mask, and a static
   // mask with a visible one-cell entity above it in z-order (whose cell is punched out of the mask), need a
   // per-env copy in shared memory.
@@ -516,7 +541,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     if (atoi(dbg)) H->fast_compose = 0;
   }
   for (int i = 0; i < CX_MAX_LIN; ++i) H->off_colroll[i] = -1;
-  if (H->fast_compose) {
+  if (H->fast_compose && !direct_ok) {
     // A roll by (dr, dc) is a column roll inside every board row followed by a rotation of the linear
     // bitset by dr * cols bits.  Tabulating the column rolls leaves the kernel only the rotation.
     const int lw = H->mask_words + 1;
@@ -549,6 +574,74 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
       H->point_prog[H->n_points++] =
           (uint32_t)z | ((uint32_t)g.ch << 8) | ((uint32_t)g.dyn_slot << 16) | ((uint32_t)(g.stamps ? 1 : 0) << 24);
     }
+  }
+  // ---- direct composer (see CxGenHeader::direct) --------------------------------------------------
+  {
+    const bool ok = direct_ok;
+    const int xw = (cells + 16 + 31) / 32 + 1;
+    if (ok) {
+      H->direct = 1;
+      H->fast_compose = 1;
+      H->dtab_words = xw;
+      H->n_lin = 0;
+      for (int z = 0; z < E; ++z) H->ent[z].lin_slot = 0xFF;
+      for (int i = 0; i < CX_MAX_LIN; ++i) H->off_colroll[i] = -1;  // (their bytes stay in the blob, unused)
+      for (int i = 0; i < H->n_masks; ++i) {
+        const int z = (int)(H->mask_prog[i] & 0xFF);
+        const bool roll = H->ent[z].kind == CX_KIND_ROLL;
+        H->mask_prog[i] |= 0xFFu << 16;
+        const int rows_in_tab = roll ? C : 1;
+        const int32_t off = B->reserve((size_t)rows_in_tab * xw * 4);
+        H->off_dtab[i] = off;
+        const uint8_t* m = d->masks + (size_t)z * cells;
+        for (int dc = 0; dc < rows_in_tab; ++dc) {
+          uint32_t* w = (uint32_t*)&B->bytes[off + (size_t)dc * xw * 4];
+          auto bit = [&](int cell) { return m[(cell / C) * C + ((cell % C) - dc + C) % C] != 0; };
+          for (int c = 0; c < cells + 16; ++c)
+            if (bit(c % cells)) w[c >> 5] |= 1u << (c & 31);
+        }
+      }
+      for (int i = 0; i < H->n_points; ++i) {
+        const int z = (int)(H->point_prog[i] & 0xFF);
+        int below = 0;
+        for (int y = 0; y < z; ++y)
+          if (H->ent[y].kind == CX_KIND_STATIC || H->ent[y].kind == CX_KIND_ROLL) ++below;
+        H->point_holes[i] = 0;
+        if (below) H->point_prog[i] |= 2u << 24;  // above the masks: stored over the finished board
+      }
+    }
+  }
+  // ---- table-driven step (see CxGenHeader::simple_step) ------------------------------------------------
+  H->n_stampers = 0;
+  for (int z = 0; z < E; ++z)
+    if (H->ent[z].stamps) H->stamper[H->n_stampers++] = (uint16_t)((H->ent[z].ch << 8) | H->ent[z].dyn_slot);
+  {
+    bool simple = !needs_prev && H->n_groups == 1;
+    if (const char* dbg = getenv("CX_GEN_SIMPLE")) simple = simple && atoi(dbg) != 0;  // development knob
+    for (int z = 0; z < E; ++z) {
+      const CxGenEntity& g = H->ent[z];
+      if (g.dyn_slot == 0xFF) continue;
+      H->slot_kind[g.dyn_slot] = g.kind;
+      memcpy(H->slot_dr[g.dyn_slot], g.dr, CX_MAX_ACTIONS);
+      memcpy(H->slot_dc[g.dyn_slot], g.dc, CX_MAX_ACTIONS);
+    }
+    for (int a = 0; a < A; ++a) {
+      bool first_add = true;
+      float summed = 0.0f;
+      for (int i = 0; i < E; ++i) {
+        const cx_entity_desc& e = d->entities[order[i]];
+        if (!(e.reward_actions >> a & 1)) continue;
+        if (first_add) {
+          summed = e.step_reward[a];
+          first_add = false;
+        } else {
+          volatile float s2 = e.step_reward[a] + summed;  // plot.py:211: reward + running sum
+          summed = s2;
+        }
+      }
+      H->simple_reward[a] = summed;
+    }
+    H->simple_step = simple ? 1 : 0;
   }
   // envs per warp: one plane tile of at most 8 KB per warp keeps >= 20 warps per SM resident
   int tile = 32;

@@ -138,10 +138,9 @@ __device__ __forceinline__ uint64_t entity_row(const Ctx& X, const uint16_t* st,
 // rendering.py:150 through the alias of :128 -- sprites behind the first drape paint into the backdrop
 __device__ __forceinline__ void stamp(const Ctx& X, const uint16_t* st, uint8_t* plane) {
   const CxGenHeader& H = *X.H;
-  if (!H.has_dynbd) return;
-  for (int z = 0; z < H.n_ent; ++z) {
-    const CxGenEntity& e = H.ent[z];
-    if (e.stamps) plane[st[e.dyn_slot]] = e.ch;
+  for (int i = 0; i < H.n_stampers; ++i) {
+    const uint32_t sp = H.stamper[i];
+    plane[st[sp & 0xFF]] = (uint8_t)(sp >> 8);
   }
 }
 
@@ -224,6 +223,43 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
   }
   stamp(X, st, plane);  // the render that produces this step's observation
   reward = summed;
+  disc = H.act.discount[a];
+  flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+}
+
+// Engine.play() of a game whose entities never consult the last render (CxGenHeader::simple_step): every
+// dynamic slot moves by its per-action toroidal delta; reward, discount and directives depend on the action
+// alone.  Same results as generic_env_step.
+__device__ __forceinline__ void simple_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint8_t* plane, float& reward,
+                                                uint32_t& flags, float& disc) {
+  const CxGenHeader& H = *X.H;
+  if (a >= (uint32_t)H.n_actions) {
+    reward = 0.0f;
+    disc = 1.0f;
+    flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;
+    return;
+  }
+  const int R = H.rows, C = H.cols;
+  for (int d = 0; d < H.n_dyn; ++d) {
+    const uint32_t s = st[d];
+    const int dr = H.slot_dr[d][a], dc = H.slot_dc[d][a];
+    uint32_t rc;
+    const bool roll = H.slot_kind[d] == CX_KIND_ROLL;
+    if (roll) {
+      rc = s;
+    } else {
+      if (s == CX_EMPTY_CELL16) continue;
+      rc = X.rc[s];
+    }
+    int r = (int)(rc >> 8) + dr, c = (int)(rc & 255u) + dc;  // |dr| < rows, |dc| < cols
+    r += r < 0 ? R : 0;
+    c += c < 0 ? C : 0;
+    r -= r >= R ? R : 0;
+    c -= c >= C ? C : 0;
+    st[d] = (uint16_t)(roll ? (r << 8) | c : r * C + c);
+  }
+  stamp(X, st, plane);
+  reward = H.simple_reward[a];
   disc = H.act.discount[a];
   flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
 }
@@ -369,13 +405,21 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
   return m;
 }
 
-// branch-free on purpose: the chunk loop is straight-line code, so two chunks per lane interleave (ILP)
-__device__ __forceinline__ void overlay16(uint4& v, uint32_t slice, uint32_t ch4) {
+// branch-free on purpose: the chunk loop is straight-line code, so two chunks per lane interleave (ILP).
+// Only bits 0-15 of `slice` are used.  Nibbles at bits 4-7 are expanded in place with their own multiplier
+// (bit 4+i -> bit 7+8i), which saves the shifts.
+__device__ __forceinline__ uint32_t expand4_hi(uint32_t nib_at_4) {
   uint32_t m;
-  m = expand4(slice & 15u);         v.x = (v.x & ~m) | (ch4 & m);
-  m = expand4((slice >> 4) & 15u);  v.y = (v.y & ~m) | (ch4 & m);
-  m = expand4((slice >> 8) & 15u);  v.z = (v.z & ~m) | (ch4 & m);
-  m = expand4(slice >> 12);         v.w = (v.w & ~m) | (ch4 & m);
+  asm("prmt.b32 %0, %1, 0, 0xBA98;" : "=r"(m) : "r"(nib_at_4 * 0x01020408u));
+  return m;
+}
+__device__ __forceinline__ void overlay16(uint4& v, uint32_t slice, uint32_t ch4) {
+  const uint32_t hi = slice >> 8;
+  uint32_t m;
+  m = expand4(slice & 0x0Fu);     v.x = (v.x & ~m) | (ch4 & m);
+  m = expand4_hi(slice & 0xF0u);  v.y = (v.y & ~m) | (ch4 & m);
+  m = expand4(hi & 0x0Fu);        v.z = (v.z & ~m) | (ch4 & m);
+  m = expand4_hi(hi & 0xF0u);     v.w = (v.w & ~m) | (ch4 & m);
 }
 
 // bits [o, o+16) of a linear bitset (one word of slack behind the last is readable)
@@ -450,12 +494,171 @@ __device__ __forceinline__ void compose_stream(const Ctx& X, const WarpMem& W, i
   }
 }
 
+// ---- direct composer (CxGenHeader::direct) ------------------------------------------------------------
+// bits [S, S+16) of a table row; rows carry 16 wrap-around bits and a slack word behind the bitset
+struct DirectMask {
+  const uint32_t* row;  // table row of this env (static drape: the only row; rolling drape: row dc)
+  uint32_t rot;         // (cells - dr * cols) mod cells: first source bit of cell 0
+};
+__device__ __forceinline__ DirectMask direct_mask(const Ctx& X, const WarpMem& W, int i, int e) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t prog = H.mask_prog[i];
+  DirectMask m;
+  m.row = reinterpret_cast<const uint32_t*>(X.smem + H.off_dtab[i]);
+  m.rot = 0;
+  if ((prog >> 24) == CX_KIND_ROLL) {
+    const uint32_t s = W.dyn[e][H.ent[prog & 0xFF].dyn_slot];
+    m.row += (s & 255u) * H.dtab_words;
+    const uint32_t back = (s >> 8) * H.cols;
+    m.rot = back ? H.cells - back : 0u;
+  }
+  return m;
+}
+__device__ __forceinline__ uint32_t direct_slice(const DirectMask& m, uint32_t o, uint32_t cells) {
+  uint32_t S = o + m.rot;
+  S = min(S, S - cells);  // S mod cells (unsigned wrap makes S - cells huge while S < cells)
+  const uint32_t j = S >> 5;
+  return __funnelshift_r(m.row[j], m.row[j + 1], S & 31u);  // bits 16-31: don't care
+}
+
+// Boards of at most 496 cells (every env has at most 31 whole chunks), exactly NM masks: one env per
+// iteration, one lane per chunk, branch-free so that consecutive envs interleave.  The per-env table row
+// and rotation of each mask are computed once by lane = env and broadcast with a shuffle.
+template <int NM>
+__device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t cells = H.cells;
+  const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
+  uint4* d16 = reinterpret_cast<uint4*>(dst);
+  uint32_t pk[NM > 0 ? NM : 1], ch4[NM > 0 ? NM : 1];
+#pragma unroll
+  for (int i = 0; i < NM; ++i) {
+    ch4[i] = ((H.mask_prog[i] >> 8) & 0xFF) * 0x01010101u;
+    pk[i] = 0;
+    if (lane < nenv) {
+      const DirectMask m = direct_mask(X, W, i, lane);
+      pk[i] = m.rot | ((uint32_t)(reinterpret_cast<const uint8_t*>(m.row) - X.smem) << 12);
+    }
+  }
+#pragma unroll 4
+  for (int e = 0; e < nenv; ++e) {
+    const uint32_t b0 = (uint32_t)e * cells;
+    const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
+    const uint32_t c = c_lo + lane;
+    const bool ok = c < c_hi;
+    const uint32_t cc = ok ? c : 0u, o = ok ? 16u * c - b0 : 0u;
+    uint4 v = p16[cc];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+      const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e);
+      DirectMask m;
+      m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
+      m.rot = q & 0xFFFu;
+      overlay16(v, direct_slice(m, o, cells), ch4[i]);
+    }
+    if (ok) __stcs(d16 + c, v);
+  }
+}
+
+__device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t cells = H.cells;
+  const int n_masks = H.n_masks;
+  const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
+  uint4* d16 = reinterpret_cast<uint4*>(dst);
+  constexpr int HOIST = 2;
+  uint32_t ch4[HOIST];
+#pragma unroll
+  for (int i = 0; i < HOIST; ++i) ch4[i] = i < n_masks ? ((H.mask_prog[i] >> 8) & 0xFF) * 0x01010101u : 0u;
+  // pass A: one env per iteration (its table rows and rotations are warp-uniform), one lane per 16-byte chunk
+  // that lies inside the env
+  const bool small = cells <= 496u && n_masks <= 2;
+  if (small) {
+    if (n_masks == 0) compose_direct_small<0>(X, W, nenv, dst, lane);
+    else if (n_masks == 1) compose_direct_small<1>(X, W, nenv, dst, lane);
+    else compose_direct_small<2>(X, W, nenv, dst, lane);
+  }
+#pragma unroll 2
+  for (int e = 0; e < (small ? 0 : nenv); ++e) {
+    const uint32_t b0 = (uint32_t)e * cells;
+    const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
+    DirectMask dm[HOIST];
+#pragma unroll
+    for (int i = 0; i < HOIST; ++i)
+      if (i < n_masks) dm[i] = direct_mask(X, W, i, e);
+    for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
+      const uint32_t o = 16u * c - b0;
+      uint4 v = p16[c];
+#pragma unroll
+      for (int i = 0; i < HOIST; ++i)
+        if (i < n_masks) overlay16(v, direct_slice(dm[i], o, cells), ch4[i]);
+      for (int i = HOIST; i < n_masks; ++i) {
+        const DirectMask m = direct_mask(X, W, i, e);
+        overlay16(v, direct_slice(m, o, cells), ((H.mask_prog[i] >> 8) & 0xFF) * 0x01010101u);
+      }
+      __stcs(d16 + c, v);
+    }
+  }
+  // pass B: the chunk across the boundary between env i-1 and env i (lane i), if there is one
+  if ((cells & 15u) != 0) {
+    for (int i = lane + 1; i < nenv; i += 32) {
+      const uint32_t b = (uint32_t)i * cells;
+      if ((b & 15u) == 0) continue;
+      const uint32_t k = b >> 4, cnt = b - 16u * k;       // cnt cells of env i-1, 16-cnt cells of env i
+      const uint32_t o = cells - cnt, lo_mask = (1u << cnt) - 1u;
+      uint4 v = p16[k];
+      for (int m = 0; m < n_masks; ++m) {
+        const DirectMask m0 = direct_mask(X, W, m, i - 1), m1 = direct_mask(X, W, m, i);
+        const uint32_t sl = (direct_slice(m0, o, cells) & lo_mask) | (direct_slice(m1, 0u, cells) << cnt);
+        overlay16(v, sl, ((H.mask_prog[m] >> 8) & 0xFF) * 0x01010101u);
+      }
+      __stcs(d16 + k, v);
+    }
+  }
+}
+
+// one-cell entities of the direct composer: those below every mask are poked into the plane before the
+// composition (and restored afterwards), those above every mask are stored over the finished board
+__device__ __forceinline__ uint64_t poke_below(const Ctx& X, const WarpMem& W, int e) {
+  const CxGenHeader& H = *X.H;
+  uint8_t* plane = W.plane + e * H.cells;
+  uint64_t saved = 0;
+  for (int i = 0; i < H.n_points; ++i) {
+    const uint32_t prog = H.point_prog[i], slot = (prog >> 16) & 0xFF;
+    if (prog >> 24) continue;  // stamped for good (1) or above the masks (2)
+    const uint32_t s = W.dyn[e][slot];
+    if (s == CX_EMPTY_CELL16) continue;
+    saved |= (uint64_t)plane[s] << (8 * slot);
+    plane[s] = (uint8_t)(prog >> 8);
+  }
+  return saved;
+}
+__device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int e, uint8_t* dst) {
+  const CxGenHeader& H = *X.H;
+  for (int i = 0; i < H.n_points; ++i) {
+    const uint32_t prog = H.point_prog[i];
+    if (!((prog >> 24) & 2u)) continue;
+    const uint32_t s = W.dyn[e][(prog >> 16) & 0xFF];
+    if (s != CX_EMPTY_CELL16) dst[(uint32_t)e * H.cells + s] = (uint8_t)(prog >> 8);
+  }
+}
+
 // Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
 // per-cell painter's algorithm with byte stores (any geometry, any alignment).
 __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, bool fast,
                                              int lane) {
   const CxGenHeader& H = *X.H;
-  if (fast) {
+  if (fast && H.direct) {
+    uint64_t saved = 0;
+    if (lane < nenv) saved = poke_below(X, W, lane);
+    __syncwarp();
+    compose_direct(X, W, nenv, dst, lane);
+    __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
+    if (lane < nenv) {
+      store_above(X, W, lane, dst);
+      unpoke_points(X, W, lane, saved);
+    }
+  } else if (fast) {
     build_linear_masks(X, W, nenv, lane);
     __syncwarp();
     uint64_t saved = 0;
@@ -499,7 +702,7 @@ __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem,
   return W;
 }
 
-__global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ GenParams P) {
+__global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
   __shared__ WarpTile s_w[NT / 32];
@@ -547,6 +750,8 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
   double ep_sum = 0.0, ep_sumsq = 0.0;
   float ep_max = -INFINITY, ep_negmin = -INFINITY;
 
+  uint32_t a_next = 0;  // this lane's action for the coming step, loaded one step ahead of its use
+  if (mine && !P.synth) a_next = P.actions[env0 + lane];
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * P.n + env0;
     bool reset_me = false;
@@ -556,7 +761,8 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
         a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t, (uint32_t)H.n_actions);
         if (P.actions_out) P.actions_out[row + lane] = (uint8_t)a;
       } else {
-        a = P.actions[row + lane];
+        a = a_next;
+        if (t + 1 < P.T) a_next = P.actions[row + P.n + lane];
       }
       float rw, dc;
       uint32_t f;
@@ -565,7 +771,10 @@ __global__ void __launch_bounds__(NT) k_generic_rollout(const __grid_constant__ 
         dc = 0.0f;
         f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
       } else {
-        generic_env_step(X, a, dyn[lane], W.prev[lane], plane + lane * cells, rw, f, dc);
+        if (H.simple_step)
+          simple_env_step(X, a, dyn[lane], plane + lane * cells, rw, f, dc);
+        else
+          generic_env_step(X, a, dyn[lane], W.prev[lane], plane + lane * cells, rw, f, dc);
       }
       if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
         const uint32_t steps = ts + 1u;

@@ -98,6 +98,24 @@ struct CxGenHeader {
   uint32_t point_holes[CX_MAX_DYN];      // bit s: per-env mask bitset s lies below the point entity (its cell is punched out)
   int32_t off_colroll[CX_MAX_LIN];       // per lin slot of a rolling drape: u32 [cols][mask_words + 1], the static mask
                                          // rolled right by dc columns, as linear bitsets; -1: not tabulated
+  // direct composer: no per-env bitsets at all.  Every mask entity has a bit table in the blob -- one row
+  // (static drape) or `cols` rows (rolling drape: the mask rolled right by dc columns), each row the linear
+  // bitset followed by a copy of its first 16 bits (so a 16-bit slice may run over the end) -- and the
+  // composer slices bits [S, S+16), S = (o - dr * cols) mod cells, straight from the row.  Visible one-cell
+  // entities are either below every mask (poked into the plane) or above every mask (stored over the
+  // finished board); games with a one-cell entity between two masks keep the per-env bitsets.
+  int32_t direct;
+  int32_t dtab_words;                    // u32 words per table row: ceil((cells + 16) / 32) + 1
+  int32_t off_dtab[CX_MAX_ENTITIES];     // per mask_prog index
+  // table-driven step: no entity looks at the last render (no blockers, no entry rewards) and there is one
+  // update group, so a step is "move every dynamic slot by its per-action delta" and the reward is a
+  // function of the action alone (summed on the host in update order, float32, plot.py:208-211)
+  int32_t simple_step;
+  uint8_t slot_kind[CX_MAX_DYN];         // cx_kind of the entity behind each dynamic slot
+  int8_t slot_dr[CX_MAX_DYN][CX_MAX_ACTIONS], slot_dc[CX_MAX_DYN][CX_MAX_ACTIONS];
+  float simple_reward[CX_MAX_ACTIONS];
+  int32_t n_stampers;
+  uint16_t stamper[CX_MAX_DYN];          // back to front: ch << 8 | dyn_slot of the sprites that stamp the plane
   int32_t blob_bytes;
   CxActionTable act;
 };
