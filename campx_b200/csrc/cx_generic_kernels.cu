@@ -264,6 +264,55 @@ __device__ __forceinline__ void simple_env_step(const Ctx& X, uint32_t a, uint16
   flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
 }
 
+// simple_env_step with the entity state in registers (k_generic_rollout<true>): sreg[d] = row << 8 | col for
+// every kind (0xFFFF: empty one-cell mask), so a move is two adds and two wraps with no table look-up in the
+// dependency chain, and the slots are independent instruction streams.  st[] (shared memory) receives the
+// representation the composer reads: cell index, or roll offset for rolling drapes.
+__device__ __forceinline__ void fast_env_step(const Ctx& X, uint32_t a, uint32_t (&sreg)[CX_MAX_DYN], uint16_t* st,
+                                              uint8_t* plane, float& reward, uint32_t& flags, float& disc) {
+  const CxGenHeader& H = *X.H;
+  if (a >= (uint32_t)H.n_actions) {
+    reward = 0.0f;
+    disc = 1.0f;
+    flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;
+    return;
+  }
+  const int R = H.rows, C = H.cols;
+  const uint4 dl4 = *reinterpret_cast<const uint4*>(X.smem + H.off_sdelta + a * (CX_MAX_DYN * 2));
+  const uint32_t w[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+  for (int d = 0; d < CX_MAX_DYN; ++d) {
+    if (d < H.n_dyn) {
+      const uint32_t dl = (d & 1) ? w[d >> 1] >> 16 : w[d >> 1] & 0xFFFFu;
+      const uint32_t s = sreg[d];
+      int r = (int)(s >> 8) + (int)(int8_t)(dl >> 8), c = (int)(s & 255u) + (int)(int8_t)(dl & 255u);
+      r += r < 0 ? R : 0;
+      c += c < 0 ? C : 0;
+      r -= r >= R ? R : 0;
+      c -= c >= C ? C : 0;
+      const uint32_t ns = ((uint32_t)r << 8) | (uint32_t)c;
+      const bool live = s != 0xFFFFu;
+      sreg[d] = live ? ns : s;
+      if (live) st[d] = (uint16_t)(((H.roll_slots >> d) & 1u) ? ns : (uint32_t)(r * C + c));
+    }
+  }
+  stamp(X, st, plane);
+  reward = H.simple_reward[a];
+  disc = H.act.discount[a];
+  flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+}
+__device__ __forceinline__ void fast_load_state(const Ctx& X, const uint16_t* st, uint32_t (&sreg)[CX_MAX_DYN]) {
+  const CxGenHeader& H = *X.H;
+#pragma unroll
+  for (int d = 0; d < CX_MAX_DYN; ++d) {
+    sreg[d] = 0xFFFFu;
+    if (d < H.n_dyn) {
+      const uint32_t v = st[d];
+      sreg[d] = ((H.roll_slots >> d) & 1u) ? v : (v == CX_EMPTY_CELL16 ? 0xFFFFu : (uint32_t)X.rc[v]);
+    }
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -558,6 +607,28 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
     }
     if (ok) __stcs(d16 + c, v);
   }
+  // the chunk across the boundary between env i-1 and env i (lane i), if there is one
+  if ((cells & 15u) != 0) {
+    uint32_t pk_prev[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) pk_prev[i] = __shfl_up_sync(0xffffffffu, pk[i], 1);
+    const uint32_t b = (uint32_t)lane * cells;
+    if (lane >= 1 && lane < nenv && (b & 15u) != 0) {
+      const uint32_t k = b >> 4, cnt = b - 16u * k;       // cnt cells of env lane-1, 16-cnt cells of env lane
+      const uint32_t o = cells - cnt, lo_mask = (1u << cnt) - 1u;
+      uint4 v = p16[k];
+#pragma unroll
+      for (int i = 0; i < NM; ++i) {
+        DirectMask m0, m1;
+        m0.row = reinterpret_cast<const uint32_t*>(X.smem + (pk_prev[i] >> 12));
+        m0.rot = pk_prev[i] & 0xFFFu;
+        m1.row = reinterpret_cast<const uint32_t*>(X.smem + (pk[i] >> 12));
+        m1.rot = pk[i] & 0xFFFu;
+        overlay16(v, (direct_slice(m0, o, cells) & lo_mask) | (direct_slice(m1, 0u, cells) << cnt), ch4[i]);
+      }
+      __stcs(d16 + k, v);
+    }
+  }
 }
 
 __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
@@ -577,9 +648,10 @@ __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, i
     if (n_masks == 0) compose_direct_small<0>(X, W, nenv, dst, lane);
     else if (n_masks == 1) compose_direct_small<1>(X, W, nenv, dst, lane);
     else compose_direct_small<2>(X, W, nenv, dst, lane);
+    return;
   }
 #pragma unroll 2
-  for (int e = 0; e < (small ? 0 : nenv); ++e) {
+  for (int e = 0; e < nenv; ++e) {
     const uint32_t b0 = (uint32_t)e * cells;
     const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
     DirectMask dm[HOIST];
@@ -702,6 +774,7 @@ __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem,
   return W;
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
@@ -745,6 +818,8 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
     }
   }
   __syncwarp();
+  uint32_t sreg[CX_MAX_DYN];
+  if (FAST && mine) fast_load_state(X, dyn[lane], sreg);
 
   uint32_t ep_cnt = 0, ep_len = 0;
   double ep_sum = 0.0, ep_sumsq = 0.0;
@@ -771,7 +846,9 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
         dc = 0.0f;
         f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
       } else {
-        if (H.simple_step)
+        if (FAST)
+          fast_env_step(X, a, sreg, dyn[lane], plane + lane * cells, rw, f, dc);
+        else if (H.simple_step)
           simple_env_step(X, a, dyn[lane], plane + lane * cells, rw, f, dc);
         else
           generic_env_step(X, a, dyn[lane], W.prev[lane], plane + lane * cells, rw, f, dc);
@@ -809,9 +886,11 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
     if (rmask) {
-      if (reset_me)
+      if (reset_me) {
         for (int z = 0; z < H.n_ent; ++z)
           if (H.ent[z].dyn_slot != 0xFF) dyn[lane][H.ent[z].dyn_slot] = H.ent[z].init_state;
+        if (FAST) fast_load_state(X, dyn[lane], sreg);
+      }
       if (H.has_dynbd) {
         while (rmask) {  // the plane of each finished env goes back to the its_showtime backdrop
           const int e = __ffs(rmask) - 1;
@@ -931,7 +1010,8 @@ bool gen_vec_ok(const cx_game* g, int64_t n, const void* d_board) {
 int configure_once() {
   static bool configured = false;
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
@@ -966,7 +1046,10 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   }
   int rc = configure_once();
   if (rc) return rc;
-  k_generic_rollout<<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+  if (g->gh.fast_loop && P.vec)
+    k_generic_rollout<true><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+  else
+    k_generic_rollout<false><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -114,6 +114,9 @@ struct CxGenHeader {
   uint8_t slot_kind[CX_MAX_DYN];         // cx_kind of the entity behind each dynamic slot
   int8_t slot_dr[CX_MAX_DYN][CX_MAX_ACTIONS], slot_dc[CX_MAX_DYN][CX_MAX_ACTIONS];
   float simple_reward[CX_MAX_ACTIONS];
+  int32_t off_sdelta;                    // u16 [CX_MAX_ACTIONS][CX_MAX_DYN]: (dr & 0xFF) << 8 | (dc & 0xFF) per action and slot
+  uint32_t roll_slots;                   // bit d: dynamic slot d holds a roll offset (row << 8 | col), not a cell index
+  int32_t fast_loop;                     // simple_step && direct && cells <= 496 && n_masks <= 2: k_generic_rollout<true>
   int32_t n_stampers;
   uint16_t stamper[CX_MAX_DYN];          // back to front: ch << 8 | dyn_slot of the sprites that stamp the plane
   int32_t blob_bytes;
