@@ -7,12 +7,13 @@ compute entry point is needed, this module raises.  The library is built in-tree
 import ctypes
 import os
 
-CX_ABI_VERSION = 1
+CX_ABI_VERSION = 2
 CX_MAX_ENTITIES = 16
 CX_MAX_ACTIONS = 8
 CX_MAX_CHARS = 32
 CX_MAX_CELLS = 4096
 CX_MAX_GROUPS = 8
+CX_MAX_ZDIRS = 2
 
 CX_OK = 0
 CX_ERR_INVALID_ARG = -1
@@ -21,6 +22,7 @@ CX_ERR_CUDA = -3
 CX_ERR_NOMEM = -4
 
 CX_KIND_STATIC, CX_KIND_CELL, CX_KIND_ROLL, CX_KIND_SPRITE = 0, 1, 2, 3
+CX_VIS_KEEP, CX_VIS_SHOW, CX_VIS_HIDE, CX_VIS_TOGGLE = 0, 1, 2, 3
 
 CX_FLAG_TERMINATED = 0x01
 CX_FLAG_TRUNCATED = 0x02
@@ -61,6 +63,10 @@ class EntityDesc(ctypes.Structure):
         ("step_reward", ctypes.c_float * CX_MAX_ACTIONS),
         ("entry_reward", (ctypes.c_float * CX_MAX_CHARS) * CX_MAX_ACTIONS),
         ("discount_value", ctypes.c_float * CX_MAX_ACTIONS),
+        ("visible_op", ctypes.c_uint8 * CX_MAX_ACTIONS),
+        ("n_zdirs", ctypes.c_uint8 * CX_MAX_ACTIONS),
+        ("z_move", (ctypes.c_int8 * CX_MAX_ZDIRS) * CX_MAX_ACTIONS),
+        ("z_front", (ctypes.c_int8 * CX_MAX_ZDIRS) * CX_MAX_ACTIONS),
     ]
 
 
@@ -82,13 +88,15 @@ class GameDesc(ctypes.Structure):
         ("track_returns", ctypes.c_int32),
         ("first_reward", ctypes.c_float),
         ("first_discount", ctypes.c_float),
+        ("backdrop_dr", ctypes.c_int8 * CX_MAX_ACTIONS),
+        ("backdrop_dc", ctypes.c_int8 * CX_MAX_ACTIONS),
     ]
 
 
 class GameInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "rows", "cols", "cells", "n_chars", "n_actions", "n_entities", "path", "can_terminate", "tracks",
-        "has_dynamic_backdrop", "state_bytes_per_env", "board_bytes_per_env")]
+        "has_dynamic_backdrop", "state_bytes_per_env", "board_bytes_per_env", "dynamic_render")]
 
 
 _P = ctypes.c_void_p
@@ -117,6 +125,7 @@ PROTOTYPES = {
     "cx_fill_actions": (ctypes.c_int, [_U64, _U64, _U64, _I32, _I64, _I32, _P, _P]),
     "cx_get_entity_state": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "cx_set_entity_state": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "cx_get_render_state": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "cx_get_episode_state": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
     "cx_stats_read": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_double), _P]),
     "cx_step_perf": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _P]),

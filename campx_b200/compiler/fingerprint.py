@@ -14,10 +14,14 @@ Probe set
   * for sprites / rolling drapes: every action from the board corners and a few interior
     positions/offsets (pins the toroidal wrap).
 
+  * for sprites that change `_visible`: every action from the other visibility state;
+  * for a Backdrop whose update() changes its curtain: every action from a few pre-rolled curtains.
+
 Fitted per entity (see include/campx_b200.h `cx_entity_desc`)
   kind, per-action toroidal move, blocker characters (one-cell drapes), per-action step reward,
   "entry" reward as a function of (action, character the last render showed at a watched entity's
-  current cell), terminate / default-discount directives per action.
+  current cell), terminate / default-discount directives per action, per-action visibility
+  operation (sprites), per-action `change_z_order` calls; per game: the backdrop's per-action roll.
 """
 import collections
 
@@ -66,14 +70,24 @@ def _snapshot(shadow):
 
 class _Probe(object):
     __slots__ = ("action", "teleports", "pre", "post", "group_board", "after", "events", "reward", "discount",
-                 "game_over", "backdrop_pre", "backdrop_post")
+                 "game_over", "backdrop_pre", "backdrop_post", "z_post")
+
+
+BACKDROP = "__backdrop__"          # teleport key: pre-roll the backdrop curtain by (d_row, d_col)
 
 
 def _teleport(shadow, base_masks, ch, where):
+    if ch == BACKDROP:
+        cur = shadow.backdrop.curtain
+        rolled = np.roll(cur.as_subclass(torch.Tensor).numpy(), (where[0], where[1]), axis=(0, 1)).copy()
+        cur.copy_(torch.from_numpy(rolled).to(cur.dtype))
+        return
     ent = shadow.things[ch]
     rows, cols = shadow.rows, shadow.cols
     if isinstance(ent, things.Sprite):
         ent._position = ent.Position(int(where[0]), int(where[1]))
+        if len(where) > 2:
+            ent._visible = bool(where[2])
         return
     cur = ent.curtain
     if where[0] == "cell":
@@ -124,6 +138,7 @@ def run_probe(base, base_masks, fmt, n_actions, action, teleports):
         p.events[who].append((kind, payload))
     p.post = _snapshot(s)
     p.backdrop_post = s.backdrop.curtain.as_subclass(torch.Tensor).numpy().copy()
+    p.z_post = list(s.things.keys())
     return p
 
 
@@ -197,7 +212,8 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             continue
 
         def outcome(pr):
-            state = tuple((ch, v[1] if v[0] == "sprite" else v[1].tobytes()) for ch, v in sorted(pr.post.items()))
+            state = tuple((ch, v[1:] if v[0] == "sprite" else v[1].tobytes()) for ch, v in sorted(pr.post.items()))
+            state += (pr.backdrop_post.tobytes(),)
             events = tuple((who, tuple((k, float(_f32(p)) if k == "reward" else p) for k, p in ev))
                            for who, ev in sorted(pr.events.items(), key=lambda kv: str(kv[0])))
             return state, events, pr.game_over
@@ -231,13 +247,33 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             kind[ch] = N.CX_KIND_ROLL
 
     # ---- sprites: per-action displacement, verified from corners -------------------------------------
+    visible_ops = {}
     for ch in [c for c in z_chars if kind[c] == N.CX_KIND_SPRITE]:
-        p0 = base_snap[ch][1]
+        p0, vis0 = base_snap[ch][1], base_snap[ch][2]
         mv = []
         for pr in s0_probes:
             q = pr.post[ch][1]
             mv.append((_signed(q[0] - p0[0], rows), _signed(q[1] - p0[1], cols)))
         moves[ch] = mv
+        # Sprite._visible (things.py:320): per action keep / show / hide / toggle.  If it ever changes from the
+        # initial state, every action is also probed from the other state (keep vs show are told apart there).
+        seen = {a: {(vis0, s0_probes[a].post[ch][2])} for a in range(A)}
+        if any(pr.post[ch][2] != vis0 for pr in s0_probes):
+            for a in range(A):
+                pr = probe(a, {ch: (p0[0], p0[1], not vis0)})
+                seen[a].add((not vis0, pr.post[ch][2]))
+        ops = []
+        for a in range(A):
+            fits = [op for op, fn in ((N.CX_VIS_KEEP, lambda v: v), (N.CX_VIS_SHOW, lambda v: True),
+                                      (N.CX_VIS_HIDE, lambda v: False), (N.CX_VIS_TOGGLE, lambda v: not v))
+                    if all(fn(pre) == post for pre, post in seen[a])]
+            if not fits:
+                raise CompileError("sprite %r: action %d changes its visibility in a way that is not "
+                                   "keep/show/hide/toggle" % (ch, a))
+            ops.append(fits[0])
+        visible_ops[ch] = ops
+        model_vis = lambda a, v, _ops=ops: {N.CX_VIS_KEEP: v, N.CX_VIS_SHOW: True, N.CX_VIS_HIDE: False,
+                                            N.CX_VIS_TOGGLE: not v}[_ops[a]]
         spots = {(0, 0), (rows - 1, cols - 1), (0, cols - 1), (rows - 1, 0), (rows // 2, cols // 2)}
         for spot in sorted(spots):
             for a in range(A):
@@ -246,8 +282,8 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                 if pr.post[ch][1] != want:
                     raise CompileError("sprite %r does not move by a fixed toroidal displacement per action "
                                        "(from %s action %d: got %s, model %s)" % (ch, spot, a, pr.post[ch][1], want))
-                if pr.post[ch][2] != base_snap[ch][2]:
-                    raise CompileError("sprite %r changes its visibility; not supported yet" % ch)
+                if pr.post[ch][2] != model_vis(a, pr.pre[ch][2]):
+                    raise CompileError("sprite %r: its visibility depends on more than the action" % ch)
 
     # ---- rolling drapes -----------------------------------------------------------------------------
     for ch in [c for c in z_chars if kind[c] == N.CX_KIND_ROLL]:
@@ -314,29 +350,72 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                                    "%s but update() gave %s" % (ch, p, a, mv[a], "".join(sorted(blk)), model, q))
         blockers[ch] = "".join(sorted(blk))
 
-    # ---- backdrop must be static apart from the sprite stamps of quirk Q1 ----------------------------------
-    first_drape = next((i for i, c in enumerate(z_chars) if kind[c] != N.CX_KIND_SPRITE), len(z_chars))
-    stampers = [c for c in z_chars[:first_drape] if base_snap[c][2]] if first_drape < len(z_chars) else []
+    # ---- backdrop: static apart from the sprite stamps of quirk Q1, or rolled by Backdrop.update() ------------
+    def first_drape_of(order_):
+        return next((i for i, c in enumerate(order_) if kind[c] != N.CX_KIND_SPRITE), len(order_))
+
+    any_drape = first_drape_of(z_chars) < len(z_chars)
+    backdrop_moves = None
+    s0_changed = [not np.array_equal(pr.backdrop_pre, pr.backdrop_post) for pr in s0_probes]
+    stamp_cells_only = True
+    for pr in s0_probes:
+        for r, c in np.argwhere(pr.backdrop_pre != pr.backdrop_post):
+            if not any(kind[s_] == N.CX_KIND_SPRITE and pr.post[s_][1] == (int(r), int(c)) and
+                       pr.backdrop_post[r, c] == ord(s_) for s_ in z_chars):
+                stamp_cells_only = False
+    if any(s0_changed) and any_drape and not stamp_cells_only:
+        # things.py:103-148 Backdrop.update(): fitted as a per-action toroidal roll of the curtain (scrolling scenery)
+        bd0 = s0_probes[0].backdrop_pre
+        backdrop_moves = []
+        for pr in s0_probes:
+            sh = _find_roll(bd0, pr.backdrop_post)
+            if sh is None:
+                raise CompileError("Backdrop.update() changes the backdrop in a way that is not a toroidal roll "
+                                   "of its curtain")
+            backdrop_moves.append(sh)
+        for off in sorted({(rows - 1, cols - 1), (1, 0), (0, 1), (rows // 2, cols // 3)}):
+            for a in range(A):
+                pr = probe(a, {BACKDROP: off})
+                want = np.roll(pr.backdrop_pre, backdrop_moves[a], axis=(0, 1))
+                if not np.array_equal(pr.backdrop_post, want):
+                    raise CompileError("Backdrop.update() does not roll the backdrop by a fixed shift per action")
     for pr in probes:
-        diff = np.argwhere(pr.backdrop_pre != pr.backdrop_post)
-        for r, c in diff:
-            ok = any(pr.post[s][1] == (int(r), int(c)) and pr.backdrop_post[r, c] == ord(s) for s in stampers)
-            if not ok and first_drape < len(z_chars):
-                raise CompileError("Backdrop.update() changes the backdrop; dynamic backdrops are not supported yet")
+        if pr.events.get(None):
+            raise CompileError("Backdrop.update() issues plot directives (%s); not supported"
+                               % ", ".join(sorted({k for k, _ in pr.events[None]})))
+        if backdrop_moves is not None:
+            if BACKDROP not in pr.teleports and not np.array_equal(
+                    pr.backdrop_post, np.roll(pr.backdrop_pre, backdrop_moves[pr.action], axis=(0, 1))):
+                raise CompileError("Backdrop.update() does not roll the backdrop by a fixed shift per action")
+            continue
+        # sprites that lie, visibly, behind the first drape of the initial or the resulting z-order stamp
+        # their character into the backdrop
+        allowed = set()
+        for order_ in (z_chars, pr.z_post):
+            fd = first_drape_of(order_)
+            if fd < len(order_):
+                allowed.update(c for c in order_[:fd] if pr.post[c][2])
+        for r, c in np.argwhere(pr.backdrop_pre != pr.backdrop_post):
+            ok = any(pr.post[s_][1] == (int(r), int(c)) and pr.backdrop_post[r, c] == ord(s_) for s_ in allowed)
+            if not ok and any_drape:
+                raise CompileError("Backdrop.update() changes the backdrop in a way that is neither a sprite stamp "
+                                   "nor a roll of the whole curtain")
 
     # ---- rewards, terminate, discount ----------------------------------------------------------------------
     movers = [c for c in z_chars if kind[c] in (N.CX_KIND_CELL, N.CX_KIND_SPRITE)]
     specs = []
     for z, ch in enumerate(z_chars):
         obs = []                                  # (probe, action, f32 reward or None)
-        term, disc = {}, {}
+        term, disc, zord = {}, {}, {}
         for pr in probes:
             val = None
+            zs = []
             for k, payload in pr.events.get(ch, ()):
                 if k == "reward":
                     val = _f32(payload) if val is None else np.float32(_f32(payload) + val)
                 elif k == "z_order":
-                    raise CompileError("change_z_order is not supported yet")
+                    zs.append(tuple(payload))
+            zord.setdefault(pr.action, set()).add(tuple(zs))
             obs.append((pr, pr.action, val))
             t = [payload for k, payload in pr.events.get(ch, ()) if k == "terminate"]
             d = [payload for k, payload in pr.events.get(ch, ()) if k == "discount"]
@@ -346,6 +425,21 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             for a, vals in table.items():
                 if len(vals) != 1:
                     raise CompileError("entity %r calls %s for action %d only in some states" % (ch, name, a))
+        z_orders = {}
+        for a, vals in zord.items():
+            if len(vals) != 1:
+                raise CompileError("entity %r calls change_z_order for action %d only in some states" % (ch, a))
+            calls = list(next(iter(vals)))
+            for move_this, front_of in calls:
+                for c in (move_this,) if front_of is None else (move_this, front_of):
+                    if c not in z_chars:       # engine.py:247-262
+                        raise CompileError("A z-order change directive names character %r, but no such Sprite or "
+                                           "Drape exists" % (c,))
+                if move_this == front_of:
+                    raise CompileError("change_z_order(%r, %r) would drop the entity from the game "
+                                       "(engine.py:270-279); not supported" % (move_this, front_of))
+            if calls:
+                z_orders[a] = calls
         terminate = {a: next(iter(v)) for a, v in term.items() if next(iter(v)) is not None}
         discount = {a: next(iter(v)) for a, v in disc.items() if next(iter(v)) is not None and a not in terminate}
 
@@ -417,7 +511,8 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             init_pos=(snap[1] if snap[0] == "sprite" else None),
             moves=moves.get(ch), blockers=blockers.get(ch, ""),
             step_reward=step_reward, watch=watch, entry_reward=entry,
-            terminate=terminate or None, discount=discount or None))
+            terminate=terminate or None, discount=discount or None,
+            visible_op=visible_ops.get(ch), z_orders=z_orders or None))
 
     # ---- whole-step consistency: the per-entity fits must add up to what play() returned --------------------
     spec = GameSpec(rows=rows, cols=cols, chars=chars, n_actions=A, entities=specs,
@@ -425,6 +520,6 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                     n_groups=len(base.update_groups), max_episode_steps=max_episode_steps,
                     auto_reset=auto_reset, track_returns=track_returns,
                     first_reward=None if first_reward is None else float(_f32(first_reward)),
-                    first_discount=float(first_discount), action_format=fmt)
+                    first_discount=float(first_discount), action_format=fmt, backdrop_moves=backdrop_moves)
     spec.n_probes = len(probes)
     return spec

@@ -155,8 +155,24 @@ class ShadowEngine(object):
             plot.current_entity = None
             self.render()                             # engine.py:208
         d = plot._get_engine_directives()
+        for move_this, in_front_of_that in d.z_updates:      # engine.py:242-281
+            for ch in (move_this,) if in_front_of_that is None else (move_this, in_front_of_that):
+                if ch not in self.things:
+                    raise RuntimeError('A z-order change directive names character {}, but no such Sprite or '
+                                       'Drape exists'.format(repr(ch)))
+            mover = self.things[move_this]
+            reordered = collections.OrderedDict()
+            if in_front_of_that is None:
+                reordered[move_this] = mover
+            for ch, ent in self.things.items():
+                if ch == move_this:
+                    continue
+                reordered[ch] = ent
+                if ch == in_front_of_that:
+                    reordered[move_this] = mover
+            self.things = reordered
         if d.z_updates:
-            raise NotImplementedError('change_z_order directives are not supported by the batched engine yet')
+            self.render()                             # engine.py:163
         self.game_over = d.game_over
         reward, discount = d.summed_reward, d.discount
         plot._clear_engine_directives()

@@ -325,8 +325,7 @@ int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d
     GenInit gi;
     memset(&gi, 0, sizeof(gi));
     gi.n_dyn = g->gh.n_dyn;
-    for (int z = 0; z < g->gh.n_ent; ++z)
-      if (g->gh.ent[z].dyn_slot != 0xFF) gi.init[g->gh.ent[z].dyn_slot] = g->gh.ent[z].init_state;
+    memcpy(gi.init, g->gh.slot_init, sizeof(gi.init));
     k_generic_reset<<<blocks_for(n), TB, 0, s>>>(reinterpret_cast<uint16_t*>(base + L.off_dyn), tstep, ret,
                                                  g->info.tracks, gi, d_mask, n);
     if (g->gh.has_dynbd)
@@ -381,6 +380,46 @@ int cx_launch_set_entity(const cx_game* g, void* d_state, int64_t n, int32_t z, 
     k_set_generic<<<blocks_for(n), TB, 0, s>>>(dyn, d_in, kind == CX_KIND_ROLL, kind == CX_KIND_CELL, g->gh.cols,
                                                g->gh.cells, n);
   }
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+namespace {
+__global__ void k_get_render_state(const uint16_t* dyn, int64_t n, int n_ent, int slot_vis, int slot_zperm,
+                                   int slot_bd, uint32_t static_vis, int cols, uint32_t* zorder, uint32_t* visible,
+                                   int32_t* bd_off) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  if (zorder) {
+    uint32_t perm = 0;
+    if (slot_zperm >= 0) {
+      perm = (uint32_t)dyn[(int64_t)slot_zperm * n + i] | ((uint32_t)dyn[(int64_t)(slot_zperm + 1) * n + i] << 16);
+      if (n_ent < 8) perm &= (1u << (4 * n_ent)) - 1u;
+    } else {
+      for (int p = 0; p < n_ent && p < 8; ++p) perm |= (uint32_t)p << (4 * p);
+    }
+    zorder[i] = perm;
+  }
+  if (visible) visible[i] = slot_vis >= 0 ? dyn[(int64_t)slot_vis * n + i] : static_vis;
+  if (bd_off) {
+    const uint32_t s = slot_bd >= 0 ? dyn[(int64_t)slot_bd * n + i] : 0u;
+    bd_off[i] = (int32_t)((s >> 8) * cols + (s & 255u));
+  }
+}
+}  // namespace
+
+int cx_launch_get_render_state(const cx_game* g, const void* d_state, int64_t n, uint32_t* d_zorder,
+                               uint32_t* d_visible, int32_t* d_backdrop_off, cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  const uint8_t* base = static_cast<const uint8_t*>(d_state);
+  uint32_t static_vis = 0;
+  for (int z = 0; z < g->desc.n_entities; ++z)
+    if (g->desc.entities[z].kind == CX_KIND_SPRITE && g->desc.entities[z].visible) static_vis |= 1u << z;
+  const bool gen = g->path == CX_PATH_GENERIC;
+  k_get_render_state<<<blocks_for(n), TB, 0, s>>>(
+      reinterpret_cast<const uint16_t*>(base + L.off_dyn), n, g->desc.n_entities, gen ? g->gh.slot_vis : -1,
+      gen ? g->gh.slot_zperm : -1, gen ? g->gh.slot_bd : -1, static_vis, g->desc.cols, d_zorder, d_visible,
+      d_backdrop_off);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

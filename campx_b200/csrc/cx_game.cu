@@ -204,6 +204,28 @@ static int validate(const cx_game_desc* d) {
       }
     }
     for (int a = 0; a < d->n_actions; ++a) {
+      if (e.visible_op[a] > CX_VIS_TOGGLE || (e.visible_op[a] != CX_VIS_KEEP && e.kind != CX_KIND_SPRITE)) {
+        cx_set_error("cx_game_create: entity %d action %d has visible_op %d (sprites only, 0..3)", z, a,
+                     e.visible_op[a]);
+        return CX_ERR_INVALID_ARG;
+      }
+      if (e.n_zdirs[a] > CX_MAX_ZDIRS) {
+        cx_set_error("cx_game_create: entity %d action %d has %d z-order directives (max %d)", z, a, e.n_zdirs[a],
+                     CX_MAX_ZDIRS);
+        return CX_ERR_INVALID_ARG;
+      }
+      for (int k = 0; k < e.n_zdirs[a]; ++k) {
+        const int mv = e.z_move[a][k], fr = e.z_front[a][k];
+        if (mv < 0 || mv >= d->n_entities || fr < -1 || fr >= d->n_entities) {
+          // engine.py:247-262: "A z-order change directive said to move a Sprite or Drape ... no such ... exists"
+          cx_set_error("cx_game_create: z-order directive of entity %d names an entity that does not exist", z);
+          return CX_ERR_INVALID_ARG;
+        }
+        if (mv == fr) {  // engine.py:270-279 would drop the entity from the game altogether
+          cx_set_error("cx_game_create: z-order directive moves entity %d in front of itself", mv);
+          return CX_ERR_UNSUPPORTED;
+        }
+      }
       if (abs((int)e.move_dr[a]) >= d->rows + (d->rows == 1) || abs((int)e.move_dc[a]) >= d->cols + (d->cols == 1)) {
         cx_set_error("cx_game_create: entity %d action %d moves by (%d, %d), not less than the board size", z, a,
                      e.move_dr[a], e.move_dc[a]);
@@ -216,6 +238,12 @@ static int validate(const cx_game_desc* d) {
       }
     }
   }
+  for (int a = 0; a < d->n_actions; ++a)
+    if (abs((int)d->backdrop_dr[a]) >= d->rows + (d->rows == 1) || abs((int)d->backdrop_dc[a]) >= d->cols + (d->cols == 1)) {
+      cx_set_error("cx_game_create: action %d rolls the backdrop by (%d, %d), not less than the board size", a,
+                   d->backdrop_dr[a], d->backdrop_dc[a]);
+      return CX_ERR_INVALID_ARG;
+    }
   // update groups must be ordered consistently with ranks (engine.py:520-521 sorts groups; ranks follow)
   for (int z = 0; z < d->n_entities; ++z)
     for (int y = 0; y < d->n_entities; ++y)
@@ -237,9 +265,24 @@ struct Blob {
   void pad() { bytes.resize((bytes.size() + 15) / 16 * 16, 0); }
 };
 
+// z-order directives, sprite visibility directives or a rolling backdrop: render state that changes during play
+static void dynamic_render_needs(const cx_game_desc* d, bool* vis, bool* zord, bool* bd) {
+  *vis = *zord = *bd = false;
+  for (int a = 0; a < d->n_actions; ++a) {
+    if (d->backdrop_dr[a] || d->backdrop_dc[a]) *bd = true;
+    for (int z = 0; z < d->n_entities; ++z) {
+      if (d->entities[z].visible_op[a] != CX_VIS_KEEP) *vis = true;
+      if (d->entities[z].n_zdirs[a]) *zord = true;
+    }
+  }
+}
+
 static bool agent_path_applies(const cx_game_desc* d, int* agent_z) {
   const int cells = d->rows * d->cols;
   if (cells > CX_AGENT_MAX_CELLS || d->n_groups > 1) return false;
+  bool vis, zord, bd;
+  dynamic_render_needs(d, &vis, &zord, &bd);
+  if (vis || zord || bd) return false;
   int moving = -1, count = 0;
   for (int z = 0; z < d->n_entities; ++z) {
     const cx_entity_desc& e = d->entities[z];
@@ -437,6 +480,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     memcpy(g.dr, e.move_dr, CX_MAX_ACTIONS);
     memcpy(g.dc, e.move_dc, CX_MAX_ACTIONS);
     memcpy(g.step_reward, e.step_reward, sizeof(g.step_reward));
+    memcpy(g.vis_op, e.visible_op, CX_MAX_ACTIONS);
     g.dyn_slot = 0xFF;
     if (e.kind != CX_KIND_STATIC) {
       if (n_dyn >= CX_MAX_DYN) {
@@ -460,6 +504,68 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
         break;
       default:
         g.init_state = 0;
+    }
+  }
+  // ---- render state that changes during play: extra dynamic slots behind those of the moving entities ----
+  bool dyn_vis, dyn_z, dyn_bd;
+  dynamic_render_needs(d, &dyn_vis, &dyn_z, &dyn_bd);
+  H->dyn_render = (dyn_vis || dyn_z || dyn_bd) ? 1 : 0;
+  H->slot_vis = H->slot_zperm = H->slot_bd = -1;
+  for (int z = 0; z < E; ++z)
+    if (H->ent[z].dyn_slot != 0xFF) H->slot_init[H->ent[z].dyn_slot] = H->ent[z].init_state;
+  if (H->dyn_render) {
+    const int need = (dyn_vis ? 1 : 0) + (dyn_z ? 2 : 0) + (dyn_bd ? 1 : 0);
+    if (n_dyn + need > CX_MAX_DYN) {
+      cx_set_error("cx_game_create: %d moving entities + %d render-state slots exceed %d state slots", n_dyn, need,
+                   CX_MAX_DYN);
+      return CX_ERR_UNSUPPORTED;
+    }
+    if (dyn_z && E > CX_ZPERM_MAX_ENT) {
+      cx_set_error("cx_game_create: z-order directives are supported for games of at most %d sprites and drapes",
+                   CX_ZPERM_MAX_ENT);
+      return CX_ERR_UNSUPPORTED;
+    }
+    if (dyn_vis) {
+      uint16_t bits = 0;
+      for (int z = 0; z < E; ++z)
+        if (H->ent[z].kind == CX_KIND_SPRITE && H->ent[z].visible) bits |= (uint16_t)(1u << z);
+      H->slot_vis = n_dyn;
+      H->slot_init[n_dyn++] = bits;
+    }
+    if (dyn_z) {
+      H->slot_zperm = n_dyn;
+      H->slot_init[n_dyn++] = 0x3210;
+      H->slot_init[n_dyn++] = 0x7654;
+    }
+    if (dyn_bd) {
+      H->slot_bd = n_dyn;
+      H->slot_init[n_dyn++] = 0;
+    }
+    // With visibility or z-order changes any sprite may come to lie, visibly, behind the first drape and
+    // stamp the backdrop (quirk Q1): keep a per-env plane whenever the game has both sprites and drapes.
+    bool any_sprite = false;
+    for (int z = 0; z < E; ++z) any_sprite |= d->entities[z].kind == CX_KIND_SPRITE;
+    if ((dyn_vis || dyn_z) && any_sprite && !H->zero_backdrop) any_stamp = true;
+    if (dyn_bd && any_stamp) {
+      cx_set_error("cx_game_create: a rolling backdrop together with sprites that stamp the backdrop "
+                   "(sprites behind the first drape, SURVEY quirk Q1) is not supported");
+      return CX_ERR_UNSUPPORTED;
+    }
+    memcpy(H->bd_dr, d->backdrop_dr, CX_MAX_ACTIONS);
+    memcpy(H->bd_dc, d->backdrop_dc, CX_MAX_ACTIONS);
+    for (int a = 0; a < A; ++a) {
+      int k = 0;
+      for (int i = 0; i < E; ++i) {  // directives are applied in call order = update order (plot.py:157-159)
+        const cx_entity_desc& e = d->entities[order[i]];
+        for (int j = 0; j < e.n_zdirs[a]; ++j) {
+          if (k >= CX_MAX_ZDIR_GAME) {
+            cx_set_error("cx_game_create: more than %d z-order directives in one step", CX_MAX_ZDIR_GAME);
+            return CX_ERR_UNSUPPORTED;
+          }
+          H->zdir[a][k++] = (uint8_t)((e.z_move[a][j] << 4) | (e.z_front[a][j] < 0 ? 0xF : e.z_front[a][j]));
+        }
+      }
+      H->n_zdir[a] = (uint8_t)k;
     }
   }
   H->n_dyn = n_dyn;
@@ -496,7 +602,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     }
   }
   // direct composer eligibility (see CxGenHeader::direct)
-  bool direct_ok = cells >= 16 && E > 0;
+  bool direct_ok = cells >= 16 && E > 0 && !H->dyn_render;
   {
     bool ok = direct_ok;
     if (const char* dbg = getenv("CX_GEN_DIRECT")) ok = ok && atoi(dbg) != 0;  // development knob
@@ -536,7 +642,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     if (per_env) g.lin_slot = (uint8_t)(n_lin < 255 ? n_lin : 254), ++n_lin;
   }
   H->n_lin = n_lin;
-  H->fast_compose = (n_lin <= CX_MAX_LIN && !wide_roll && cells >= 16) ? 1 : 0;
+  H->fast_compose = (n_lin <= CX_MAX_LIN && !wide_roll && cells >= 16 && !H->dyn_render) ? 1 : 0;
   if (const char* dbg = getenv("CX_GEN_SLOW")) {  // development knob: force the per-cell composer
     if (atoi(dbg)) H->fast_compose = 0;
   }
@@ -616,7 +722,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
   for (int z = 0; z < E; ++z)
     if (H->ent[z].stamps) H->stamper[H->n_stampers++] = (uint16_t)((H->ent[z].ch << 8) | H->ent[z].dyn_slot);
   {
-    bool simple = !needs_prev && H->n_groups == 1;
+    bool simple = !needs_prev && H->n_groups == 1 && !H->dyn_render;
     if (const char* dbg = getenv("CX_GEN_SIMPLE")) simple = simple && atoi(dbg) != 0;  // development knob
     for (int z = 0; z < E; ++z) {
       const CxGenEntity& g = H->ent[z];
@@ -645,7 +751,7 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     H->off_sdelta = B->reserve((size_t)CX_MAX_ACTIONS * CX_MAX_DYN * 2);
     uint16_t* sd = (uint16_t*)&B->bytes[H->off_sdelta];
     H->roll_slots = 0;
-    for (int dslot = 0; dslot < n_dyn; ++dslot) {
+    for (int dslot = 0; dslot < n_dyn && !H->dyn_render; ++dslot) {
       if (H->slot_kind[dslot] == CX_KIND_ROLL) H->roll_slots |= 1u << dslot;
       for (int a = 0; a < A; ++a)
         sd[a * CX_MAX_DYN + dslot] =
@@ -724,6 +830,7 @@ extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
   I.tracks = tracks;
   I.has_dynamic_backdrop = g->path == CX_PATH_GENERIC ? g->gh.has_dynbd : 0;
   I.board_bytes_per_env = cells;
+  I.dynamic_render = g->path == CX_PATH_GENERIC ? g->gh.dyn_render : 0;
   I.state_bytes_per_env = (g->path == CX_PATH_AGENT ? 1 : 2 * g->gh.n_dyn) + (tracks ? 6 : 0) +
                           (I.has_dynamic_backdrop ? cells : 0);
 
@@ -902,6 +1009,13 @@ extern "C" int cx_get_episode_state(const cx_game* g, const void* d_state, int64
     return CX_ERR_INVALID_ARG;
   }
   return cx_launch_get_episode(g, d_state, n, d_steps, d_returns, (cudaStream_t)stream);
+}
+
+extern "C" int cx_get_render_state(const cx_game* g, const void* d_state, int64_t n, uint32_t* d_zorder,
+                                   uint32_t* d_visible, int32_t* d_backdrop_off, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_get_render_state");
+  if (rc) return rc;
+  return cx_launch_get_render_state(g, d_state, n, d_zorder, d_visible, d_backdrop_off, (cudaStream_t)stream);
 }
 
 extern "C" int cx_stats_read(const cx_game* g, const void* d_state, double* h_out, void* stream) {

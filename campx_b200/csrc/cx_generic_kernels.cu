@@ -88,11 +88,50 @@ __device__ __forceinline__ bool mask_bit(const Ctx& X, int z, int cell) {
   return (X.masks[z * X.H->mask_words + (cell >> 5)] >> (cell & 31)) & 1u;
 }
 
+// ---- render state that changes during play (CxGenHeader::dyn_render) ----------------------------------------
+// z-order of this env: 4 bits per position back to front (engine.py:242-281 rebuilds the OrderedDict)
+__device__ __forceinline__ uint32_t zperm_of(const CxGenHeader& H, const uint16_t* st) {
+  return H.slot_zperm >= 0 ? (uint32_t)st[H.slot_zperm] | ((uint32_t)st[H.slot_zperm + 1] << 16) : 0x76543210u;
+}
+__device__ __forceinline__ int z_at(const CxGenHeader& H, uint32_t perm, int p) {
+  return H.slot_zperm >= 0 ? (int)((perm >> (4 * p)) & 15u) : p;
+}
+// Sprite.visible (things.py:390-392; engine.py:315 paints visible sprites only)
+__device__ __forceinline__ bool visible_now(const CxGenHeader& H, const uint16_t* st, int z) {
+  return H.slot_vis >= 0 ? ((st[H.slot_vis] >> z) & 1u) != 0 : H.ent[z].visible != 0;
+}
+// Backdrop character at `cell`: the per-env plane, or the static scenery rolled by the backdrop's offset
+// (Backdrop.update, things.py:103-148, fitted as a toroidal roll of its curtain)
+__device__ __forceinline__ uint8_t backdrop_at(const Ctx& X, const uint16_t* st, const uint8_t* plane, int cell) {
+  const CxGenHeader& H = *X.H;
+  if (H.slot_bd < 0) return plane[cell];
+  const uint32_t off = st[H.slot_bd], rcv = X.rc[cell];
+  int r = (int)(rcv >> 8) - (int)(off >> 8), c = (int)(rcv & 255) - (int)(off & 255);
+  if (r < 0) r += H.rows;
+  if (c < 0) c += H.cols;
+  return X.backdrop[r * H.cols + c];
+}
+// the_plot.change_z_order(move_this, in_front_of_that): engine.py:262-279
+__device__ __forceinline__ uint32_t apply_zdir(uint32_t perm, int n_ent, uint32_t mv, uint32_t fr) {
+  uint32_t out = 0;
+  int k = 0;
+  if (fr == 0xFu) out |= mv << (4 * k++);  // in_front_of_that is None: all the way to the back
+  for (int p = 0; p < n_ent; ++p) {
+    const uint32_t z = (perm >> (4 * p)) & 15u;
+    if (z == mv) continue;
+    out |= z << (4 * k++);
+    if (z == fr) out |= mv << (4 * k++);
+  }
+  return out;
+}
+
 // Painter's algorithm at ONE cell on top of backdrop byte v (engine.py:310-321).  Used for the few
 // point queries of the last render (wall gate, entry rewards) and by the wide-board fallback.
 __device__ __forceinline__ uint8_t overlay(const Ctx& X, const uint16_t* st, int cell, uint8_t v) {
   const CxGenHeader& H = *X.H;
-  for (int z = 0; z < H.n_ent; ++z) {
+  const uint32_t perm = zperm_of(H, st);
+  for (int p = 0; p < H.n_ent; ++p) {
+    const int z = z_at(H, perm, p);
     const CxGenEntity& e = H.ent[z];
     bool covers;
     switch (e.kind) {
@@ -107,8 +146,11 @@ __device__ __forceinline__ uint8_t overlay(const Ctx& X, const uint16_t* st, int
         covers = mask_bit(X, z, r * H.cols + c);
         break;
       }
-      default:  // CELL drape or SPRITE: one cell
-        covers = e.visible && st[e.dyn_slot] == cell;
+      case CX_KIND_SPRITE:
+        covers = visible_now(H, st, z) && st[e.dyn_slot] == cell;
+        break;
+      default:  // CELL drape: one cell
+        covers = st[e.dyn_slot] == cell;
     }
     if (covers) v = e.ch;
   }
@@ -138,6 +180,17 @@ __device__ __forceinline__ uint64_t entity_row(const Ctx& X, const uint16_t* st,
 // rendering.py:150 through the alias of :128 -- sprites behind the first drape paint into the backdrop
 __device__ __forceinline__ void stamp(const Ctx& X, const uint16_t* st, uint8_t* plane) {
   const CxGenHeader& H = *X.H;
+  if (H.dyn_render) {  // who lies behind the first drape, and is visible, depends on this env's state
+    if (!H.has_dynbd) return;
+    const uint32_t perm = zperm_of(H, st);
+    for (int p = 0; p < H.n_ent; ++p) {
+      const int z = z_at(H, perm, p);
+      const CxGenEntity& e = H.ent[z];
+      if (e.kind != CX_KIND_SPRITE) break;  // rendering.py:178: the first drape re-seats the canvas
+      if (visible_now(H, st, z)) plane[st[e.dyn_slot]] = e.ch;
+    }
+    return;
+  }
   for (int i = 0; i < H.n_stampers; ++i) {
     const uint32_t sp = H.stamper[i];
     plane[st[sp & 0xFF]] = (uint8_t)(sp >> 8);
@@ -169,6 +222,12 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
     return;
   }
   for (int d = 0; d < H.n_dyn; ++d) prev[d] = st[d];
+  if (H.slot_bd >= 0) {  // engine.py:190: the backdrop updates first; entities still see the last render
+    const uint32_t off = st[H.slot_bd];
+    uint32_t rr, cc;
+    wrap_move(H, off >> 8, off & 255, H.bd_dr[a], H.bd_dc[a], &rr, &cc);
+    st[H.slot_bd] = (uint16_t)((rr << 8) | cc);
+  }
   float summed = 0.0f;
   bool first = true;
   int group = H.n_ent > 0 ? H.ent[H.update_order[0]].group : 0;
@@ -188,11 +247,12 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
         const uint32_t rcv = X.rc[p];
         uint32_t t = wrap_move(H, rcv >> 8, rcv & 255, dr, dc, &rr, &cc);
         if (e.blockers) {
-          const uint8_t k = X.chidx[overlay(X, prev, (int)t, plane[t])];
+          const uint8_t k = X.chidx[overlay(X, prev, (int)t, backdrop_at(X, prev, plane, (int)t))];
           if (k != 0xFF && ((e.blockers >> k) & 1u)) {
             // fall back to the agent layer of the last render (boat_race.py:55-56)
             const uint32_t pp = prev[e.dyn_slot];
-            const bool vis = pp != CX_EMPTY_CELL16 && overlay(X, prev, (int)pp, plane[pp]) == e.ch;
+            const bool vis = pp != CX_EMPTY_CELL16 &&
+                             overlay(X, prev, (int)pp, backdrop_at(X, prev, plane, (int)pp)) == e.ch;
             t = vis ? pp : CX_EMPTY_CELL16;
           }
         }
@@ -202,6 +262,10 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
       const uint32_t rcv = X.rc[st[e.dyn_slot]];
       uint32_t rr, cc;
       st[e.dyn_slot] = (uint16_t)wrap_move(H, rcv >> 8, rcv & 255, dr, dc, &rr, &cc);
+      if (H.slot_vis >= 0 && e.vis_op[a] != CX_VIS_KEEP) {
+        const uint32_t bit = 1u << z, bits = st[H.slot_vis], op = e.vis_op[a];
+        st[H.slot_vis] = (uint16_t)(op == CX_VIS_SHOW ? bits | bit : op == CX_VIS_HIDE ? bits & ~bit : bits ^ bit);
+      }
     } else if (e.kind == CX_KIND_ROLL) {
       const uint32_t off = st[e.dyn_slot];
       uint32_t rr, cc;
@@ -213,7 +277,7 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
       if (e.watch != 0xFF) {
         const uint32_t wc = st[H.ent[e.watch].dyn_slot];  // things[...] is current, not last-render, state
         if (wc != CX_EMPTY_CELL16) {
-          const uint8_t k = X.chidx[overlay(X, prev, (int)wc, plane[wc])];
+          const uint8_t k = X.chidx[overlay(X, prev, (int)wc, backdrop_at(X, prev, plane, (int)wc))];
           if (k != 0xFF) r = __fadd_rn(r, X.entry[(z * H.n_actions + a) * H.n_chars + k]);
         }
       }
@@ -222,6 +286,13 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
     }
   }
   stamp(X, st, plane);  // the render that produces this step's observation
+  if (H.slot_zperm >= 0 && H.n_zdir[a]) {  // engine.py:242-281, then the re-render of engine.py:163
+    uint32_t perm = zperm_of(H, st);
+    for (int i = 0; i < H.n_zdir[a]; ++i) perm = apply_zdir(perm, H.n_ent, H.zdir[a][i] >> 4, H.zdir[a][i] & 15u);
+    st[H.slot_zperm] = (uint16_t)perm;
+    st[H.slot_zperm + 1] = (uint16_t)(perm >> 16);
+    stamp(X, st, plane);
+  }
   reward = summed;
   disc = H.act.discount[a];
   flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
@@ -744,7 +815,7 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int
     const uint32_t inv_cells = div_inverse((uint32_t)cells);
     for (int b = lane; b < nenv * cells; b += 32) {
       const int e = (int)fast_div((uint32_t)b, inv_cells), cell = b - e * cells;
-      dst[b] = overlay(X, W.dyn[e], cell, W.plane[b]);
+      dst[b] = overlay(X, W.dyn[e], cell, backdrop_at(X, W.dyn[e], W.plane + e * cells, cell));
     }
   }
   __syncwarp();
@@ -887,8 +958,7 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
     if (rmask) {
       if (reset_me) {
-        for (int z = 0; z < H.n_ent; ++z)
-          if (H.ent[z].dyn_slot != 0xFF) dyn[lane][H.ent[z].dyn_slot] = H.ent[z].init_state;
+        for (int d = 0; d < H.n_dyn; ++d) dyn[lane][d] = H.slot_init[d];
         if (FAST) fast_load_state(X, dyn[lane], sreg);
       }
       if (H.has_dynbd) {

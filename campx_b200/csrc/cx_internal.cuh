@@ -23,6 +23,8 @@
 #define CX_GEN_CTA_THREADS 128
 #define CX_MAX_DYN 8             // moving entities in the generic path
 #define CX_MAX_LIN 4             // per-env mask bitsets the fast composer keeps in shared memory
+#define CX_MAX_ZDIR_GAME 8       // change_z_order directives of a whole game in one step
+#define CX_ZPERM_MAX_ENT 8       // games whose z-order changes: 8 entities x 4 bits = two 16-bit state slots
 
 // ---- per-action engine directives, identical for both paths (plot.py:161-257, engine.py:285-290) ----
 struct CxActionTable {
@@ -71,6 +73,7 @@ struct CxGenEntity {
   float step_reward[CX_MAX_ACTIONS];
   uint16_t init_state;      // cell / linear offset after its_showtime
   uint16_t pad2;
+  uint8_t vis_op[CX_MAX_ACTIONS];  // sprites: cx_visible_op per action
 };
 
 struct CxGenHeader {
@@ -121,6 +124,17 @@ struct CxGenHeader {
   uint16_t stamper[CX_MAX_DYN];          // back to front: ch << 8 | dyn_slot of the sprites that stamp the plane
   int32_t blob_bytes;
   CxActionTable act;
+  // ---- render state that changes during play; such games run on the general step +
+  // per-cell painter only.  The state lives in ordinary dynamic slots behind those of the moving entities.
+  int32_t dyn_render;       // any of the three below
+  int32_t slot_vis;         // slot with the sprite visibility bits (bit z: entity z is visible); -1: static
+  int32_t slot_zperm;       // first of two slots with the z-order, 4 bits per position back to front
+                            // (entity ids = initial z indices); -1: static
+  int32_t slot_bd;          // slot with the backdrop's roll offset (row << 8 | col); -1: static backdrop
+  uint16_t slot_init[CX_MAX_DYN];  // its_showtime value of every dynamic slot
+  int8_t bd_dr[CX_MAX_ACTIONS], bd_dc[CX_MAX_ACTIONS];
+  uint8_t n_zdir[CX_MAX_ACTIONS];
+  uint8_t zdir[CX_MAX_ACTIONS][CX_MAX_ZDIR_GAME];  // move_this << 4 | in_front_of_that (0xF: None), in call order
 };
 
 // ---- state blob layout (caller-allocated; see cx_state_bytes) ----
@@ -185,3 +199,5 @@ int cx_launch_set_entity(const cx_game* g, void* d_state, int64_t n, int32_t z, 
                          cudaStream_t s);
 int cx_launch_get_episode(const cx_game* g, const void* d_state, int64_t n, int32_t* d_steps, float* d_ret,
                           cudaStream_t s);
+int cx_launch_get_render_state(const cx_game* g, const void* d_state, int64_t n, uint32_t* d_zorder,
+                               uint32_t* d_visible, int32_t* d_backdrop_off, cudaStream_t s);

@@ -32,6 +32,8 @@ class EntitySpec:
     entry_reward: Optional[Dict[int, Dict[str, float]]] = None   # action -> {char seen: extra reward}
     terminate: Optional[Dict[int, float]] = None          # action -> discount passed to terminate_episode
     discount: Optional[Dict[int, float]] = None           # action -> change_default_discount value
+    visible_op: Optional[List[int]] = None                # sprites, per action: CX_VIS_* applied to Sprite.visible
+    z_orders: Optional[Dict[int, List[tuple]]] = None     # action -> [(move_this, in_front_of_that or None), ...]
 
     def summary(self):
         out = {"char": self.character, "kind": KIND_NAMES[self.kind], "rank": self.update_rank,
@@ -52,6 +54,10 @@ class EntitySpec:
         if self.kind == N.CX_KIND_SPRITE:
             out["init_pos"] = tuple(self.init_pos)
             out["visible"] = bool(self.visible)
+        if self.visible_op and any(self.visible_op):
+            out["visible_op"] = [("keep", "show", "hide", "toggle")[v] for v in self.visible_op]
+        if self.z_orders:
+            out["z_orders"] = {a: list(v) for a, v in sorted(self.z_orders.items())}
         return out
 
 
@@ -70,11 +76,14 @@ class GameSpec:
     first_reward: Optional[float] = None
     first_discount: float = 1.0
     action_format: str = "index"          # how the world's update() methods take actions (host side only)
+    backdrop_moves: Optional[List[tuple]] = None   # per action (d_row, d_col): Backdrop.update() rolls its curtain
 
     def summary(self):
         return {"rows": self.rows, "cols": self.cols, "chars": self.chars, "n_actions": self.n_actions,
                 "n_groups": self.n_groups, "action_format": self.action_format,
                 "first_reward": self.first_reward, "first_discount": self.first_discount,
+                **({"backdrop_moves": [tuple(m) for m in self.backdrop_moves]}
+                   if self.backdrop_moves and any(m != (0, 0) for m in self.backdrop_moves) else {}),
                 "entities": [e.summary() for e in self.entities]}
 
     def validate(self):
@@ -138,6 +147,16 @@ class GameSpec:
                     ta |= 1 << a
                     c.discount_value[a] = float(e.terminate[a])
             c.reward_actions, c.terminate_actions, c.discount_actions = ra, ta, da
+            for a in range(self.n_actions):
+                c.visible_op[a] = int(e.visible_op[a]) if e.visible_op else N.CX_VIS_KEEP
+                zd = (e.z_orders or {}).get(a) or []
+                if len(zd) > N.CX_MAX_ZDIRS:
+                    raise NotImplementedError("more than %d change_z_order calls by one entity in one step"
+                                              % N.CX_MAX_ZDIRS)
+                c.n_zdirs[a] = len(zd)
+                for k, (move_this, front_of) in enumerate(zd):
+                    c.z_move[a][k] = z_of[move_this]
+                    c.z_front[a][k] = -1 if front_of is None else z_of[front_of]
         backdrop = np.ascontiguousarray(np.asarray(self.backdrop, dtype=np.uint8).reshape(-1))
         masks = np.ascontiguousarray(masks)
         d.backdrop = backdrop.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
@@ -147,4 +166,6 @@ class GameSpec:
         d.track_returns = 1 if self.track_returns else 0
         d.first_reward = float("nan") if self.first_reward is None else float(self.first_reward)
         d.first_discount = float(self.first_discount)
+        for a, (dr, dc) in enumerate(self.backdrop_moves or []):
+            d.backdrop_dr[a], d.backdrop_dc[a] = int(dr), int(dc)
         return d, (backdrop, masks)

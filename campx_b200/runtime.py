@@ -209,6 +209,17 @@ class NativeGame(object):
             N.check(self._lib.cx_set_entity_state(self._handle, _ptr(self.state), self.num_envs,
                                                   self._z_of[character], _ptr(cells), _stream()))
 
+    def render_state(self):
+        """(z_order uint32 [N]: 4 bits per z position back to front = entity id, visible uint32 [N]: bit z,
+        backdrop_offset int32 [N]: row * cols + col) -- the render state of games where it changes during play."""
+        z = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        vis = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        off = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_get_render_state(self._handle, _ptr(self.state), self.num_envs, _ptr(z), _ptr(vis),
+                                                  _ptr(off), _stream()))
+        return z, vis, off
+
     def episode_state(self):
         steps = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
         returns = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)

@@ -52,13 +52,14 @@ extern "C" {
 #define CX_API
 #endif
 
-#define CX_ABI_VERSION 1
+#define CX_ABI_VERSION 2
 
 #define CX_MAX_ENTITIES 16   /* sprites + drapes in one game                         */
 #define CX_MAX_ACTIONS 8     /* discrete actions                                     */
 #define CX_MAX_CHARS 32      /* distinct characters (entities + backdrop palette)    */
 #define CX_MAX_CELLS 4096    /* rows * cols                                          */
 #define CX_MAX_GROUPS 8      /* update groups                                        */
+#define CX_MAX_ZDIRS 2       /* change_z_order calls of one entity in one step       */
 
 typedef enum cx_status {
   CX_OK = 0,
@@ -111,7 +112,25 @@ typedef struct cx_entity_desc {
                               at the watched entity's current cell (boat_race.py:79-87: k == own
                               char; Demo 3 cell 3: k in reward_chars)                            */
   float discount_value[CX_MAX_ACTIONS]; /* argument of terminate_episode / change_default_discount */
+  /* --- engine generality: state that the six reference worlds keep constant --- */
+  uint8_t visible_op[CX_MAX_ACTIONS];
+                           /* SPRITE: what update() does to Sprite.visible (things.py:320,390-392) for
+                              action a: cx_visible_op.  Invisible sprites are neither painted
+                              (engine.py:315) nor, by quirk Q1, stamped into the backdrop              */
+  uint8_t n_zdirs[CX_MAX_ACTIONS];
+                           /* number of the_plot.change_z_order(move_this, in_front_of_that) calls
+                              (plot.py:121-159) update() makes for action a; applied after all updates
+                              in call order, then the board is re-rendered (engine.py:242-281,163)     */
+  int8_t z_move[CX_MAX_ACTIONS][CX_MAX_ZDIRS];  /* z-index (initial order) of move_this                  */
+  int8_t z_front[CX_MAX_ACTIONS][CX_MAX_ZDIRS]; /* z-index of in_front_of_that; -1: None = to the back  */
 } cx_entity_desc;
+
+typedef enum cx_visible_op {
+  CX_VIS_KEEP = 0,
+  CX_VIS_SHOW = 1,
+  CX_VIS_HIDE = 2,
+  CX_VIS_TOGGLE = 3
+} cx_visible_op;
 
 /* A whole game, as produced by the host-side game compiler at Engine.its_showtime(). */
 typedef struct cx_game_desc {
@@ -131,6 +150,8 @@ typedef struct cx_game_desc {
   int32_t track_returns;   /* 1: keep per-env episode return/length and global episode stats      */
   float first_reward;      /* its_showtime() outputs (engine.py:544): reward (NaN == None) ...    */
   float first_discount;    /* ... and discount                                                    */
+  int8_t backdrop_dr[CX_MAX_ACTIONS]; /* Backdrop.update() (things.py:103-148) rolls its curtain toroidally */
+  int8_t backdrop_dc[CX_MAX_ACTIONS]; /*   by this much for action a (scrolling scenery); 0: static         */
 } cx_game_desc;
 
 typedef struct cx_game cx_game; /* opaque */
@@ -144,6 +165,8 @@ typedef struct cx_game_info {
                               backdrop (rendering.py:128,150)                                     */
   int32_t state_bytes_per_env;  /* algorithmic state bytes per env (excl. alignment)             */
   int32_t board_bytes_per_env;  /* rows*cols                                                     */
+  int32_t dynamic_render;  /* z-order, sprite visibility or the backdrop change during play: the game
+                              runs on the general (per-cell painter) kernel                          */
 } cx_game_info;
 
 /* Episode statistics kept at the head of the state blob (8 doubles), all-reducible as-is. */
@@ -232,6 +255,15 @@ CX_API int cx_get_entity_state(const cx_game* game, const void* d_state, int64_t
                         int32_t* d_cells, void* stream);
 CX_API int cx_set_entity_state(const cx_game* game, void* d_state, int64_t n_envs, int32_t z_index,
                         const int32_t* d_cells, void* stream);
+
+/* Render state of games whose z-order, sprite visibility or backdrop change during play
+ * (info.dynamic_render; Engine._sprites_and_drapes order engine.py:242-281, Sprite.visible things.py:390-392,
+ * Backdrop.curtain).  Any output may be NULL.
+ *   d_zorder       [n] uint32  4 bits per z position, back to front: entity id (= initial z index)
+ *   d_visible      [n] uint32  bit z: entity z is a visible sprite
+ *   d_backdrop_off [n] int32   accumulated roll of the backdrop, row * cols + col */
+CX_API int cx_get_render_state(const cx_game* game, const void* d_state, int64_t n_envs, uint32_t* d_zorder,
+                        uint32_t* d_visible, int32_t* d_backdrop_off, void* stream);
 
 /* Per-env episode counters (valid when info.tracks): d_steps [n] int32, d_returns [n] float32. */
 CX_API int cx_get_episode_state(const cx_game* game, const void* d_state, int64_t n_envs, int32_t* d_steps,

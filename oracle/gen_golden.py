@@ -56,11 +56,11 @@ def ref_frame_record(game, obs, reward, discount):
 
 
 def encode_action(world, index):
-    if world == "hello":
+    if world in ("hello", "zswap", "ghost"):
         return int(index)
     onehot = [0] * 5
     onehot[int(index)] = 1
-    if world in ("boat_race", "demo4"):
+    if world in ("boat_race", "demo4", "scroll"):
         return torch.FloatTensor(onehot)
     return onehot
 
@@ -75,8 +75,130 @@ _NOTEBOOKS = {
 _ns_cache = {}
 
 
+# ---- engine-generality worlds, written against the REFERENCE API -------------------------
+# None of the reference's own worlds changes its z-order, hides a sprite or updates its backdrop, so these
+# three small worlds exercise campx/engine.py:242-281,163 (z-order directives + re-render), things.py:320,
+# 390-392 + engine.py:315 (Sprite.visible) and things.py:103-148 (Backdrop.update) on the reference itself.
+ZSWAP_ART = ["S.....",
+             ".XX.Y.",
+             ".XXYY.",
+             "...YY.",
+             "......"]
+GHOST_ART = ["G..@.",
+             "..@..",
+             "H...."]
+SCROLL_ART = ["A.~~.^",
+              ".~..^.",
+              "~..^..",
+              "..^..~"]
+GENERALITY_WORLDS = ("zswap", "ghost", "scroll")
+
+
+def make_ref_generality_game(world):
+    from campx import things
+    from campx.ascii_art import ascii_art_to_game, Partial
+
+    def roll(t, shift, axis):
+        return torch.from_numpy(np.roll(t.numpy(), shift, axis).copy())
+
+    if world == "zswap":
+        class XDrape(things.Drape):
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                if actions == 0:
+                    self.curtain.set_(roll(self.curtain, 1, 1))
+                    the_plot.add_reward(1)
+                if actions == 1:
+                    the_plot.change_z_order("X", "Y")
+                if actions == 2:
+                    the_plot.change_z_order("Y", None)
+                if actions == 3:
+                    the_plot.change_z_order("X", None)
+                    the_plot.change_z_order("Y", "X")
+
+        class SSprite(things.Sprite):
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                row, col = self.position
+                if actions == 0:
+                    col = (col + 1) % self.corner.col
+                if actions == 1:
+                    row = (row + 1) % self.corner.row
+                self._position = self.Position(row, col)
+                if actions == 4:
+                    the_plot.change_z_order("S", "Y")
+                if actions == 2:
+                    the_plot.change_z_order("S", None)
+
+        return ascii_art_to_game(ZSWAP_ART, ".", sprites={"S": SSprite},
+                                 drapes={"X": XDrape, "Y": things.FixedDrape},
+                                 update_schedule="SXY", z_order="SXY")
+    if world == "ghost":
+        class Ghost(things.Sprite):
+            def __init__(self, corner, position, character, start_visible, d_row, d_col):
+                super(Ghost, self).__init__(corner, position, character)
+                self._visible = start_visible
+                self._d = (d_row, d_col)
+
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                row, col = self.position
+                if actions == 0:
+                    col = (col + self._d[1]) % self.corner.col
+                if actions == 1:
+                    row = (row + self._d[0]) % self.corner.row
+                self._position = self.Position(row, col)
+                if self.character == "G":
+                    if actions == 2:
+                        self._visible = False
+                    if actions == 3:
+                        self._visible = True
+                if actions == 4:
+                    self._visible = not self._visible
+
+        class Rain(things.Drape):
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                if actions == 1:
+                    self.curtain.set_(roll(self.curtain, 1, 0))
+                the_plot.add_reward(0.5)
+
+        return ascii_art_to_game(GHOST_ART, ".",
+                                 sprites={"G": Partial(Ghost, True, 1, 1), "H": Partial(Ghost, False, 1, -1)},
+                                 drapes={"@": Rain}, update_schedule="GH@", z_order="GH@")
+    if world == "scroll":
+        import boat_race
+
+        class Scroller(things.Backdrop):
+            def update(self, actions, board, layers, all_things, the_plot):
+                if actions is None:
+                    return
+                a = int(torch.as_tensor(actions).argmax())
+                if a < 4:
+                    shift, axis = ((-1, 1), (1, 1), (-1, 0), (1, 0))[a]
+                    self.curtain.set_(roll(self.curtain, shift, axis))
+
+        class Hiker(boat_race.AgentDrape):       # the reference's own agent: stops at '^' instead of '#'
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                super(Hiker, self).update(actions, board, layers, backdrop, all_things, the_plot)
+                if actions is not None:
+                    the_plot.add_reward(1)
+
+        return ascii_art_to_game(SCROLL_ART, ".", drapes={"A": Partial(Hiker, blocking_chars="^")},
+                                 backdrop=Scroller, z_order="A")
+    raise KeyError(world)
+
+
 def make_ref_game(world):
     """-> (game, first_obs, first_reward, first_discount) from the reference's own make_game()."""
+    if world in GENERALITY_WORLDS:
+        game = make_ref_generality_game(world)
+        obs, reward, discount = game.its_showtime()
+        return game, obs, reward, discount
     if world == "boat_race":
         import boat_race
         return boat_race.make_game()
@@ -237,6 +359,21 @@ def main():
     for world, kw in jobs.items():
         fx = world_fixture(world, **kw)
         path = os.path.join(GOLDEN_DIR, world + ".json")
+        with open(path, "w") as f:
+            json.dump(fx, f, separators=(",", ":"))
+        print(world, "->", path, os.path.getsize(path), "bytes;",
+              sum(len(e["frames"]) for e in fx["episodes"]), "frames")
+    gen_jobs = {
+        "zswap": dict(scripted=[("each_action", [0, 1, 0, 2, 0, 3, 4, 0, 1, 2, 1, 1, 0, 3, 0, 0, 4])],
+                      n_random=3, random_len=60, seed=21, action_hi=5),
+        "ghost": dict(scripted=[("each_action", [0, 1, 2, 0, 3, 4, 1, 4, 0, 0, 2, 2, 3, 1, 4, 4])],
+                      n_random=3, random_len=60, seed=22, action_hi=5),
+        "scroll": dict(scripted=[("each_action", [0, 1, 1, 2, 3, 3, 4, 1, 1, 1, 3, 0, 2, 2])],
+                       n_random=3, random_len=60, seed=23, action_hi=5),
+    }
+    for world, kw in gen_jobs.items():
+        fx = world_fixture(world, **kw)
+        path = os.path.join(GOLDEN_DIR, "generality_" + world + ".json")
         with open(path, "w") as f:
             json.dump(fx, f, separators=(",", ":"))
         print(world, "->", path, os.path.getsize(path), "bytes;",

@@ -54,12 +54,32 @@ def test_unsupported_behaviour_is_refused_not_approximated():
     with pytest.raises(NotImplementedError):
         g.compile()
 
-    class Zed(things.Drape):
+    class Zed(things.Drape):                     # engine.py:270-279 would drop 'Z' from the game altogether
         def update(self, actions, board, layers, backdrop, all_things, the_plot):
             if actions == 1:
-                the_plot.change_z_order("Z", None)
+                the_plot.change_z_order("Z", "Z")
 
     g = ascii_art_to_game(["Z."], ".", drapes={"Z": Zed}, action_format="index")
+    with pytest.raises((NotImplementedError, KeyError)):
+        g.compile()
+
+    class Blinker(things.Sprite):                # visibility depends on the position, not only on the action
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is not None:
+                self._position = self.Position(self.position.row, (self.position.col + 1) % self.corner.col)
+                self._visible = self.position.row == 0
+
+    g = ascii_art_to_game(["B...", "...."], ".", sprites={"B": Blinker}, action_format="index")
+    with pytest.raises(NotImplementedError):
+        g.compile()
+
+    class Painter(things.Backdrop):              # the backdrop changes, but not by a roll
+        def update(self, actions, board, layers, all_things, the_plot):
+            if actions is not None:
+                self.curtain[0, 0] = ord("x")
+
+    g = ascii_art_to_game(["W.x", "..."], ".", drapes={"W": things.FixedDrape}, backdrop=Painter,
+                          action_format="index")
     with pytest.raises(NotImplementedError):
         g.compile()
 
@@ -97,6 +117,21 @@ def test_custom_world_with_two_groups_and_discount():
     assert h["moves"] == [(0, 1), (0, -1), (0, 0), (0, 0)]
     assert h["step_reward"] == [2.5] * 4
     assert h["terminate"] == {3: 0.25} and h["discount"] == {2: 0.5}
+
+
+def test_engine_generality_primitives():
+    """z-order directives, sprite visibility and a scrolling backdrop are fitted per action."""
+    from examples.generality_worlds import make_generality_world
+    s = make_generality_world("zswap").compile().summary()
+    x = [e for e in s["entities"] if e["char"] == "X"][0]
+    assert x["z_orders"] == {1: [("X", "Y")], 2: [("Y", None)], 3: [("X", None), ("Y", "X")]}
+    s = make_generality_world("ghost").compile().summary()
+    g = [e for e in s["entities"] if e["char"] == "G"][0]
+    assert g["visible_op"] == ["keep", "keep", "hide", "show", "toggle"] and g["visible"] is True
+    h = [e for e in s["entities"] if e["char"] == "H"][0]
+    assert h["visible"] is False and h["visible_op"][4] == "toggle"
+    s = make_generality_world("scroll").compile().summary()
+    assert s["backdrop_moves"] == [(0, -1), (0, 1), (-1, 0), (1, 0), (0, 0)]
 
 
 def _reference_present():

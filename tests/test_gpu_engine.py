@@ -9,11 +9,24 @@ import pytest
 import torch
 
 from oracle import campx_oracle as O
-from examples.worlds import make_world, BOAT_RACE_REGIONS
+from examples.worlds import make_world as _make_reference_world, BOAT_RACE_REGIONS
+from examples.generality_worlds import make_generality_world
 
 pytestmark = pytest.mark.gpu
 
-WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
+# the six reference worlds + the engine-generality worlds (z-order directives, sprite visibility, scrolling
+# backdrop: SURVEY 8(f) row 3), whose fixtures were also recorded from the reference (oracle/gen_golden.py)
+WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll"]
+
+
+def make_world(name, **kw):
+    if name in O.GENERALITY_WORLDS:
+        return make_generality_world(name, **kw)
+    return _make_reference_world(name, **kw)
+
+
+def golden_path(golden_dir, world):
+    return os.path.join(golden_dir, ("generality_" if world in O.GENERALITY_WORLDS else "") + world + ".json")
 
 
 def board_str(b):
@@ -22,17 +35,17 @@ def board_str(b):
 
 def ref_action(world, a):
     """The action object a reference user passes for index a (boat_race.py:26; notebooks)."""
-    if world == "hello":
+    if world in ("hello", "zswap", "ghost"):
         return int(a)
     onehot = [0] * 5
     onehot[a] = 1
-    return torch.FloatTensor(onehot) if world in ("boat_race", "demo4") else onehot
+    return torch.FloatTensor(onehot) if world in ("boat_race", "demo4", "scroll") else onehot
 
 
 @pytest.mark.parametrize("world", WORLDS)
 def test_single_env_drop_in_matches_golden(golden_dir, world):
     """num_envs=None: reference shapes, reference action objects, reference error behaviour."""
-    with open(os.path.join(golden_dir, world + ".json")) as f:
+    with open(golden_path(golden_dir, world)) as f:
         fx = json.load(f)
     for ep in fx["episodes"][:3]:
         game = make_world(world)
@@ -83,7 +96,7 @@ def test_batched_play_matches_oracle(world):
         acts[(acts == 4) & (rng.random((T, n)) < 0.7)] = 1
     oracles = [O.rollout(world, acts[:, i], rebuild_on_done=True, max_episode_steps=limit) for i in range(n)]
     for t in range(T):
-        if world in ("boat_race", "demo4") and t % 2:          # one-hot float batch, as the reference's worlds take
+        if world in ("boat_race", "demo4", "scroll") and t % 2:   # one-hot float batch, as the reference's worlds take
             a = torch.nn.functional.one_hot(torch.from_numpy(acts[t]).long(), 5).float().cuda()
         else:
             a = torch.from_numpy(acts[t]).cuda()

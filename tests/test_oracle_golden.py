@@ -12,11 +12,14 @@ import pytest
 
 from oracle import campx_oracle as O
 
-WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
+# the six reference worlds + the three engine-generality worlds (z-order directives, sprite
+# visibility, scrolling backdrop), all recorded from the reference itself by oracle/gen_golden.py
+WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll"]
 
 
 def load(golden_dir, world):
-    with open(os.path.join(golden_dir, world + ".json")) as f:
+    name = ("generality_" + world) if world in O.GENERALITY_WORLDS else world
+    with open(os.path.join(golden_dir, name + ".json")) as f:
         return json.load(f)
 
 
