@@ -121,6 +121,9 @@ PROTOTYPES = {
     "cx_rollout_observations": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "cx_layers_from_board": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_layers_from_board_f32": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "cx_board_mapper_create": (ctypes.c_int, [_P, _P, _I32, _I32, ctypes.POINTER(_P)]),
+    "cx_board_mapper_destroy": (ctypes.c_int, [_P]),
+    "cx_board_mapper_apply": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, ctypes.POINTER(_I32), _P, _P, _P]),
     "cx_onehot_to_index": (ctypes.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "cx_fill_actions": (ctypes.c_int, [_U64, _U64, _U64, _I32, _I64, _I32, _P, _P]),
     "cx_get_entity_state": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),

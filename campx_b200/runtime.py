@@ -279,3 +279,63 @@ class NativeGame(object):
         if not t.is_contiguous():
             raise ValueError("%s must be contiguous" % what)
         return t
+
+
+class BoardMapper(object):
+    """Device value table + the `cx_board_mapper_apply` launch: boards -> arrays of mapped values.
+
+    The device side of `rendering.ObservationToArray` / `ObservationToFeatureArray`
+    (campx/rendering.py:461-712).  `values` is a numpy array `[256, depth]` (the value of every byte a
+    board may hold), `known` a `[256]` bool array saying which bytes the mapping really covers.
+    """
+
+    def __init__(self, values, known, device=None):
+        import numpy as np
+        N.require_cuda()
+        self._lib = N.load()
+        values = np.ascontiguousarray(values)
+        if values.ndim != 2 or values.shape[0] != 256:
+            raise ValueError("values must have shape [256, depth]")
+        known = np.ascontiguousarray(known, dtype=np.uint8)
+        if known.shape != (256,):
+            raise ValueError("known must have shape [256]")
+        self.depth = int(values.shape[1])
+        self.np_dtype = values.dtype
+        self.elem_size = int(values.dtype.itemsize)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise N.NativeLibraryError("campx_b200 runs on CUDA devices only (got %s)" % self.device)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_board_mapper_create(values.ctypes.data_as(ctypes.c_void_p),
+                                                     known.ctypes.data_as(ctypes.c_void_p), self.depth,
+                                                     self.elem_size, ctypes.byref(self._handle)))
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.cx_board_mapper_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, board, out, permute=None, unknown=None):
+        """board uint8 [..., rows, cols] (contiguous) -> out [n_boards * depth * rows * cols] elements, in the
+        axis order `permute` asks for.  `unknown`: int32[1] device counter, nonzero afterwards if a board held
+        a byte outside the mapping."""
+        if board.dtype != torch.uint8 or not board.is_contiguous() or board.device != self.device:
+            raise ValueError("board must be a contiguous uint8 tensor on %s" % self.device)
+        rows, cols = int(board.shape[-2]), int(board.shape[-1])
+        nb = board.numel() // (rows * cols)
+        if out.device != self.device or not out.is_contiguous() or out.element_size() != self.elem_size \
+                or out.numel() != nb * self.depth * rows * cols:
+            raise ValueError("out must be a contiguous tensor of %d %d-byte elements on %s"
+                             % (nb * self.depth * rows * cols, self.elem_size, self.device))
+        perm = None if permute is None else (ctypes.c_int32 * 3)(*[int(p) for p in permute])
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_board_mapper_apply(self._handle, _ptr(board), nb, rows, cols, perm, _ptr(out),
+                                                    _ptr(unknown), _stream()))
+        return out

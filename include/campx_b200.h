@@ -19,6 +19,8 @@
  *   cx_layers_from_board[_f32]         <-  BaseObservationRenderer.render() campx/rendering.py:181-219
  *   cx_rollout_observations            <-  Engine.play() returning the full Observation(board, layers,
  *                                          layered_board)                   campx/rendering.py:29,181-219
+ *   cx_board_mapper_create/apply/destroy <- ObservationToArray (RGB / value rendering) and
+ *                                          ObservationToFeatureArray        campx/rendering.py:461-594,597-712
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
  *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
@@ -238,6 +240,22 @@ CX_API int cx_layers_from_board(const cx_game* game, const uint8_t* d_board, int
                          void* stream);
 CX_API int cx_layers_from_board_f32(const cx_game* game, const uint8_t* d_board, int64_t n_boards, float* d_layered,
                              void* stream);
+
+/* Board -> array conversion (ObservationToArray campx/rendering.py:461-594, ObservationToFeatureArray :597-712).
+ * A mapper holds the value mapping: h_values HOST [256][depth] elements of elem_size (1, 2, 4 or 8) bytes, the
+ * value (scalar: depth 1; 1-D vector, e.g. RGB: depth 3) of every byte a board may contain; h_known HOST [256],
+ * nonzero where the mapping has an entry.  depth * elem_size <= 128.  create/destroy synchronise (table upload). */
+typedef struct cx_board_mapper cx_board_mapper; /* opaque */
+CX_API int cx_board_mapper_create(const void* h_values, const uint8_t* h_known, int32_t depth, int32_t elem_size,
+                           cx_board_mapper** out);
+CX_API int cx_board_mapper_destroy(cx_board_mapper* mapper);
+/* d_board [n_boards, rows*cols] uint8 -> d_out [n_boards, s0, s1, s2] elements, where (s0, s1, s2) is
+ * (depth, rows, cols) reordered by `permute` (HOST int32[3], a permutation of 0 = vector, 1 = row, 2 = column as
+ * in rendering.py:478-489; NULL = (0, 1, 2); (1, 2, 0) = channels last).  Boards holding a byte without an entry
+ * (the reference raises RuntimeError, rendering.py:571-577) make *d_unknown (int32, device, may be NULL) nonzero;
+ * their output elements are the h_values rows of those bytes. */
+CX_API int cx_board_mapper_apply(const cx_board_mapper* mapper, const uint8_t* d_board, int64_t n_boards, int32_t rows,
+                          int32_t cols, const int32_t* permute, void* d_out, int32_t* d_unknown, void* stream);
 
 /* One-hot (or any argmax-able) float actions [n, n_actions] -> uint8 indices; rows that are not
  * exactly one-hot (boat_race.py:48 `assert sum(act) == 1`) set *d_bad_count (int32, device) += 1. */
