@@ -666,6 +666,12 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     }
   }
   H->n_masks = H->n_points = 0;
+  H->n_poke = H->n_above = 0;
+  {
+    int gcd16 = 16;
+    while (cells % gcd16) gcd16 >>= 1;
+    H->chunk_period = 16 / gcd16;
+  }
   for (int z = 0; z < E; ++z) {
     const CxGenEntity& g = H->ent[z];
     if (g.kind == CX_KIND_STATIC || g.kind == CX_KIND_ROLL) {
@@ -714,6 +720,12 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
           if (H->ent[y].kind == CX_KIND_STATIC || H->ent[y].kind == CX_KIND_ROLL) ++below;
         H->point_holes[i] = 0;
         if (below) H->point_prog[i] |= 2u << 24;  // above the masks: stored over the finished board
+      }
+      H->n_poke = H->n_above = 0;
+      for (int i = 0; i < H->n_points; ++i) {
+        const uint32_t prog = H->point_prog[i];
+        if (!(prog >> 24)) ++H->n_poke;
+        if ((prog >> 24) & 2u) H->above_prog[H->n_above++] = (uint16_t)((prog & 0xFF00u) | ((prog >> 16) & 0xFFu));
       }
     }
   }

@@ -644,7 +644,7 @@ __device__ __forceinline__ uint32_t direct_slice(const DirectMask& m, uint32_t o
 // Boards of at most 496 cells (every env has at most 31 whole chunks), exactly NM masks: one env per
 // iteration, one lane per chunk, branch-free so that consecutive envs interleave.  The per-env table row
 // and rotation of each mask are computed once by lane = env and broadcast with a shuffle.
-template <int NM>
+template <int NM, int PER>
 __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
   const CxGenHeader& H = *X.H;
   const uint32_t cells = H.cells;
@@ -660,23 +660,57 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
       pk[i] = m.rot | ((uint32_t)(reinterpret_cast<const uint8_t*>(m.row) - X.smem) << 12);
     }
   }
-#pragma unroll 4
-  for (int e = 0; e < nenv; ++e) {
-    const uint32_t b0 = (uint32_t)e * cells;
-    const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
-    const uint32_t c = c_lo + lane;
-    const bool ok = c < c_hi;
-    const uint32_t cc = ok ? c : 0u, o = ok ? 16u * c - b0 : 0u;
-    uint4 v = p16[cc];
+  if (PER > 0) {
+    // The chunk geometry of env e + PER is that of env e moved by PER * cells / 16 whole chunks (PER = 16 /
+    // gcd(cells, 16)), so this lane's chunk index, offset and validity in envs r, r + PER, ... are computed once.
+    constexpr int PR = PER > 0 ? PER : 1;
+    uint32_t gc[PR], go[PR];
+    bool gok[PR];
 #pragma unroll
-    for (int i = 0; i < NM; ++i) {
-      const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e);
-      DirectMask m;
-      m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
-      m.rot = q & 0xFFFu;
-      overlay16(v, direct_slice(m, o, cells), ch4[i]);
+    for (int r = 0; r < PR; ++r) {
+      const uint32_t b0 = (uint32_t)r * cells;
+      const uint32_t c = ((b0 + 15u) >> 4) + lane;
+      gok[r] = c < ((b0 + cells) >> 4);
+      gc[r] = gok[r] ? c : 0u;
+      go[r] = gok[r] ? 16u * c - b0 : 0u;
     }
-    if (ok) __stcs(d16 + c, v);
+    const uint32_t adv = (uint32_t)PR * cells >> 4;
+    uint32_t cq = 0;
+    for (int e0 = 0; e0 < nenv; e0 += PR, cq += adv) {
+#pragma unroll
+      for (int r = 0; r < PR; ++r) {
+        const uint32_t c = cq + gc[r];
+        uint4 v = p16[c];
+#pragma unroll
+        for (int i = 0; i < NM; ++i) {
+          const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e0 + r);
+          DirectMask m;
+          m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
+          m.rot = q & 0xFFFu;
+          overlay16(v, direct_slice(m, go[r], cells), ch4[i]);
+        }
+        if (gok[r]) __stcs(d16 + c, v);
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int e = 0; e < nenv; ++e) {
+      const uint32_t b0 = (uint32_t)e * cells;
+      const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
+      const uint32_t c = c_lo + lane;
+      const bool ok = c < c_hi;
+      const uint32_t cc = ok ? c : 0u, o = ok ? 16u * c - b0 : 0u;
+      uint4 v = p16[cc];
+#pragma unroll
+      for (int i = 0; i < NM; ++i) {
+        const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e);
+        DirectMask m;
+        m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
+        m.rot = q & 0xFFFu;
+        overlay16(v, direct_slice(m, o, cells), ch4[i]);
+      }
+      if (ok) __stcs(d16 + c, v);
+    }
   }
   // the chunk across the boundary between env i-1 and env i (lane i), if there is one
   if ((cells & 15u) != 0) {
@@ -716,9 +750,19 @@ __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, i
   // that lies inside the env
   const bool small = cells <= 496u && n_masks <= 2;
   if (small) {
-    if (n_masks == 0) compose_direct_small<0>(X, W, nenv, dst, lane);
-    else if (n_masks == 1) compose_direct_small<1>(X, W, nenv, dst, lane);
-    else compose_direct_small<2>(X, W, nenv, dst, lane);
+    // periodic chunk geometry (PER = 1, 2 or 4 envs) when the warp's envs are whole periods
+    const int per = (H.chunk_period <= 4 && nenv % H.chunk_period == 0) ? H.chunk_period : 0;
+#define CX_SMALL(NMASK)                                                                 \
+  do {                                                                                  \
+    if (per == 4) compose_direct_small<NMASK, 4>(X, W, nenv, dst, lane);                \
+    else if (per == 2) compose_direct_small<NMASK, 2>(X, W, nenv, dst, lane);           \
+    else if (per == 1) compose_direct_small<NMASK, 1>(X, W, nenv, dst, lane);           \
+    else compose_direct_small<NMASK, 0>(X, W, nenv, dst, lane);                         \
+  } while (0)
+    if (n_masks == 0) CX_SMALL(0);
+    else if (n_masks == 1) CX_SMALL(1);
+    else CX_SMALL(2);
+#undef CX_SMALL
     return;
   }
 #pragma unroll 2
@@ -778,10 +822,9 @@ __device__ __forceinline__ uint64_t poke_below(const Ctx& X, const WarpMem& W, i
 }
 __device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int e, uint8_t* dst) {
   const CxGenHeader& H = *X.H;
-  for (int i = 0; i < H.n_points; ++i) {
-    const uint32_t prog = H.point_prog[i];
-    if (!((prog >> 24) & 2u)) continue;
-    const uint32_t s = W.dyn[e][(prog >> 16) & 0xFF];
+  for (int i = 0; i < H.n_above; ++i) {
+    const uint32_t prog = H.above_prog[i];
+    const uint32_t s = W.dyn[e][prog & 0xFF];
     if (s != CX_EMPTY_CELL16) dst[(uint32_t)e * H.cells + s] = (uint8_t)(prog >> 8);
   }
 }
@@ -792,14 +835,20 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int
                                              int lane) {
   const CxGenHeader& H = *X.H;
   if (fast && H.direct) {
+    const bool pokes = H.n_poke > 0;  // warp-uniform
     uint64_t saved = 0;
-    if (lane < nenv) saved = poke_below(X, W, lane);
-    __syncwarp();
+    if (pokes) {
+      if (lane < nenv) saved = poke_below(X, W, lane);
+      __syncwarp();
+    }
     compose_direct(X, W, nenv, dst, lane);
-    __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
-    if (lane < nenv) {
-      store_above(X, W, lane, dst);
-      unpoke_points(X, W, lane, saved);
+    if (H.n_above > 0) {
+      __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
+      if (lane < nenv) store_above(X, W, lane, dst);
+    }
+    if (pokes) {
+      __syncwarp();
+      if (lane < nenv) unpoke_points(X, W, lane, saved);
     }
   } else if (fast) {
     build_linear_masks(X, W, nenv, lane);
@@ -821,25 +870,25 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int
   __syncwarp();
 }
 
-struct WarpTile {
-  uint16_t dyn[GMAX][CX_MAX_DYN];
-  uint16_t prev[GMAX][CX_MAX_DYN];
-};
-
-// dynamic shared memory: [tables blob][per warp: plane tile (16-byte multiple) | per-env mask bitsets]
-__device__ __forceinline__ size_t warp_mem_bytes(const CxGenHeader& H) {
+// dynamic shared memory: [tables blob][per warp: plane tile (16-byte multiple) | per-env mask bitsets | entity
+// state u16 [G][CX_MAX_DYN] | its snapshot at the last render (only games that consult it)]
+__device__ __host__ __forceinline__ size_t warp_state_bytes(const CxGenHeader& H) {
+  return (size_t)H.tile_envs * CX_MAX_DYN * 2 * (H.needs_prev || !H.simple_step ? 2 : 1);
+}
+__device__ __host__ __forceinline__ size_t warp_mem_bytes(const CxGenHeader& H) {
   const size_t tile = ((size_t)H.tile_envs * H.cells + 15) / 16 * 16;
   const size_t lin = ((size_t)H.tile_envs * H.n_lin * (H.mask_words + 1) * 4 + 15) / 16 * 16;
-  return tile + lin;
+  return tile + lin + warp_state_bytes(H);
 }
 
-__device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem, WarpTile* wt, int warp, int lane) {
+__device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem, int warp, int lane) {
   WarpMem W;
   const size_t tile = ((size_t)H.tile_envs * H.cells + 15) / 16 * 16;
+  const size_t lin = ((size_t)H.tile_envs * H.n_lin * (H.mask_words + 1) * 4 + 15) / 16 * 16;
   W.plane = smem + H.blob_bytes + (size_t)warp * warp_mem_bytes(H);
   W.lin = reinterpret_cast<uint32_t*>(W.plane + tile);
-  W.dyn = wt[warp].dyn;
-  W.prev = wt[warp].prev;
+  W.dyn = reinterpret_cast<uint16_t (*)[CX_MAX_DYN]>(W.plane + tile + lin);
+  W.prev = W.dyn + H.tile_envs;  // only dereferenced by generic_env_step (space reserved when it can run)
   const int nwords = H.tile_envs * H.n_lin * (H.mask_words + 1);
   for (int i = lane; i < nwords; i += 32) W.lin[i] = 0u;  // incl. the slack word behind every bitset
   return W;
@@ -849,7 +898,6 @@ template <bool FAST>
 __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
-  __shared__ WarpTile s_w[NT / 32];
   const CxGenHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int G = H.tile_envs, cells = H.cells;
@@ -861,7 +909,7 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
   if (env0 >= P.n) return;
   const int nenv = (int)min((int64_t)G, P.n - env0);
-  const WarpMem W = warp_mem(H, smem, s_w, warp, lane);
+  const WarpMem W = warp_mem(H, smem, warp, lane);
   uint8_t* plane = W.plane;
   uint16_t (*dyn)[CX_MAX_DYN] = W.dyn;
   const bool fast = P.vec && H.fast_compose;
@@ -1017,7 +1065,6 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
 __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
-  __shared__ WarpTile s_w[NT / 32];
   const CxGenHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int G = H.tile_envs, cells = H.cells;
@@ -1028,7 +1075,7 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
   if (env0 >= P.n) return;
   const int nenv = (int)min((int64_t)G, P.n - env0);
-  const WarpMem W = warp_mem(H, smem, s_w, warp, lane);
+  const WarpMem W = warp_mem(H, smem, warp, lane);
   if (lane < nenv)
     for (int d = 0; d < H.n_dyn; ++d) W.dyn[lane][d] = P.dyn[(int64_t)d * P.n + env0 + lane];
   const uint32_t inv_cells = div_inverse((uint32_t)cells);
@@ -1056,11 +1103,7 @@ GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
   return P;
 }
 
-size_t gen_warp_bytes(const cx_game* g) {
-  const size_t tile = ((size_t)g->gh.tile_envs * g->gh.cells + 15) / 16 * 16;
-  const size_t lin = ((size_t)g->gh.tile_envs * g->gh.n_lin * (g->gh.mask_words + 1) * 4 + 15) / 16 * 16;
-  return tile + lin;
-}
+size_t gen_warp_bytes(const cx_game* g) { return warp_mem_bytes(g->gh); }
 // warps per CTA: share the staged tables between warps while keeping a CTA below ~100 KB of shared memory
 int gen_warps_per_cta(const cx_game* g) {
   int w = NT / 32;
