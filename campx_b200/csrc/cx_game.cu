@@ -760,14 +760,14 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
       H->simple_reward[a] = summed;
     }
     H->simple_step = simple ? 1 : 0;
-    H->off_sdelta = B->reserve((size_t)CX_MAX_ACTIONS * CX_MAX_DYN * 2);
-    uint16_t* sd = (uint16_t*)&B->bytes[H->off_sdelta];
+    H->off_sdelta = B->reserve((size_t)CX_MAX_ACTIONS * CX_MAX_DYN * 4);
+    uint32_t* sd = (uint32_t*)&B->bytes[H->off_sdelta];
     H->roll_slots = 0;
     for (int dslot = 0; dslot < n_dyn && !H->dyn_render; ++dslot) {
       if (H->slot_kind[dslot] == CX_KIND_ROLL) H->roll_slots |= 1u << dslot;
       for (int a = 0; a < A; ++a)
-        sd[a * CX_MAX_DYN + dslot] =
-            (uint16_t)((((uint32_t)H->slot_dr[dslot][a] & 0xFFu) << 8) | ((uint32_t)H->slot_dc[dslot][a] & 0xFFu));
+        sd[a * CX_MAX_DYN + dslot] =  // |dr| < rows, |dc| < cols (validated): non-negative residues
+            ((uint32_t)((H->slot_dr[dslot][a] + R) % R) << 16) | (uint32_t)((H->slot_dc[dslot][a] + C) % C);
     }
     H->fast_loop = (simple && H->direct && cells <= 496 && H->n_masks <= 2) ? 1 : 0;
     if (const char* dbg = getenv("CX_GEN_FASTLOOP")) H->fast_loop = H->fast_loop && atoi(dbg) != 0;  // development knob

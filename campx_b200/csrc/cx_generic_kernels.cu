@@ -40,6 +40,10 @@ namespace {
 #ifndef CX_GEN_UNROLL
 #define CX_GEN_UNROLL 2   // chunks of the composer loop in flight per lane (ILP)
 #endif
+#ifndef CX_GEN_MIN_CTAS
+#define CX_GEN_MIN_CTAS 4  // resident CTAs per SM the register allocation aims for: 4 x 128 threads x 128 registers measured
+                           // faster than 5 x 96 and 6 x 80 (the kernel is latency-bound; registers buy ILP), scripts/hello_time.py
+#endif
 constexpr int kChunkUnroll = CX_GEN_UNROLL;
 constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
@@ -335,10 +339,12 @@ __device__ __forceinline__ void simple_env_step(const Ctx& X, uint32_t a, uint16
   flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
 }
 
-// simple_env_step with the entity state in registers (k_generic_rollout<true>): sreg[d] = row << 8 | col for
-// every kind (0xFFFF: empty one-cell mask), so a move is two adds and two wraps with no table look-up in the
-// dependency chain, and the slots are independent instruction streams.  st[] (shared memory) receives the
-// representation the composer reads: cell index, or roll offset for rolling drapes.
+// simple_env_step with the entity state in registers (k_generic_rollout<true>): sreg[d] = row << 16 | col for
+// every kind (0xFFFFFFFF: empty one-cell mask).  The per-action deltas are tabulated as non-negative residues
+// ((dr mod rows) << 16 | (dc mod cols)), so a move is ONE add for both coordinates and one fused add-min per
+// coordinate for the toroidal wrap (x in [0, 2n-2]: min(x, x - n) as unsigned), with no table look-up in the
+// dependency chain; the slots are independent instruction streams.  st[] (shared memory) receives the
+// representation the composer reads: cell index, or roll offset (row << 8 | col) for rolling drapes.
 __device__ __forceinline__ void fast_env_step(const Ctx& X, uint32_t a, uint32_t (&sreg)[CX_MAX_DYN], uint16_t* st,
                                               uint8_t* plane, float& reward, uint32_t& flags, float& disc) {
   const CxGenHeader& H = *X.H;
@@ -348,23 +354,24 @@ __device__ __forceinline__ void fast_env_step(const Ctx& X, uint32_t a, uint32_t
     flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;
     return;
   }
-  const int R = H.rows, C = H.cols;
-  const uint4 dl4 = *reinterpret_cast<const uint4*>(X.smem + H.off_sdelta + a * (CX_MAX_DYN * 2));
-  const uint32_t w[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+  const uint32_t R = H.rows, C = H.cols;
+  const uint4* dl = reinterpret_cast<const uint4*>(X.smem + H.off_sdelta + a * (CX_MAX_DYN * 4));
+  const uint4 d0 = dl[0];
+  uint4 d1 = make_uint4(0u, 0u, 0u, 0u);
+  if (H.n_dyn > 4) d1 = dl[1];
+  const uint32_t w[CX_MAX_DYN] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
   for (int d = 0; d < CX_MAX_DYN; ++d) {
     if (d < H.n_dyn) {
-      const uint32_t dl = (d & 1) ? w[d >> 1] >> 16 : w[d >> 1] & 0xFFFFu;
       const uint32_t s = sreg[d];
-      int r = (int)(s >> 8) + (int)(int8_t)(dl >> 8), c = (int)(s & 255u) + (int)(int8_t)(dl & 255u);
-      r += r < 0 ? R : 0;
-      c += c < 0 ? C : 0;
-      r -= r >= R ? R : 0;
-      c -= c >= C ? C : 0;
-      const uint32_t ns = ((uint32_t)r << 8) | (uint32_t)c;
-      const bool live = s != 0xFFFFu;
-      sreg[d] = live ? ns : s;
-      if (live) st[d] = (uint16_t)(((H.roll_slots >> d) & 1u) ? ns : (uint32_t)(r * C + c));
+      const uint32_t t = s + w[d];
+      uint32_t r = t >> 16, c = t & 0xFFFFu;
+      r = min(r, r - R);
+      c = min(c, c - C);
+      if (s != 0xFFFFFFFFu) {
+        sreg[d] = (r << 16) | c;
+        st[d] = (uint16_t)(((H.roll_slots >> d) & 1u) ? (r << 8) | c : r * C + c);
+      }
     }
   }
   stamp(X, st, plane);
@@ -376,10 +383,14 @@ __device__ __forceinline__ void fast_load_state(const Ctx& X, const uint16_t* st
   const CxGenHeader& H = *X.H;
 #pragma unroll
   for (int d = 0; d < CX_MAX_DYN; ++d) {
-    sreg[d] = 0xFFFFu;
+    sreg[d] = 0xFFFFFFFFu;
     if (d < H.n_dyn) {
       const uint32_t v = st[d];
-      sreg[d] = ((H.roll_slots >> d) & 1u) ? v : (v == CX_EMPTY_CELL16 ? 0xFFFFu : (uint32_t)X.rc[v]);
+      const bool roll = (H.roll_slots >> d) & 1u;
+      if (roll || v != CX_EMPTY_CELL16) {
+        const uint32_t rc = roll ? v : (uint32_t)X.rc[v];
+        sreg[d] = ((rc >> 8) << 16) | (rc & 255u);
+      }
     }
   }
 }
@@ -641,11 +652,38 @@ __device__ __forceinline__ uint32_t direct_slice(const DirectMask& m, uint32_t o
   return __funnelshift_r(m.row[j], m.row[j + 1], S & 31u);  // bits 16-31: don't care
 }
 
+// What the direct composer needs per warp and does not change from step to step: computed once per launch.
+struct DirectGeom {
+  int per;            // envs per period of the chunk geometry (1, 2 or 4), 0: not periodic for this warp
+  uint32_t gc[4];     // this lane's chunk index in env r of a period (relative to the period's first chunk)
+  uint32_t go[4];     // ... and the offset of that chunk's first cell inside the env
+  uint32_t gok;       // bit r: the lane has a whole chunk in env r
+};
+__device__ __forceinline__ DirectGeom direct_geom(const CxGenHeader& H, int nenv, int lane) {
+  DirectGeom Gm;
+  const uint32_t cells = H.cells;
+  // periodic chunk geometry (PER = 1, 2 or 4 envs) when the warp's envs are whole periods
+  const int cp = H.chunk_period;
+  Gm.per = (cp == 1 || ((cp == 2 || cp == 4) && (nenv & (cp - 1)) == 0)) ? cp : 0;
+  Gm.gok = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint32_t b0 = (uint32_t)r * cells;
+    const uint32_t c = ((b0 + 15u) >> 4) + lane;
+    const bool ok = c < ((b0 + cells) >> 4);
+    Gm.gok |= ok ? 1u << r : 0u;
+    Gm.gc[r] = ok ? c : 0u;
+    Gm.go[r] = ok ? 16u * c - b0 : 0u;
+  }
+  return Gm;
+}
+
 // Boards of at most 496 cells (every env has at most 31 whole chunks), exactly NM masks: one env per
 // iteration, one lane per chunk, branch-free so that consecutive envs interleave.  The per-env table row
 // and rotation of each mask are computed once by lane = env and broadcast with a shuffle.
 template <int NM, int PER>
-__device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+__device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
+                                                     uint8_t* dst, int lane) {
   const CxGenHeader& H = *X.H;
   const uint32_t cells = H.cells;
   const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
@@ -664,22 +702,12 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
     // The chunk geometry of env e + PER is that of env e moved by PER * cells / 16 whole chunks (PER = 16 /
     // gcd(cells, 16)), so this lane's chunk index, offset and validity in envs r, r + PER, ... are computed once.
     constexpr int PR = PER > 0 ? PER : 1;
-    uint32_t gc[PR], go[PR];
-    bool gok[PR];
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const uint32_t b0 = (uint32_t)r * cells;
-      const uint32_t c = ((b0 + 15u) >> 4) + lane;
-      gok[r] = c < ((b0 + cells) >> 4);
-      gc[r] = gok[r] ? c : 0u;
-      go[r] = gok[r] ? 16u * c - b0 : 0u;
-    }
     const uint32_t adv = (uint32_t)PR * cells >> 4;
     uint32_t cq = 0;
     for (int e0 = 0; e0 < nenv; e0 += PR, cq += adv) {
 #pragma unroll
       for (int r = 0; r < PR; ++r) {
-        const uint32_t c = cq + gc[r];
+        const uint32_t c = cq + Gm.gc[r];
         uint4 v = p16[c];
 #pragma unroll
         for (int i = 0; i < NM; ++i) {
@@ -687,9 +715,9 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
           DirectMask m;
           m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
           m.rot = q & 0xFFFu;
-          overlay16(v, direct_slice(m, go[r], cells), ch4[i]);
+          overlay16(v, direct_slice(m, Gm.go[r], cells), ch4[i]);
         }
-        if (gok[r]) __stcs(d16 + c, v);
+        if ((Gm.gok >> r) & 1u) __stcs(d16 + c, v);
       }
     }
   } else {
@@ -736,7 +764,8 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
   }
 }
 
-__device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+__device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
+                                               uint8_t* dst, int lane) {
   const CxGenHeader& H = *X.H;
   const uint32_t cells = H.cells;
   const int n_masks = H.n_masks;
@@ -750,14 +779,13 @@ __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, i
   // that lies inside the env
   const bool small = cells <= 496u && n_masks <= 2;
   if (small) {
-    // periodic chunk geometry (PER = 1, 2 or 4 envs) when the warp's envs are whole periods
-    const int per = (H.chunk_period <= 4 && nenv % H.chunk_period == 0) ? H.chunk_period : 0;
+    const int per = Gm.per;
 #define CX_SMALL(NMASK)                                                                 \
   do {                                                                                  \
-    if (per == 4) compose_direct_small<NMASK, 4>(X, W, nenv, dst, lane);                \
-    else if (per == 2) compose_direct_small<NMASK, 2>(X, W, nenv, dst, lane);           \
-    else if (per == 1) compose_direct_small<NMASK, 1>(X, W, nenv, dst, lane);           \
-    else compose_direct_small<NMASK, 0>(X, W, nenv, dst, lane);                         \
+    if (per == 4) compose_direct_small<NMASK, 4>(X, W, Gm, nenv, dst, lane);                \
+    else if (per == 2) compose_direct_small<NMASK, 2>(X, W, Gm, nenv, dst, lane);           \
+    else if (per == 1) compose_direct_small<NMASK, 1>(X, W, Gm, nenv, dst, lane);           \
+    else compose_direct_small<NMASK, 0>(X, W, Gm, nenv, dst, lane);                         \
   } while (0)
     if (n_masks == 0) CX_SMALL(0);
     else if (n_masks == 1) CX_SMALL(1);
@@ -831,8 +859,8 @@ __device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int 
 
 // Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
 // per-cell painter's algorithm with byte stores (any geometry, any alignment).
-__device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, bool fast,
-                                             int lane) {
+__device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
+                                             uint8_t* dst, bool fast, int lane) {
   const CxGenHeader& H = *X.H;
   if (fast && H.direct) {
     const bool pokes = H.n_poke > 0;  // warp-uniform
@@ -841,7 +869,7 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int
       if (lane < nenv) saved = poke_below(X, W, lane);
       __syncwarp();
     }
-    compose_direct(X, W, nenv, dst, lane);
+    compose_direct(X, W, Gm, nenv, dst, lane);
     if (H.n_above > 0) {
       __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
       if (lane < nenv) store_above(X, W, lane, dst);
@@ -895,7 +923,7 @@ __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem,
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant__ GenParams P) {
+__global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
   const CxGenHeader& H = P.h;
@@ -939,6 +967,7 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
   __syncwarp();
   uint32_t sreg[CX_MAX_DYN];
   if (FAST && mine) fast_load_state(X, dyn[lane], sreg);
+  const DirectGeom Gm = direct_geom(H, nenv, lane);
 
   uint32_t ep_cnt = 0, ep_len = 0;
   double ep_sum = 0.0, ep_sumsq = 0.0;
@@ -1000,7 +1029,7 @@ __global__ void __launch_bounds__(NT, 5) k_generic_rollout(const __grid_constant
     __syncwarp();  // entity state and backdrop stamps of the warp's envs are visible
 
     // ---- phases 1b, 1c, 2: compose the boards and stream them out ----
-    compose_warp(X, W, nenv, P.board + row * cells, fast, lane);
+    compose_warp(X, W, Gm, nenv, P.board + row * cells, fast, lane);
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
@@ -1084,7 +1113,7 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
     W.plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
   }
   __syncwarp();
-  compose_warp(X, W, nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
+  compose_warp(X, W, direct_geom(H, nenv, lane), nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {

@@ -20,7 +20,9 @@
 #define CX_AGENT_CTA_THREADS 128
 
 #define CX_GEN_TILE_ENVS 32      // max envs per CTA in the generic kernels
+#ifndef CX_GEN_CTA_THREADS
 #define CX_GEN_CTA_THREADS 128
+#endif
 #define CX_MAX_DYN 8             // moving entities in the generic path
 #define CX_MAX_LIN 4             // per-env mask bitsets the fast composer keeps in shared memory
 #define CX_MAX_ZDIR_GAME 8       // change_z_order directives of a whole game in one step
@@ -122,7 +124,7 @@ struct CxGenHeader {
   uint8_t slot_kind[CX_MAX_DYN];         // cx_kind of the entity behind each dynamic slot
   int8_t slot_dr[CX_MAX_DYN][CX_MAX_ACTIONS], slot_dc[CX_MAX_DYN][CX_MAX_ACTIONS];
   float simple_reward[CX_MAX_ACTIONS];
-  int32_t off_sdelta;                    // u16 [CX_MAX_ACTIONS][CX_MAX_DYN]: (dr & 0xFF) << 8 | (dc & 0xFF) per action and slot
+  int32_t off_sdelta;                    // u32 [CX_MAX_ACTIONS][CX_MAX_DYN]: (dr mod rows) << 16 | (dc mod cols) per action and slot
   uint32_t roll_slots;                   // bit d: dynamic slot d holds a roll offset (row << 8 | col), not a cell index
   int32_t fast_loop;                     // simple_step && direct && cells <= 496 && n_masks <= 2: k_generic_rollout<true>
   int32_t n_stampers;
