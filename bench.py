@@ -119,7 +119,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -373,17 +373,35 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "return_stats": summary, "observation_contract_kernel": obs_extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
-    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; stdout carries ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+    # stdout carries ONE JSON line: NCCL prints its version banner there (NCCL_DEBUG=VERSION/INFO, from the
+    # environment or an nccl.conf), so everything but the JSON line is sent to stderr at the descriptor level
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)

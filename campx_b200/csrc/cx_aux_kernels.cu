@@ -146,9 +146,37 @@ __device__ __forceinline__ uint32_t layer_word(const uint8_t* s_board, const uin
   return m;
 }
 
-template <typename OutT>
+__device__ __forceinline__ uint32_t bytes_equal01(uint32_t w, uint32_t ch4) {  // 0x01 where the bytes are equal
+  const uint32_t x = w ^ ch4;
+  const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;   // bit 7 of a byte: one of its low 7 bits is set
+  return (~(t | x) >> 7) & 0x01010101u;
+}
+// uint8 output, rows of whole 4-byte words (cells % 4 == 0, cells >= 16): the 16 output cells of a thread lie in at
+// most two (board, channel) rows and every 4-cell word inside one of them, so a word is ONE aligned LDS.32, a
+// select of the row's character and a branch-free zero-byte test; (row, cell) come from two multiplications
+// with precomputed inverses instead of divisions.  Stores stay 16-byte chunks of the FLAT output (whole sectors).
+struct LayerDivisors {
+  uint32_t inv_cells, inv_L;  // ceil(2^32 / d)
+};
+__device__ __forceinline__ void layer_words16(const uint32_t* s32, const uint32_t* s_ch4, int L, int cells,
+                                              const LayerDivisors dv, uint32_t o, uint32_t (&w)[4]) {
+  const uint32_t row = __umulhi(o, dv.inv_cells), c = o - row * (uint32_t)cells;
+  const uint32_t e = __umulhi(row, dv.inv_L), k = row - e * (uint32_t)L;
+  const uint32_t cw = (uint32_t)cells >> 2;
+  const uint32_t left = ((uint32_t)cells - c) >> 2;          // words left in this row (>= 1)
+  const bool last = k + 1u == (uint32_t)L;
+  const uint32_t i1 = e * cw + (c >> 2), i2 = (last ? e + 1u : e) * cw;
+  const uint32_t ch1 = s_ch4[k], ch2 = s_ch4[last ? 0u : k + 1u];
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    const bool first = j < left;
+    w[j] = bytes_equal01(s32[first ? i1 + j : i2 + (j - left)], first ? ch1 : ch2);
+  }
+}
+
+template <typename OutT, bool WORDS>
 __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board, OutT* __restrict__ out, CharTable ct,
-                                               int L, int cells, int EB, int64_t n_boards) {
+                                               int L, int cells, int EB, int64_t n_boards, LayerDivisors dv) {
   extern __shared__ __align__(16) uint8_t s_board[];          // EB * cells bytes + 32 bytes of slack
   __shared__ uint32_t s_ch4[CX_MAX_CHARS];
   const int64_t b0 = (int64_t)blockIdx.x * EB;
@@ -171,14 +199,18 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
   OutT* dst = out + b0 * per;
   const bool vec = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   for (int o = threadIdx.x * 16; o < total; o += TB * 16) {   // 16 cells per thread and iteration
-    LayerCursor cur;
-    cur.e = o / per;
-    const int rem = o - cur.e * per;
-    cur.k = rem / cells;
-    cur.c = rem - cur.k * cells;
     uint32_t w[4];
+    if (WORDS) {
+      layer_words16(reinterpret_cast<const uint32_t*>(s_board), s_ch4, L, cells, dv, (uint32_t)o, w);
+    } else {
+      LayerCursor cur;
+      cur.e = o / per;
+      const int rem = o - cur.e * per;
+      cur.k = rem / cells;
+      cur.c = rem - cur.k * cells;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = layer_word(s_board, s_ch4, L, cells, cur);
+      for (int j = 0; j < 4; ++j) w[j] = layer_word(s_board, s_ch4, L, cells, cur);
+    }
     if (sizeof(OutT) == 1) {
       uint8_t* d8 = reinterpret_cast<uint8_t*>(dst) + o;
       if (vec && o + 16 <= total) {
@@ -196,6 +228,52 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
                              (float)(w[j] >> 24)));
       } else {
         for (int j = 0; j < 16 && o + j < total; ++j) df[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 1u);
+      }
+    }
+  }
+}
+
+// Boards whose rows are whole 4-byte words (cells % 4 == 0; Hello World: 468): no staging and no row arithmetic in
+// the inner loop.  One thread owns ONE board word (4 cells): a coalesced LDG.32, then per channel a branch-free
+// zero-byte test of (word ^ character) and one store -- 4 bytes (uint8: a warp writes 128 contiguous bytes per
+// channel) or 16 bytes (float32: 512 contiguous bytes), each (board, channel) row being word-aligned.  The board of
+// a word comes from one multiplication with the precomputed inverse of cells / 4.
+template <typename OutT>
+__global__ void __launch_bounds__(TB) k_layers_words(const uint32_t* __restrict__ board, OutT* __restrict__ out,
+                                                     CharTable ct, int L, int cw, int EB, int64_t n_boards,
+                                                     uint32_t inv_cw) {
+  __shared__ uint32_t s_ch4[CX_MAX_CHARS];
+  if (threadIdx.x < CX_MAX_CHARS) s_ch4[threadIdx.x] = ct.ch[threadIdx.x] * 0x01010101u;
+  __syncthreads();
+  const int64_t b0 = (int64_t)blockIdx.x * EB;
+  const int nb = (int)min((int64_t)EB, n_boards - b0);
+  const uint32_t* src = board + b0 * cw;
+  OutT* dst = out + b0 * L * cw * 4;
+  const uint32_t row = (uint32_t)cw * 4u;                     // elements per (board, channel) row
+  const uint32_t nw = (uint32_t)(nb * cw);
+  constexpr int U = 4;                                        // board words in flight per thread
+  for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += U * TB) {
+    uint32_t w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * TB;
+      w[u] = i < nw ? __ldcs(src + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * TB;
+      if (i >= nw) break;
+      const uint32_t e = __umulhi(i, inv_cw), q = i - e * (uint32_t)cw;   // exact: i * cw < 2^32 (EB * cells <= 32 KB)
+      OutT* p = dst + ((size_t)e * L * cw + q) * 4;
+#pragma unroll 4
+      for (int k = 0; k < L; ++k, p += row) {
+        const uint32_t m = bytes_equal01(w[u], s_ch4[k]);
+        if (sizeof(OutT) == 1) {
+          __stcs(reinterpret_cast<uint32_t*>(p), m);
+        } else {
+          __stcs(reinterpret_cast<float4*>(p), make_float4((float)(m & 1u), (float)((m >> 8) & 1u),
+                                                           (float)((m >> 16) & 1u), (float)(m >> 24)));
+        }
       }
     }
   }
@@ -227,7 +305,8 @@ template <typename OutT>
 int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, OutT* d_out, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
     configured = true;
   }
   CharTable ct;
@@ -244,8 +323,29 @@ int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, Ou
     CX_CUDA_OK(cudaGetLastError());
     return CX_OK;
   }
+  // float32: one board word per thread, 16-byte stores (every (board, channel) row starts 16-byte aligned)
+  if (sizeof(OutT) == 4 && cells % 4 == 0 && (reinterpret_cast<uintptr_t>(d_board) & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+    const int cw = cells / 4;
+    const uint32_t inv_cw = cw == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)cw + 1u;
+    if (cw > 1) {
+      k_layers_words<OutT><<<(unsigned)grid, TB, 0, s>>>(reinterpret_cast<const uint32_t*>(d_board), d_out, ct,
+                                                          g->info.n_chars, cw, EB, n_boards, inv_cw);
+      CX_CUDA_OK(cudaGetLastError());
+      return CX_OK;
+    }
+  }
   const size_t smem = ((size_t)EB * cells + 15) / 16 * 16 + 32;
-  k_layers<OutT><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, g->info.n_chars, cells, EB, n_boards);
+  const int L = g->info.n_chars;
+  // word path: rows of whole words, and the inverses exact for every output offset of a CTA (x * d < 2^32)
+  const bool words = cells % 4 == 0 && cells >= 16 && L > 1 && (uint64_t)EB * L * cells * (uint64_t)cells < (1ull << 32);
+  LayerDivisors dv;
+  dv.inv_cells = (uint32_t)(0xFFFFFFFFu / (uint32_t)cells + 1u);
+  dv.inv_L = L == 1 ? 0u : (uint32_t)(0xFFFFFFFFu / (uint32_t)L + 1u);
+  if (words)
+    k_layers<OutT, true><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, L, cells, EB, n_boards, dv);
+  else
+    k_layers<OutT, false><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, L, cells, EB, n_boards, dv);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -243,3 +243,33 @@ def test_random_arrow_ring_worlds(seed):
                 **{ch: hover(bonus[ch]) for ch in '^>v<'}},
         z_order='^>v<A#', update_schedule='A^>v<#')
     compare(game, factory, onehot, n=48, T=60, seed=seed)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 3), (3, 3), (2, 8), (4, 4), (5, 5), (4, 7), (8, 12), (13, 36), (16, 16), (9, 20),
+                                       (11, 13)])
+def test_layers_from_board_all_geometries(rows, cols):
+    """cx_layers_from_board (rendering.py:204-215, layers[ch] = board == ord(ch)) on arbitrary boards: rows of whole
+    words (cells % 4 == 0, cells >= 16: the aligned-word kernel), other sizes (unaligned windows), tiny boards;
+    ragged board counts and misaligned input/output views; uint8 and float32."""
+    rng = np.random.Generator(np.random.PCG64(rows * 100 + cols))
+    art = _random_art(rng, rows, cols, 0.25, 0.2)
+    game = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
+                                               '#': things.FixedDrape, '*': things.FixedDrape},
+                             z_order='*A#', num_envs=8, verify=False)
+    game.its_showtime()
+    g = game.native
+    chars = torch.tensor([ord(c) for c in g.spec.chars], dtype=torch.uint8, device="cuda")
+    alphabet = torch.cat([chars, torch.tensor([0, 1, 255, ord('A') ^ 0x80], dtype=torch.uint8, device="cuda")])
+    gen = torch.Generator(device="cuda").manual_seed(rows * 1000 + cols)
+    for nb in (1, 17, 300, 1031):
+        for skip in (0, 1, 3):
+            pool = alphabet[torch.randint(0, len(alphabet), (nb + skip, rows, cols), device="cuda", generator=gen)]
+            boards = pool[skip:]                                          # misaligned unless skip * cells % 16 == 0
+            want = (boards[:, None] == chars[None, :, None, None])
+            got = g.layers_from_board(boards)
+            assert got.shape == (nb, len(chars), rows, cols)
+            assert torch.equal(got, want.to(torch.uint8)), (nb, skip)
+            outpool = torch.full((nb + skip, len(chars), rows, cols), 7.0, device="cuda")
+            gotf = g.layers_from_board(boards, out=outpool[skip:], dtype=torch.float32)
+            assert torch.equal(gotf, want.to(torch.float32)), (nb, skip)
+            assert bool((outpool[:skip] == 7.0).all())
