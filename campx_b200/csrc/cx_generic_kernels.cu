@@ -44,7 +44,14 @@ namespace {
 #define CX_GEN_MIN_CTAS 4  // resident CTAs per SM the register allocation aims for: 4 x 128 threads x 128 registers measured
                            // faster than 5 x 96 and 6 x 80 (the kernel is latency-bound; registers buy ILP), scripts/hello_time.py
 #endif
+#ifndef CX_GEN_PERIOD_UNROLL
+#define CX_GEN_PERIOD_UNROLL 1  // periods of the direct composer in flight per warp
+#endif
+#ifndef CX_GEN_PROBE
+#define CX_GEN_PROBE 0
+#endif
 constexpr int kChunkUnroll = CX_GEN_UNROLL;
+constexpr int kPeriodUnroll = CX_GEN_PERIOD_UNROLL;
 constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
 
@@ -704,6 +711,7 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
     constexpr int PR = PER > 0 ? PER : 1;
     const uint32_t adv = (uint32_t)PR * cells >> 4;
     uint32_t cq = 0;
+#pragma unroll kPeriodUnroll
     for (int e0 = 0; e0 < nenv; e0 += PR, cq += adv) {
 #pragma unroll
       for (int r = 0; r < PR; ++r) {
@@ -978,7 +986,7 @@ __global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const _
   for (int t = 0; t < P.T; ++t) {
     const int64_t row = (int64_t)t * P.n + env0;
     bool reset_me = false;
-    if (mine) {
+    if (mine && CX_GEN_PROBE != 3) {  // development probe (3: composition only)
       uint32_t a;
       if (P.synth) {
         a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t, (uint32_t)H.n_actions);
@@ -995,7 +1003,11 @@ __global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const _
         f = CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE;
       } else {
         if (FAST)
+#if CX_GEN_PROBE == 2  // development probe (2: no entity updates)
+          rw = 0.0f, f = 0u, dc = 1.0f;
+#else
           fast_env_step(X, a, sreg, dyn[lane], plane + lane * cells, rw, f, dc);
+#endif
         else if (H.simple_step)
           simple_env_step(X, a, dyn[lane], plane + lane * cells, rw, f, dc);
         else
@@ -1029,7 +1041,9 @@ __global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const _
     __syncwarp();  // entity state and backdrop stamps of the warp's envs are visible
 
     // ---- phases 1b, 1c, 2: compose the boards and stream them out ----
+#if CX_GEN_PROBE != 1  // development probe (1: no composition)
     compose_warp(X, W, Gm, nenv, P.board + row * cells, fast, lane);
+#endif
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
