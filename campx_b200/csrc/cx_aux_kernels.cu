@@ -116,6 +116,11 @@ struct CharTable {
 // the end of a (board, channel) row, every word is the OR of two such segments.  The (board, channel, cell)
 // coordinates are divided out once per thread and iteration (16 cells) and advanced incrementally.
 // HBM traffic = cells bytes read + chars * cells * sizeof(OutT) bytes written per board.
+__device__ __forceinline__ uint32_t bytes_equal01(uint32_t w, uint32_t ch4) {  // 0x01 where the bytes are equal
+  const uint32_t x = w ^ ch4;
+  const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;   // bit 7 of a byte: one of its low 7 bits is set
+  return (~(t | x) >> 7) & 0x01010101u;
+}
 struct LayerCursor {
   int e, k, c;  // board in the tile, channel, cell
 };
@@ -129,7 +134,7 @@ __device__ __forceinline__ uint32_t layer_word(const uint8_t* s_board, const uin
   };
   const int row = cur.e * cells;
   const int l1 = min(4, cells - cur.c);                       // cells left in this (board, channel) row
-  uint32_t m = __vcmpeq4(window(row + cur.c), s_ch4[cur.k]) & 0x01010101u;
+  uint32_t m = bytes_equal01(window(row + cur.c), s_ch4[cur.k]);
   cur.c += 4;
   if (cur.c >= cells) {                                       // the word runs into the next row
     cur.c -= cells;
@@ -139,24 +144,20 @@ __device__ __forceinline__ uint32_t layer_word(const uint8_t* s_board, const uin
     }
     if (l1 < 4) {
       const uint32_t keep = (1u << (8 * l1)) - 1u;
-      const uint32_t m2 = __vcmpeq4(window(cur.e * cells), s_ch4[cur.k]) & 0x01010101u;
+      const uint32_t m2 = bytes_equal01(window(cur.e * cells), s_ch4[cur.k]);
       m = (m & keep) | (m2 << (8 * l1));
     }
   }
   return m;
 }
 
-__device__ __forceinline__ uint32_t bytes_equal01(uint32_t w, uint32_t ch4) {  // 0x01 where the bytes are equal
-  const uint32_t x = w ^ ch4;
-  const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;   // bit 7 of a byte: one of its low 7 bits is set
-  return (~(t | x) >> 7) & 0x01010101u;
-}
 // uint8 output, rows of whole 4-byte words (cells % 4 == 0, cells >= 16): the 16 output cells of a thread lie in at
 // most two (board, channel) rows and every 4-cell word inside one of them, so a word is ONE aligned LDS.32, a
 // select of the row's character and a branch-free zero-byte test; (row, cell) come from two multiplications
 // with precomputed inverses instead of divisions.  Stores stay 16-byte chunks of the FLAT output (whole sectors).
 struct LayerDivisors {
   uint32_t inv_cells, inv_L;  // ceil(2^32 / d)
+  uint32_t inv_per;           // ceil(2^32 / (L * cells)), 0: not exact for this launch (divide instead)
 };
 __device__ __forceinline__ void layer_words16(const uint32_t* s32, const uint32_t* s_ch4, int L, int cells,
                                               const LayerDivisors dv, uint32_t o, uint32_t (&w)[4]) {
@@ -204,9 +205,9 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
       layer_words16(reinterpret_cast<const uint32_t*>(s_board), s_ch4, L, cells, dv, (uint32_t)o, w);
     } else {
       LayerCursor cur;
-      cur.e = o / per;
+      cur.e = dv.inv_per ? (int)__umulhi((uint32_t)o, dv.inv_per) : o / per;
       const int rem = o - cur.e * per;
-      cur.k = rem / cells;
+      cur.k = dv.inv_per ? (int)__umulhi((uint32_t)rem, dv.inv_cells) : rem / cells;
       cur.c = rem - cur.k * cells;
 #pragma unroll
       for (int j = 0; j < 4; ++j) w[j] = layer_word(s_board, s_ch4, L, cells, cur);
@@ -342,6 +343,8 @@ int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, Ou
   LayerDivisors dv;
   dv.inv_cells = (uint32_t)(0xFFFFFFFFu / (uint32_t)cells + 1u);
   dv.inv_L = L == 1 ? 0u : (uint32_t)(0xFFFFFFFFu / (uint32_t)L + 1u);
+  const uint64_t per = (uint64_t)L * cells;   // x / d == umulhi(x, ceil(2^32 / d)) while x * d < 2^32
+  dv.inv_per = (cells > 1 && per > 1 && (uint64_t)EB * per * per < (1ull << 32)) ? (uint32_t)(0xFFFFFFFFu / (uint32_t)per + 1u) : 0u;
   if (words)
     k_layers<OutT, true><<<(unsigned)grid, TB, smem, s>>>(d_board, d_out, ct, L, cells, EB, n_boards, dv);
   else
