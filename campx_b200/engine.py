@@ -177,6 +177,9 @@ class Engine(object):
         # AFTER the next one, so a caller can copy step t to the host on a side stream while step t+1 runs
         self._out_sets = [nat.alloc_outputs(), nat.alloc_outputs()] if self._batched else [nat.alloc_outputs()]
         self._out_index = 0
+        self._layered_sets = None     # layered boards of the fused observation step, allocated on first use
+        self.fused_observation_steps = True   # False: always step kernel + lazy cx_layers_from_board
+        self._last_obs = None
         self._out_board, self._out_reward, self._out_flags, self._out_discount = self._out_sets[0]
         self._ones = None
         nat.render(self._out_board)
@@ -187,7 +190,8 @@ class Engine(object):
         discount = self._spec.first_discount
         if self._batched:
             discount = torch.full((self._num_envs,), discount, dtype=torch.float32, device=nat.device)
-        return self._observation(self._out_board), reward, discount
+        self._last_obs = self._observation(self._out_board)
+        return self._last_obs, reward, discount
 
     def play(self, actions):
         if not self._showtime:
@@ -199,8 +203,24 @@ class Engine(object):
         idx = self._action_indices(actions)
         self._out_index = (self._out_index + 1) % len(self._out_sets)
         self._out_board, self._out_reward, self._out_flags, self._out_discount = self._out_sets[self._out_index]
-        nat.step(idx, self._out_board, self._out_reward, self._out_flags, self._out_discount)
-        obs = self._observation(self._out_board)
+        # A caller that read `layers` / `layered_board` of the last Observation gets the whole Observation of this
+        # step from ONE kernel (`cx_rollout_observations`, T = 1: board and layered board leave the step kernel
+        # together) instead of a step kernel plus `cx_layers_from_board`; a caller that only reads boards never
+        # pays for the layers (they stay lazy).  Same values either way.
+        last = self._last_obs
+        if self._batched and self.fused_observation_steps and last is not None and last.layers_were_read:
+            if self._layered_sets is None:
+                shape = (self._num_envs, nat.n_chars, self._rows, self._cols)
+                self._layered_sets = [torch.empty(shape, dtype=torch.uint8, device=nat.device) for _ in self._out_sets]
+            layered = self._layered_sets[self._out_index]
+            nat.rollout_observations(idx.unsqueeze(0), self._out_board.unsqueeze(0), layered.unsqueeze(0),
+                                     self._out_reward.unsqueeze(0), self._out_flags.unsqueeze(0),
+                                     None if self._out_discount is None else self._out_discount.unsqueeze(0))
+            obs = self._observation(self._out_board, layered)
+        else:
+            nat.step(idx, self._out_board, self._out_reward, self._out_flags, self._out_discount)
+            obs = self._observation(self._out_board)
+        self._last_obs = obs
         if not self._batched:
             flags = int(self._out_flags.item())                      # one env: sync and mirror the reference
             if flags & N.CX_FLAG_BAD_ACTION:
@@ -344,11 +364,11 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------------
-    def _observation(self, board):
+    def _observation(self, board, layered=None):
         nat = self._native
         if self._batched:
             return Observation(board, self._spec.chars,
-                               lambda b, dtype=torch.uint8: nat.layers_from_board(b, dtype=dtype))
+                               lambda b, dtype=torch.uint8: nat.layers_from_board(b, dtype=dtype), layered)
         return Observation(board[0], self._spec.chars,
                            lambda b, dtype=torch.uint8: nat.layers_from_board(b.unsqueeze(0), dtype=dtype)[0])
 

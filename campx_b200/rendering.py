@@ -52,9 +52,11 @@ class Observation(object):
         self._layer_fn = layer_fn
         self._layered = layered_board
         self._layers = None
+        self.layers_were_read = False   # Engine.play() emits whole Observations for callers that read the layers
 
     @property
     def layered_board(self):
+        self.layers_were_read = True
         if self._layered is None:
             self._layered = self._layer_fn(self.board)
         return self._layered

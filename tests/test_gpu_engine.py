@@ -283,3 +283,31 @@ def test_verify_catches_a_world_outside_the_primitives():
     g = ascii_art_to_game(["S."], ".", drapes={"S": FrameReward}, action_format="index", num_envs=4)
     with pytest.raises(NotImplementedError):
         g.its_showtime()
+
+
+@pytest.mark.parametrize("world,n", [("boat_race", 96), ("boat_race", 77), ("demo3", 64), ("hello", 48)])
+def test_play_emits_the_whole_observation_from_one_kernel_once_layers_are_read(world, n):
+    """A caller that reads `layers` / `layered_board` gets board and layered board of the following steps from the
+    fused observation kernel (cx_rollout_observations, T = 1); a caller that never does keeps the lazy path.
+    Boards, rewards, flags, discounts, layered boards and the state blob are identical either way."""
+    a = make_world(world, num_envs=n, max_episode_steps=13, track_returns=True)
+    b = make_world(world, num_envs=n, max_episode_steps=13, track_returns=True)
+    oa, _, _ = a.its_showtime()
+    ob, _, _ = b.its_showtime()
+    assert torch.equal(oa.layered_board, b.native.layers_from_board(ob.board))   # first frame: lazy on both sides
+    acts = a.native.fill_actions(30, seed=9)
+    for t in range(30):
+        oa, ra, da = a.play(acts[t])
+        ob, rb, db = b.play(acts[t])
+        fused = t != 10                                                      # step 9 does not touch the layers ...
+        assert (oa._layered is not None) == fused, t                         # ... so step 10 is lazy again
+        assert torch.equal(oa.board, ob.board), t
+        assert torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(a._out_flags, b._out_flags), t
+        if t != 9:
+            lay = oa.layered_board
+            assert torch.equal(lay, b.native.layers_from_board(ob.board)), t
+            for k, ch in enumerate(oa.characters):
+                assert torch.equal(oa.layers[ch], (ob.board == ord(ch)).to(torch.uint8)), (t, ch)
+    assert torch.equal(a.native.state, b.native.state)
+    assert a.episode_stats() == b.episode_stats()
