@@ -70,16 +70,26 @@ if kname != "agent_rollout":
 ll = os.path.join(ROOT, "gpurun_out", "%s_launches.csv" % tag)
 if os.path.exists(ll):
     rows = [r for r in csv.reader(open(ll)) if len(r) > 10 and r[0].isdigit()]
-    per = collections.defaultdict(list)
-    for r in rows:
-        per[r[4].split("(")[0][-60:]].append(float(r[-1].replace(",", "")))
-    total = sum(sum(v) for v in per.values())
+    seq = [(r[4].split("(")[0][-60:], float(r[-1].replace(",", ""))) for r in rows]
+    runs = []
+    for k, t in seq:                      # run-length encoded launch sequence of the whole command
+        if runs and runs[-1][0] == k:
+            runs[-1][1] += 1
+            runs[-1][2] += t
+        else:
+            runs.append([k, 1, t])
+    total = sum(t for _, t in seq)
     with open(os.path.join(out_dir, "%s_launch_list.md" % tag), "w") as f:
         f.write("# ncu launch list of `python bench.py --steps 512 --warmup 64 --e2e-steps 8` (%s)\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 16 -c 40` -- cold-cache, serialised: compare shares\n\n")
-        f.write("| kernel | launches | total us | share | mean us |\n|---|---|---|---|---|\n")
-        for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
-            f.write("| %s | %d | %.1f | %.1f%% | %.1f |\n" % (k, len(v), sum(v) / 1e3, 100 * sum(v) / total, sum(v) / len(v) / 1e3))
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` over the whole command, in launch order "
+                "(run-length encoded) -- cold-cache, serialised: compare shares, not absolutes.\n\n")
+        f.write("| # | kernel | consecutive launches | total us | share of command | mean us |\n|---|---|---|---|---|---|\n")
+        for i, (k, n, t) in enumerate(runs):
+            f.write("| %d | %s | %d | %.1f | %.1f%% | %.1f |\n" % (i, k, n, t / 1e3, 100 * t / total, t / n / 1e3))
+        f.write("\nSections of bench.py: set-up (reset / render / `k_fill_actions`), then the warm-up + TIMED region = the one "
+                "long run of `k_agent_rollout<1, 1, 0>` (64 + 512 steps at 32 steps per launch: nothing else launches there, so "
+                "the kernel's share of a timed step is 100 %), then the e2e leg (`cx_step` = `k_agent_rollout` with T = 1, one "
+                "launch per play()), then the secondary board + layered-board measurement (`k_agent_rollout_obs`).\n")
     import shutil
     shutil.copy(ll, os.path.join(out_dir, "%s_launches.csv" % tag))
 json.dump({"k_agent_rollout_track_T32_n1048576": traffic["dram_bytes"], "detail": traffic,
