@@ -41,17 +41,24 @@ namespace {
 #define CX_GEN_UNROLL 2   // chunks of the composer loop in flight per lane (ILP)
 #endif
 #ifndef CX_GEN_MIN_CTAS
-#define CX_GEN_MIN_CTAS 4  // resident CTAs per SM the register allocation aims for: 4 x 128 threads x 128 registers measured
-                           // faster than 5 x 96 and 6 x 80 (the kernel is latency-bound; registers buy ILP), scripts/hello_time.py
+#define CX_GEN_MIN_CTAS 5  // resident CTAs per SM the register allocation aims for (5 x 128 threads x 96 registers); the
+                           // register-state kernel is also built for one CTA more, see cx_launch_generic_rollout
 #endif
 #ifndef CX_GEN_PERIOD_UNROLL
 #define CX_GEN_PERIOD_UNROLL 1  // periods of the direct composer in flight per warp
+#endif
+#ifndef CX_GEN_FLAT
+#define CX_GEN_FLAT 1   // direct composer: flat chunk mapping (aligned 512-byte warp stores); 0: per-env mapping
 #endif
 #ifndef CX_GEN_PROBE
 #define CX_GEN_PROBE 0
 #endif
 constexpr int kChunkUnroll = CX_GEN_UNROLL;
 constexpr int kPeriodUnroll = CX_GEN_PERIOD_UNROLL;
+#ifndef CX_GEN_FLAT_UNROLL
+#define CX_GEN_FLAT_UNROLL 5   // 512-byte groups of the flat composer in flight per warp
+#endif
+constexpr int kFlatUnroll = CX_GEN_FLAT_UNROLL;
 constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
 
@@ -772,6 +779,71 @@ __device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem
   }
 }
 
+// Flat variant of compose_direct_small: lane l of iteration k composes chunk 32 k + l of the warp's board tile, so
+// every warp store is one 512-byte, 512-byte-aligned run of whole lines (the per-env mapping stores 29 of 32 chunks
+// from a 16-byte-aligned start: 5 partial lines per store, measured 4.4 TB/s against 5.6 TB/s for aligned runs).
+// The env of a chunk is one multiplication with the inverse of `cells`; its table row and rotation come from the
+// lane that owns the env (SHFL with a per-lane source).  Chunks that straddle two envs are left to lane = env below.
+template <int NM, int U>
+__device__ __forceinline__ void compose_direct_flat(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t cells = H.cells;
+  const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
+  uint4* d16 = reinterpret_cast<uint4*>(dst);
+  uint32_t pk[NM > 0 ? NM : 1], ch4[NM > 0 ? NM : 1];
+#pragma unroll
+  for (int i = 0; i < NM; ++i) {
+    ch4[i] = ((H.mask_prog[i] >> 8) & 0xFF) * 0x01010101u;
+    pk[i] = 0;
+    if (lane < nenv) {
+      const DirectMask m = direct_mask(X, W, i, lane);
+      pk[i] = m.rot | ((uint32_t)(reinterpret_cast<const uint8_t*>(m.row) - X.smem) << 12);
+    }
+  }
+  const uint32_t nchunks = (uint32_t)nenv * cells >> 4;     // the tile holds whole chunks (gen_vec_ok)
+  const uint32_t inv_cells = div_inverse(cells);
+#pragma unroll U
+  for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
+    const uint32_t c = c0 + lane;
+    const bool valid = c < nchunks;
+    const uint32_t cc = valid ? c : 0u, b = 16u * cc;
+    const uint32_t e = fast_div(b, inv_cells), o = b - e * cells;
+    uint4 v = p16[cc];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+      const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e);
+      DirectMask m;
+      m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
+      m.rot = q & 0xFFFu;
+      overlay16(v, direct_slice(m, o, cells), ch4[i]);
+    }
+    if (valid && o + 16u <= cells) d16[c] = v;  // default policy: measured 3 % faster than st.global.cs here
+  }
+  // the chunk across the boundary between env i-1 and env i (lane i), if there is one
+  if ((cells & 15u) != 0) {
+    uint32_t pk_prev[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) pk_prev[i] = __shfl_up_sync(0xffffffffu, pk[i], 1);
+    const uint32_t b = (uint32_t)lane * cells;
+    if (lane >= 1 && lane < nenv && (b & 15u) != 0) {
+      const uint32_t k = b >> 4, cnt = b - 16u * k;       // cnt cells of env lane-1, 16-cnt cells of env lane
+      const uint32_t o = cells - cnt, lo_mask = (1u << cnt) - 1u;
+      uint4 v = p16[k];
+#pragma unroll
+      for (int i = 0; i < NM; ++i) {
+        DirectMask m0, m1;
+        m0.row = reinterpret_cast<const uint32_t*>(X.smem + (pk_prev[i] >> 12));
+        m0.rot = pk_prev[i] & 0xFFFu;
+        m1.row = reinterpret_cast<const uint32_t*>(X.smem + (pk[i] >> 12));
+        m1.rot = pk[i] & 0xFFFu;
+        overlay16(v, (direct_slice(m0, o, cells) & lo_mask) | (direct_slice(m1, 0u, cells) << cnt), ch4[i]);
+      }
+      d16[k] = v;
+    }
+  }
+}
+
+template <int U>
 __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
                                                uint8_t* dst, int lane) {
   const CxGenHeader& H = *X.H;
@@ -795,9 +867,15 @@ __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, c
     else if (per == 1) compose_direct_small<NMASK, 1>(X, W, Gm, nenv, dst, lane);           \
     else compose_direct_small<NMASK, 0>(X, W, Gm, nenv, dst, lane);                         \
   } while (0)
+#if CX_GEN_FLAT
+    if (n_masks == 0) compose_direct_flat<0, U>(X, W, nenv, dst, lane);
+    else if (n_masks == 1) compose_direct_flat<1, U>(X, W, nenv, dst, lane);
+    else compose_direct_flat<2, U>(X, W, nenv, dst, lane);
+#else
     if (n_masks == 0) CX_SMALL(0);
     else if (n_masks == 1) CX_SMALL(1);
     else CX_SMALL(2);
+#endif
 #undef CX_SMALL
     return;
   }
@@ -867,6 +945,7 @@ __device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int 
 
 // Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
 // per-cell painter's algorithm with byte stores (any geometry, any alignment).
+template <int U>
 __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
                                              uint8_t* dst, bool fast, int lane) {
   const CxGenHeader& H = *X.H;
@@ -877,7 +956,7 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, con
       if (lane < nenv) saved = poke_below(X, W, lane);
       __syncwarp();
     }
-    compose_direct(X, W, Gm, nenv, dst, lane);
+    compose_direct<U>(X, W, Gm, nenv, dst, lane);
     if (H.n_above > 0) {
       __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
       if (lane < nenv) store_above(X, W, lane, dst);
@@ -930,8 +1009,8 @@ __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem,
   return W;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const __grid_constant__ GenParams P) {
+template <bool FAST, int OCC>
+__global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
   const CxGenHeader& H = P.h;
@@ -1042,7 +1121,7 @@ __global__ void __launch_bounds__(NT, CX_GEN_MIN_CTAS) k_generic_rollout(const _
 
     // ---- phases 1b, 1c, 2: compose the boards and stream them out ----
 #if CX_GEN_PROBE != 1  // development probe (1: no composition)
-    compose_warp(X, W, Gm, nenv, P.board + row * cells, fast, lane);
+    compose_warp<OCC >= 6 ? 3 : kFlatUnroll>(X, W, Gm, nenv, P.board + row * cells, fast, lane);
 #endif
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
@@ -1127,7 +1206,7 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
     W.plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
   }
   __syncwarp();
-  compose_warp(X, W, direct_geom(H, nenv, lane), nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
+  compose_warp<kFlatUnroll>(X, W, direct_geom(H, nenv, lane), nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
@@ -1166,8 +1245,9 @@ bool gen_vec_ok(const cx_game* g, int64_t n, const void* d_board) {
 int configure_once() {
   static bool configured = false;
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, CX_GEN_MIN_CTAS + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
@@ -1203,9 +1283,16 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   int rc = configure_once();
   if (rc) return rc;
   if (g->gh.fast_loop && P.vec)
-    k_generic_rollout<true><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    // Two register budgets of the same kernel: CX_GEN_MIN_CTAS + 1 resident CTAs per SM (80 registers) wins once the
+    // grid is several waves deep; one CTA fewer with more registers wins on 1-2 waves, where the tail of a nearly
+    // empty last wave costs more than the extra warps hide (Hello World: 65,536 envs 8.4e9 vs 7.9e9, 2^18 envs 9.8e9
+    // vs 1.02e10 env-steps/s)
+    if (grid >= 4 * (int64_t)g->sm_count * (CX_GEN_MIN_CTAS + 1))
+      k_generic_rollout<true, CX_GEN_MIN_CTAS + 1><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    else
+      k_generic_rollout<true, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   else
-    k_generic_rollout<false><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    k_generic_rollout<false, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }
