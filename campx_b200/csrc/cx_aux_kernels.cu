@@ -234,48 +234,82 @@ __global__ void __launch_bounds__(TB) k_layers(const uint8_t* __restrict__ board
   }
 }
 
-// Boards whose rows are whole 4-byte words (cells % 4 == 0; Hello World: 468): no staging and no row arithmetic in
-// the inner loop.  One thread owns ONE board word (4 cells): a coalesced LDG.32, then per channel a branch-free
-// zero-byte test of (word ^ character) and one store -- 4 bytes (uint8: a warp writes 128 contiguous bytes per
-// channel) or 16 bytes (float32: 512 contiguous bytes), each (board, channel) row being word-aligned.  The board of
-// a word comes from one multiplication with the precomputed inverse of cells / 4.
+// float32 output, boards whose rows are whole 4-byte words (cells % 4 == 0; Hello World: 468): one thread owns one
+// 16-byte group of the FLAT output (4 cells of one (board, channel) row, which never straddles rows), so a warp
+// store is one aligned 512-byte run of whole lines; (board, channel, word) come from two multiplications with
+// precomputed inverses, the board word from a cached load (each is read once per channel), the compare is a
+// branch-free zero-byte test.
 template <typename OutT>
 __global__ void __launch_bounds__(TB) k_layers_words(const uint32_t* __restrict__ board, OutT* __restrict__ out,
                                                      CharTable ct, int L, int cw, int EB, int64_t n_boards,
-                                                     uint32_t inv_cw) {
+                                                     uint32_t inv_cw, uint32_t inv_L) {
+  static_assert(sizeof(OutT) == 4, "float32 layered boards");
   __shared__ uint32_t s_ch4[CX_MAX_CHARS];
   if (threadIdx.x < CX_MAX_CHARS) s_ch4[threadIdx.x] = ct.ch[threadIdx.x] * 0x01010101u;
   __syncthreads();
   const int64_t b0 = (int64_t)blockIdx.x * EB;
   const int nb = (int)min((int64_t)EB, n_boards - b0);
   const uint32_t* src = board + b0 * cw;
-  OutT* dst = out + b0 * L * cw * 4;
-  const uint32_t row = (uint32_t)cw * 4u;                     // elements per (board, channel) row
-  const uint32_t nw = (uint32_t)(nb * cw);
-  constexpr int U = 4;                                        // board words in flight per thread
-  for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += U * TB) {
-    uint32_t w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = i0 + u * TB;
-      w[u] = i < nw ? __ldcs(src + i) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = i0 + u * TB;
-      if (i >= nw) break;
-      const uint32_t e = __umulhi(i, inv_cw), q = i - e * (uint32_t)cw;   // exact: i * cw < 2^32 (EB * cells <= 32 KB)
-      OutT* p = dst + ((size_t)e * L * cw + q) * 4;
+  float4* dst4 = reinterpret_cast<float4*>(out + b0 * L * cw * 4);
+  const uint32_t total = (uint32_t)nb * (uint32_t)L * (uint32_t)cw;   // 16-byte output groups of this CTA
 #pragma unroll 4
-      for (int k = 0; k < L; ++k, p += row) {
-        const uint32_t m = bytes_equal01(w[u], s_ch4[k]);
-        if (sizeof(OutT) == 1) {
-          __stcs(reinterpret_cast<uint32_t*>(p), m);
-        } else {
-          __stcs(reinterpret_cast<float4*>(p), make_float4((float)(m & 1u), (float)((m >> 8) & 1u),
-                                                           (float)((m >> 16) & 1u), (float)(m >> 24)));
+  for (uint32_t i = threadIdx.x; i < total; i += TB) {
+    // exact: i * cw < 2^32 and row * L < 2^32 (EB * cells <= 32 KB, L <= CX_MAX_CHARS)
+    const uint32_t row = __umulhi(i, inv_cw), q = i - row * (uint32_t)cw;
+    const uint32_t e = L == 1 ? row : __umulhi(row, inv_L), k = row - e * (uint32_t)L;
+    const uint32_t m = bytes_equal01(src[e * (uint32_t)cw + q], s_ch4[k]);   // re-read once per channel: L1 hits
+    __stcs(dst4 + i, make_float4((float)(m & 1u), (float)((m >> 8) & 1u), (float)((m >> 16) & 1u), (float)(m >> 24)));
+  }
+}
+
+// float32 output, any board size: one thread owns one 16-byte group of the FLAT output = 4 consecutive cells of the
+// [board, channel, cell] order (they may run over the end of a row), so warp stores are aligned 512-byte runs here
+// too.  The cursor (board, channel, cell) comes from two inverse multiplications and advances cell by cell; board
+// bytes are staged in shared memory.
+__global__ void __launch_bounds__(TB) k_layers_cells_f32(const uint8_t* __restrict__ board, float* __restrict__ out,
+                                                         CharTable ct, int L, int cells, int EB, int64_t n_boards,
+                                                         uint32_t inv_cells, uint32_t inv_L) {
+  extern __shared__ __align__(16) uint8_t s_board[];          // EB * cells bytes
+  __shared__ uint8_t s_ch[CX_MAX_CHARS];
+  const int64_t b0 = (int64_t)blockIdx.x * EB;
+  const int nb = (int)min((int64_t)EB, n_boards - b0);
+  const int tile_bytes = nb * cells;
+  const uint8_t* src = board + b0 * cells;
+  if (threadIdx.x < CX_MAX_CHARS) s_ch[threadIdx.x] = ct.ch[threadIdx.x];
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint4* s16 = reinterpret_cast<const uint4*>(src);
+    uint4* d16 = reinterpret_cast<uint4*>(s_board);
+    for (int i = threadIdx.x; i < tile_bytes / 16; i += TB) d16[i] = __ldcs(s16 + i);
+    for (int i = (tile_bytes & ~15) + threadIdx.x; i < tile_bytes; i += TB) s_board[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < tile_bytes; i += TB) s_board[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t total = (uint32_t)nb * (uint32_t)L * (uint32_t)cells;   // output elements of this CTA
+  float* dst = out + b0 * L * cells;
+#pragma unroll 2
+  for (uint32_t f = threadIdx.x * 4u; f < total; f += TB * 4u) {
+    // exact: f * cells < 2^32 and row * L < 2^32 (checked by the launcher)
+    const uint32_t row = __umulhi(f, inv_cells);
+    uint32_t c = f - row * (uint32_t)cells;
+    const uint32_t e = L == 1 ? row : __umulhi(row, inv_L);
+    uint32_t k = row - e * (uint32_t)L, base = e * (uint32_t)cells;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = (f + j < total && s_board[base + c] == s_ch[k]) ? 1.0f : 0.0f;
+      if (++c == (uint32_t)cells) {
+        c = 0;
+        if (++k == (uint32_t)L) {
+          k = 0;
+          base += cells;
         }
       }
+    }
+    if (f + 4u <= total) {
+      __stcs(reinterpret_cast<float4*>(dst + f), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+      for (uint32_t j = 0; f + j < total; ++j) dst[f + j] = v[j];
     }
   }
 }
@@ -330,14 +364,30 @@ int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, Ou
     const int cw = cells / 4;
     const uint32_t inv_cw = cw == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)cw + 1u;
     if (cw > 1) {
-      k_layers_words<OutT><<<(unsigned)grid, TB, 0, s>>>(reinterpret_cast<const uint32_t*>(d_board), d_out, ct,
-                                                          g->info.n_chars, cw, EB, n_boards, inv_cw);
+      const int Lc = g->info.n_chars;
+      const uint32_t inv_Lc = Lc == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)Lc + 1u;
+      k_layers_words<float><<<(unsigned)grid, TB, 0, s>>>(reinterpret_cast<const uint32_t*>(d_board),
+                                                           reinterpret_cast<float*>(d_out), ct, Lc, cw, EB, n_boards,
+                                                           inv_cw, inv_Lc);
       CX_CUDA_OK(cudaGetLastError());
       return CX_OK;
     }
   }
   const size_t smem = ((size_t)EB * cells + 15) / 16 * 16 + 32;
   const int L = g->info.n_chars;
+  if (sizeof(OutT) == 4 && cells > 1 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
+      (uint64_t)EB * L * cells * (uint64_t)cells < (1ull << 32)) {
+    static bool configured_cells = false;
+    if (!configured_cells) {
+      CX_CUDA_OK(cudaFuncSetAttribute(k_layers_cells_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
+      configured_cells = true;
+    }
+    k_layers_cells_f32<<<(unsigned)grid, TB, smem, s>>>(d_board, reinterpret_cast<float*>(d_out), ct, L, cells, EB, n_boards,
+                                                        (uint32_t)(0xFFFFFFFFu / (uint32_t)cells + 1u),
+                                                        L == 1 ? 0u : (uint32_t)(0xFFFFFFFFu / (uint32_t)L + 1u));
+    CX_CUDA_OK(cudaGetLastError());
+    return CX_OK;
+  }
   // word path: rows of whole words, and the inverses exact for every output offset of a CTA (x * d < 2^32)
   const bool words = cells % 4 == 0 && cells >= 16 && L > 1 && (uint64_t)EB * L * cells * (uint64_t)cells < (1ull << 32);
   LayerDivisors dv;
