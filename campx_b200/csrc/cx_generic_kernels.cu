@@ -92,6 +92,7 @@ struct Ctx {
   const uint64_t* rowbits;
   const uint8_t* chidx;  // [256] char code -> game char index (0xFF: not a game char)
   const uint8_t* smem;   // staged tables blob
+  const uint4* act;      // [n_actions] {simple_reward bits, discount bits, directive flags, 0}: one LDS.128 per step
 };
 
 // per-warp view of the shared-memory working set
@@ -348,9 +349,10 @@ __device__ __forceinline__ void simple_env_step(const Ctx& X, uint32_t a, uint16
     st[d] = (uint16_t)(roll ? (r << 8) | c : r * C + c);
   }
   stamp(X, st, plane);
-  reward = H.simple_reward[a];
-  disc = H.act.discount[a];
-  flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+  const uint4 at = X.act[a];
+  reward = __uint_as_float(at.x);
+  disc = __uint_as_float(at.y);
+  flags = at.z;
 }
 
 // simple_env_step with the entity state in registers (k_generic_rollout<true>): sreg[d] = row << 16 | col for
@@ -389,9 +391,10 @@ __device__ __forceinline__ void fast_env_step(const Ctx& X, uint32_t a, uint32_t
     }
   }
   stamp(X, st, plane);
-  reward = H.simple_reward[a];
-  disc = H.act.discount[a];
-  flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+  const uint4 at = X.act[a];
+  reward = __uint_as_float(at.x);
+  disc = __uint_as_float(at.y);
+  flags = at.z;
 }
 __device__ __forceinline__ void fast_load_state(const Ctx& X, const uint16_t* st, uint32_t (&sreg)[CX_MAX_DYN]) {
   const CxGenHeader& H = *X.H;
@@ -429,7 +432,8 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   }
 }
 
-__device__ __forceinline__ void setup_ctx(Ctx& X, const GenParams& P, uint8_t* smem, uint8_t* s_chidx) {
+__device__ __forceinline__ void setup_ctx(Ctx& X, const GenParams& P, uint8_t* smem, uint8_t* s_chidx, const uint4* s_act) {
+  X.act = s_act;
   X.H = &P.h;
   X.masks = reinterpret_cast<const uint32_t*>(smem + P.h.off_masks);
   X.backdrop = smem + P.h.off_backdrop;
@@ -440,7 +444,12 @@ __device__ __forceinline__ void setup_ctx(Ctx& X, const GenParams& P, uint8_t* s
   X.smem = smem;
 }
 
-__device__ __forceinline__ void stage_tables(const GenParams& P, uint8_t* smem, uint8_t* s_chidx) {
+__device__ __forceinline__ void stage_tables(const GenParams& P, uint8_t* smem, uint8_t* s_chidx, uint4* s_act) {
+  if (threadIdx.x < CX_MAX_ACTIONS) {  // per-action directives: indexed by a lane-varying action in the step
+    const int a = threadIdx.x;
+    s_act[a] = make_uint4(__float_as_uint(P.h.simple_reward[a]), __float_as_uint(P.h.act.discount[a]),
+                          (P.h.act.over[a] ? CX_FLAG_TERMINATED : 0u) | (P.h.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0u), 0u);
+  }
   const uint4* src = reinterpret_cast<const uint4*>(P.blob);
   uint4* dst = reinterpret_cast<uint4*>(smem);
   for (int i = threadIdx.x; i < P.h.blob_bytes / 16; i += blockDim.x) dst[i] = src[i];
@@ -1013,12 +1022,13 @@ template <bool FAST, int OCC>
 __global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
+  __shared__ uint4 s_act[CX_MAX_ACTIONS];
   const CxGenHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int G = H.tile_envs, cells = H.cells;
-  stage_tables(P, smem, s_chidx);
+  stage_tables(P, smem, s_chidx, s_act);
   Ctx X;
-  setup_ctx(X, P, smem, s_chidx);
+  setup_ctx(X, P, smem, s_chidx, s_act);
   __syncthreads();  // tables staged; warps are independent from here on
 
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
@@ -1187,12 +1197,13 @@ __global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_consta
 __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
+  __shared__ uint4 s_act[CX_MAX_ACTIONS];
   const CxGenHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int G = H.tile_envs, cells = H.cells;
-  stage_tables(P, smem, s_chidx);
+  stage_tables(P, smem, s_chidx, s_act);
   Ctx X;
-  setup_ctx(X, P, smem, s_chidx);
+  setup_ctx(X, P, smem, s_chidx, s_act);
   __syncthreads();
   const int64_t env0 = ((int64_t)blockIdx.x * wpc + warp) * G;
   if (env0 >= P.n) return;
