@@ -667,11 +667,6 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
   }
   H->n_masks = H->n_points = 0;
   H->n_poke = H->n_above = 0;
-  {
-    int gcd16 = 16;
-    while (cells % gcd16) gcd16 >>= 1;
-    H->chunk_period = 16 / gcd16;
-  }
   for (int z = 0; z < E; ++z) {
     const CxGenEntity& g = H->ent[z];
     if (g.kind == CX_KIND_STATIC || g.kind == CX_KIND_ROLL) {

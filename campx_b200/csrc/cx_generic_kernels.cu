@@ -29,6 +29,12 @@
 //             bitset (funnel shift), expanded to byte masks (multiply trick) and merged with LOP3, then
 //             STG.128 (st.global.cs) straight from registers.  Chunks that straddle two envs (cells is
 //             not a multiple of 16) take a second pass with two slices per mask.
+// DIRECT composer (CxGenHeader::direct: at most 2 mask entities on boards of at most 496 cells; Hello World): phases
+// 1b/1c disappear.  A rolled mask is a slice of a host-built table (row dc = the static mask rolled by dc columns as
+// a linear bitset with wrap-around bits; the row roll is a rotation by dr * cols bits, i.e. an offset into that row),
+// lane l of iteration k composes chunk 32 k + l of the warp's tile, so every warp store is one aligned 512-byte run
+// of whole lines, and one-cell entities above the masks are byte-stored over the finished board.  Games whose
+// entities never consult the last render keep their entity state in registers (k_generic_rollout<true, ...>).
 // Per env-step HBM traffic is the observation contract only (board + reward + flags + discount + action);
 // entity state and the plane move once per launch.  Games with more than CX_MAX_LIN per-env masks, rolling
 // drapes wider than 64 columns, or unaligned buffers use the per-cell painter's algorithm instead.
@@ -44,22 +50,14 @@ namespace {
 #define CX_GEN_MIN_CTAS 5  // resident CTAs per SM the register allocation aims for (5 x 128 threads x 96 registers); the
                            // register-state kernel is also built for one CTA more, see cx_launch_generic_rollout
 #endif
-#ifndef CX_GEN_PERIOD_UNROLL
-#define CX_GEN_PERIOD_UNROLL 1  // periods of the direct composer in flight per warp
-#endif
-#ifndef CX_GEN_FLAT
-#define CX_GEN_FLAT 1   // direct composer: flat chunk mapping (aligned 512-byte warp stores); 0: per-env mapping
-#endif
 #ifndef CX_GEN_PROBE
 #define CX_GEN_PROBE 0
 #endif
 constexpr int kChunkUnroll = CX_GEN_UNROLL;
-constexpr int kPeriodUnroll = CX_GEN_PERIOD_UNROLL;
 #ifndef CX_GEN_FLAT_UNROLL
 #define CX_GEN_FLAT_UNROLL 5   // 512-byte groups of the flat composer in flight per warp
 #endif
 constexpr int kFlatUnroll = CX_GEN_FLAT_UNROLL;
-constexpr int GMAX = CX_GEN_TILE_ENVS;
 constexpr int NT = CX_GEN_CTA_THREADS;
 
 struct GenParams {
@@ -174,26 +172,6 @@ __device__ __forceinline__ uint8_t overlay(const Ctx& X, const uint16_t* st, int
     if (covers) v = e.ch;
   }
   return v;
-}
-
-// One board row of entity z as a bitset (bit c = column c), cols <= 64.
-__device__ __forceinline__ uint64_t entity_row(const Ctx& X, const uint16_t* st, int z, int r) {
-  const CxGenHeader& H = *X.H;
-  const CxGenEntity& e = H.ent[z];
-  if (e.kind == CX_KIND_STATIC) return X.rowbits[z * H.rows + r];
-  const uint32_t s = st[e.dyn_slot];
-  if (e.kind == CX_KIND_ROLL) {  // np.roll: content moves down/right by the accumulated offset
-    int sr = r - (int)(s >> 8);
-    if (sr < 0) sr += H.rows;
-    const uint64_t x = X.rowbits[z * H.rows + sr];
-    const uint32_t k = s & 255, C = H.cols;
-    if (k == 0) return x;
-    const uint64_t full = C == 64 ? ~0ull : ((1ull << C) - 1ull);
-    return ((x << k) | (x >> (C - k))) & full;
-  }
-  if (!e.visible || s == CX_EMPTY_CELL16) return 0ull;
-  const uint32_t rcv = X.rc[s];
-  return (rcv >> 8) == (uint32_t)r ? 1ull << (rcv & 255) : 0ull;
 }
 
 // rendering.py:150 through the alias of :128 -- sprites behind the first drape paint into the backdrop
@@ -675,122 +653,10 @@ __device__ __forceinline__ uint32_t direct_slice(const DirectMask& m, uint32_t o
   return __funnelshift_r(m.row[j], m.row[j + 1], S & 31u);  // bits 16-31: don't care
 }
 
-// What the direct composer needs per warp and does not change from step to step: computed once per launch.
-struct DirectGeom {
-  int per;            // envs per period of the chunk geometry (1, 2 or 4), 0: not periodic for this warp
-  uint32_t gc[4];     // this lane's chunk index in env r of a period (relative to the period's first chunk)
-  uint32_t go[4];     // ... and the offset of that chunk's first cell inside the env
-  uint32_t gok;       // bit r: the lane has a whole chunk in env r
-};
-__device__ __forceinline__ DirectGeom direct_geom(const CxGenHeader& H, int nenv, int lane) {
-  DirectGeom Gm;
-  const uint32_t cells = H.cells;
-  // periodic chunk geometry (PER = 1, 2 or 4 envs) when the warp's envs are whole periods
-  const int cp = H.chunk_period;
-  Gm.per = (cp == 1 || ((cp == 2 || cp == 4) && (nenv & (cp - 1)) == 0)) ? cp : 0;
-  Gm.gok = 0;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const uint32_t b0 = (uint32_t)r * cells;
-    const uint32_t c = ((b0 + 15u) >> 4) + lane;
-    const bool ok = c < ((b0 + cells) >> 4);
-    Gm.gok |= ok ? 1u << r : 0u;
-    Gm.gc[r] = ok ? c : 0u;
-    Gm.go[r] = ok ? 16u * c - b0 : 0u;
-  }
-  return Gm;
-}
-
-// Boards of at most 496 cells (every env has at most 31 whole chunks), exactly NM masks: one env per
-// iteration, one lane per chunk, branch-free so that consecutive envs interleave.  The per-env table row
-// and rotation of each mask are computed once by lane = env and broadcast with a shuffle.
-template <int NM, int PER>
-__device__ __forceinline__ void compose_direct_small(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
-                                                     uint8_t* dst, int lane) {
-  const CxGenHeader& H = *X.H;
-  const uint32_t cells = H.cells;
-  const uint4* p16 = reinterpret_cast<const uint4*>(W.plane);
-  uint4* d16 = reinterpret_cast<uint4*>(dst);
-  uint32_t pk[NM > 0 ? NM : 1], ch4[NM > 0 ? NM : 1];
-#pragma unroll
-  for (int i = 0; i < NM; ++i) {
-    ch4[i] = ((H.mask_prog[i] >> 8) & 0xFF) * 0x01010101u;
-    pk[i] = 0;
-    if (lane < nenv) {
-      const DirectMask m = direct_mask(X, W, i, lane);
-      pk[i] = m.rot | ((uint32_t)(reinterpret_cast<const uint8_t*>(m.row) - X.smem) << 12);
-    }
-  }
-  if (PER > 0) {
-    // The chunk geometry of env e + PER is that of env e moved by PER * cells / 16 whole chunks (PER = 16 /
-    // gcd(cells, 16)), so this lane's chunk index, offset and validity in envs r, r + PER, ... are computed once.
-    constexpr int PR = PER > 0 ? PER : 1;
-    const uint32_t adv = (uint32_t)PR * cells >> 4;
-    uint32_t cq = 0;
-#pragma unroll kPeriodUnroll
-    for (int e0 = 0; e0 < nenv; e0 += PR, cq += adv) {
-#pragma unroll
-      for (int r = 0; r < PR; ++r) {
-        const uint32_t c = cq + Gm.gc[r];
-        uint4 v = p16[c];
-#pragma unroll
-        for (int i = 0; i < NM; ++i) {
-          const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e0 + r);
-          DirectMask m;
-          m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
-          m.rot = q & 0xFFFu;
-          overlay16(v, direct_slice(m, Gm.go[r], cells), ch4[i]);
-        }
-        if ((Gm.gok >> r) & 1u) d16[c] = v;  // default policy: measured 3 % faster than st.global.cs here
-      }
-    }
-  } else {
-#pragma unroll 4
-    for (int e = 0; e < nenv; ++e) {
-      const uint32_t b0 = (uint32_t)e * cells;
-      const uint32_t c_lo = (b0 + 15u) >> 4, c_hi = (b0 + cells) >> 4;
-      const uint32_t c = c_lo + lane;
-      const bool ok = c < c_hi;
-      const uint32_t cc = ok ? c : 0u, o = ok ? 16u * c - b0 : 0u;
-      uint4 v = p16[cc];
-#pragma unroll
-      for (int i = 0; i < NM; ++i) {
-        const uint32_t q = __shfl_sync(0xffffffffu, pk[i], e);
-        DirectMask m;
-        m.row = reinterpret_cast<const uint32_t*>(X.smem + (q >> 12));
-        m.rot = q & 0xFFFu;
-        overlay16(v, direct_slice(m, o, cells), ch4[i]);
-      }
-      if (ok) __stcs(d16 + c, v);
-    }
-  }
-  // the chunk across the boundary between env i-1 and env i (lane i), if there is one
-  if ((cells & 15u) != 0) {
-    uint32_t pk_prev[NM > 0 ? NM : 1];
-#pragma unroll
-    for (int i = 0; i < NM; ++i) pk_prev[i] = __shfl_up_sync(0xffffffffu, pk[i], 1);
-    const uint32_t b = (uint32_t)lane * cells;
-    if (lane >= 1 && lane < nenv && (b & 15u) != 0) {
-      const uint32_t k = b >> 4, cnt = b - 16u * k;       // cnt cells of env lane-1, 16-cnt cells of env lane
-      const uint32_t o = cells - cnt, lo_mask = (1u << cnt) - 1u;
-      uint4 v = p16[k];
-#pragma unroll
-      for (int i = 0; i < NM; ++i) {
-        DirectMask m0, m1;
-        m0.row = reinterpret_cast<const uint32_t*>(X.smem + (pk_prev[i] >> 12));
-        m0.rot = pk_prev[i] & 0xFFFu;
-        m1.row = reinterpret_cast<const uint32_t*>(X.smem + (pk[i] >> 12));
-        m1.rot = pk[i] & 0xFFFu;
-        overlay16(v, (direct_slice(m0, o, cells) & lo_mask) | (direct_slice(m1, 0u, cells) << cnt), ch4[i]);
-      }
-      __stcs(d16 + k, v);
-    }
-  }
-}
-
-// Flat variant of compose_direct_small: lane l of iteration k composes chunk 32 k + l of the warp's board tile, so
-// every warp store is one 512-byte, 512-byte-aligned run of whole lines (the per-env mapping stores 29 of 32 chunks
-// from a 16-byte-aligned start: 5 partial lines per store, measured 4.4 TB/s against 5.6 TB/s for aligned runs).
+// Boards of at most 496 cells, exactly NM masks.  Flat chunk mapping: lane l of iteration k composes chunk 32 k + l
+// of the warp's board tile, so every warp store is one 512-byte, 512-byte-aligned run of whole lines (a mapping
+// that follows the envs -- 29 of 32 lanes storing from a 16-byte-aligned start, 5 partial lines per store --
+// measured 4.4 TB/s against 5.6 TB/s for aligned runs, see profiles/r01_ncu_generic_rollout.md).
 // The env of a chunk is one multiplication with the inverse of `cells`; its table row and rotation come from the
 // lane that owns the env (SHFL with a per-lane source).  Chunks that straddle two envs are left to lane = env below.
 template <int NM, int U>
@@ -853,8 +719,7 @@ __device__ __forceinline__ void compose_direct_flat(const Ctx& X, const WarpMem&
 }
 
 template <int U>
-__device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
-                                               uint8_t* dst, int lane) {
+__device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
   const CxGenHeader& H = *X.H;
   const uint32_t cells = H.cells;
   const int n_masks = H.n_masks;
@@ -868,24 +733,9 @@ __device__ __forceinline__ void compose_direct(const Ctx& X, const WarpMem& W, c
   // that lies inside the env
   const bool small = cells <= 496u && n_masks <= 2;
   if (small) {
-    const int per = Gm.per;
-#define CX_SMALL(NMASK)                                                                 \
-  do {                                                                                  \
-    if (per == 4) compose_direct_small<NMASK, 4>(X, W, Gm, nenv, dst, lane);                \
-    else if (per == 2) compose_direct_small<NMASK, 2>(X, W, Gm, nenv, dst, lane);           \
-    else if (per == 1) compose_direct_small<NMASK, 1>(X, W, Gm, nenv, dst, lane);           \
-    else compose_direct_small<NMASK, 0>(X, W, Gm, nenv, dst, lane);                         \
-  } while (0)
-#if CX_GEN_FLAT
     if (n_masks == 0) compose_direct_flat<0, U>(X, W, nenv, dst, lane);
     else if (n_masks == 1) compose_direct_flat<1, U>(X, W, nenv, dst, lane);
     else compose_direct_flat<2, U>(X, W, nenv, dst, lane);
-#else
-    if (n_masks == 0) CX_SMALL(0);
-    else if (n_masks == 1) CX_SMALL(1);
-    else CX_SMALL(2);
-#endif
-#undef CX_SMALL
     return;
   }
 #pragma unroll 2
@@ -955,8 +805,8 @@ __device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int 
 // Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
 // per-cell painter's algorithm with byte stores (any geometry, any alignment).
 template <int U>
-__device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, const DirectGeom& Gm, int nenv,
-                                             uint8_t* dst, bool fast, int lane) {
+__device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, bool fast,
+                                             int lane) {
   const CxGenHeader& H = *X.H;
   if (fast && H.direct) {
     const bool pokes = H.n_poke > 0;  // warp-uniform
@@ -965,7 +815,7 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, con
       if (lane < nenv) saved = poke_below(X, W, lane);
       __syncwarp();
     }
-    compose_direct<U>(X, W, Gm, nenv, dst, lane);
+    compose_direct<U>(X, W, nenv, dst, lane);
     if (H.n_above > 0) {
       __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
       if (lane < nenv) store_above(X, W, lane, dst);
@@ -1064,7 +914,6 @@ __global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_consta
   __syncwarp();
   uint32_t sreg[CX_MAX_DYN];
   if (FAST && mine) fast_load_state(X, dyn[lane], sreg);
-  const DirectGeom Gm = direct_geom(H, nenv, lane);
 
   uint32_t ep_cnt = 0, ep_len = 0;
   double ep_sum = 0.0, ep_sumsq = 0.0;
@@ -1131,7 +980,7 @@ __global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_consta
 
     // ---- phases 1b, 1c, 2: compose the boards and stream them out ----
 #if CX_GEN_PROBE != 1  // development probe (1: no composition)
-    compose_warp<OCC >= 6 ? 3 : kFlatUnroll>(X, W, Gm, nenv, P.board + row * cells, fast, lane);
+    compose_warp<OCC >= 6 ? 3 : kFlatUnroll>(X, W, nenv, P.board + row * cells, fast, lane);
 #endif
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
@@ -1217,7 +1066,7 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
     W.plane[b] = H.has_dynbd ? P.dynbd[env0 * cells + b] : X.backdrop[b - e * cells];
   }
   __syncwarp();
-  compose_warp<kFlatUnroll>(X, W, direct_geom(H, nenv, lane), nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
+  compose_warp<kFlatUnroll>(X, W, nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {

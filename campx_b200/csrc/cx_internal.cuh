@@ -105,7 +105,6 @@ struct CxGenHeader {
   int32_t n_poke;                        // below every mask and not stamping: poked into the plane around the composition
   int32_t n_above;                       // above every mask: stored over the finished board
   uint16_t above_prog[CX_MAX_DYN];       // back to front: ch << 8 | dyn_slot
-  int32_t chunk_period;                  // 16 / gcd(cells, 16): the 16-byte chunk geometry of env e + period equals env e's
   int32_t off_colroll[CX_MAX_LIN];       // per lin slot of a rolling drape: u32 [cols][mask_words + 1], the static mask
                                          // rolled right by dc columns, as linear bitsets; -1: not tabulated
   // direct composer: no per-env bitsets at all.  Every mask entity has a bit table in the blob -- one row
