@@ -843,6 +843,7 @@ extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
 
   CX_CUDA_OK(cudaGetDevice(&g->device));
   CX_CUDA_OK(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+  CX_CUDA_OK(cudaDeviceGetAttribute(&g->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, g->device));
   CX_CUDA_OK(cudaMalloc((void**)&g->d_blob, blob.bytes.size()));
   CX_CUDA_OK(cudaMemcpy(g->d_blob, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice));
   CX_CUDA_OK(cudaMalloc((void**)&g->d_chars, CX_MAX_CHARS));

@@ -59,6 +59,7 @@ constexpr int kChunkUnroll = CX_GEN_UNROLL;
 #endif
 constexpr int kFlatUnroll = CX_GEN_FLAT_UNROLL;
 constexpr int NT = CX_GEN_CTA_THREADS;
+constexpr int kWaveThreads = 448;  // fat CTAs of the one-wave build: 2 x 448 threads x 72 registers per SM
 
 struct GenParams {
   CxGenHeader h;
@@ -868,8 +869,8 @@ __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem,
   return W;
 }
 
-template <bool FAST, int OCC>
-__global__ void __launch_bounds__(NT, OCC) k_generic_rollout(const __grid_constant__ GenParams P) {
+template <bool FAST, int BLK, int OCC>
+__global__ void __launch_bounds__(BLK, OCC) k_generic_rollout(const __grid_constant__ GenParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint8_t s_chidx[256];
   __shared__ uint4 s_act[CX_MAX_ACTIONS];
@@ -1105,9 +1106,10 @@ bool gen_vec_ok(const cx_game* g, int64_t n, const void* d_board) {
 int configure_once() {
   static bool configured = false;
   if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, CX_GEN_MIN_CTAS + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false, NT, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, kWaveThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
@@ -1142,17 +1144,27 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   }
   int rc = configure_once();
   if (rc) return rc;
-  if (g->gh.fast_loop && P.vec)
-    // Two register budgets of the same kernel: CX_GEN_MIN_CTAS + 1 resident CTAs per SM (80 registers) wins once the
-    // grid is several waves deep; one CTA fewer with more registers wins on 1-2 waves, where the tail of a nearly
-    // empty last wave costs more than the extra warps hide (Hello World: 65,536 envs 8.4e9 vs 7.9e9, 2^18 envs 9.8e9
-    // vs 1.02e10 env-steps/s)
-    if (grid >= 4 * (int64_t)g->sm_count * (CX_GEN_MIN_CTAS + 1))
-      k_generic_rollout<true, CX_GEN_MIN_CTAS + 1><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
-    else
-      k_generic_rollout<true, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+  if (g->gh.fast_loop && P.vec) {
+    // Three builds of the register-state kernel, chosen by how the batch fills the machine:
+    //  * a batch that needs slightly more warps per SM than 4-warp CTAs keep resident (Hello World, 65,536 envs: 27.7
+    //    against 20-24) would run 1.2-1.4 waves; two fat CTAs per SM (up to 14 warps each, 72 registers) hold it in
+    //    ONE wave instead;
+    //  * CX_GEN_MIN_CTAS + 1 resident CTAs per SM (80 registers) once the grid is several waves deep;
+    //  * CX_GEN_MIN_CTAS CTAs (96 registers) otherwise.
+    const int64_t per_sm = (warps + g->sm_count - 1) / g->sm_count;
+    const int fat = (int)((per_sm + 1) / 2);  // warps per CTA with two CTAs per SM
+    if (per_sm > (int64_t)wpc * CX_GEN_MIN_CTAS && fat * 32 <= kWaveThreads &&
+        2 * (gen_smem_bytes(g, fat) + 1024 + 512) <= (size_t)g->smem_per_sm) {
+      const int64_t fgrid = (warps + fat - 1) / fat;
+      k_generic_rollout<true, kWaveThreads, 2><<<(unsigned)fgrid, fat * 32, gen_smem_bytes(g, fat), s>>>(P);
+    } else if (grid >= 4 * (int64_t)g->sm_count * (CX_GEN_MIN_CTAS + 1)) {
+      k_generic_rollout<true, NT, CX_GEN_MIN_CTAS + 1><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    } else {
+      k_generic_rollout<true, NT, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    }
+  }
   else
-    k_generic_rollout<false, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
+    k_generic_rollout<false, NT, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

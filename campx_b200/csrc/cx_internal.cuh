@@ -164,6 +164,7 @@ struct cx_game {
   uint8_t* d_chars;        // device copy of chars[] for the layer kernels
   int device;
   int sm_count;
+  int smem_per_sm;   // cudaDevAttrMaxSharedMemoryPerMultiprocessor (bytes)
 };
 
 CxStateLayout cx_layout(const cx_game* g, int64_t n);

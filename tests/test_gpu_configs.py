@@ -120,3 +120,22 @@ def test_config2_walls_and_hover_rewards_2pow20_envs(world):
         obs, rew, _ = game2.play(acts[t])
         assert torch.equal(obs.board.view(n, 25), flat[t]) and torch.equal(rew, rewards[t])
     replay(world, acts, boards, rewards, flags, sample_envs(n, 24, 3), limit)
+
+
+@pytest.mark.parametrize("n", [49152, 57344 + 16 * 37])
+def test_one_wave_build_matches_the_standard_build(n):
+    """Batches that need 21..28 warps per SM run on the fat-CTA build of the register-state kernel (two CTAs of up to 14
+    warps per SM, one wave; cx_launch_generic_rollout).  Environments are independent, so any 64 of them replayed in a
+    64-env batch (standard build) must give the same boards, rewards, flags and discounts."""
+    T = 14
+    big = make_world("hello", num_envs=n, max_episode_steps=9, track_returns=True, verify=False)
+    small = make_world("hello", num_envs=64, max_episode_steps=9, track_returns=True, verify=False)
+    big.its_showtime()
+    small.its_showtime()
+    acts = big.native.fill_actions(T, seed=77)
+    boards, rewards, discounts, flags = big.rollout(acts)
+    pick = torch.cat([torch.arange(0, 16), torch.arange(n // 2 - 16, n // 2 + 16), torch.arange(n - 16, n)]).cuda()
+    b2, r2, d2, f2 = small.rollout(acts[:, pick].contiguous())
+    assert torch.equal(boards[:, pick], b2) and torch.equal(rewards[:, pick], r2) and torch.equal(flags[:, pick], f2)
+    assert (discounts is None and d2 is None) or torch.equal(discounts[:, pick], d2)
+    assert big.episode_stats()["env_steps"] == n * T
