@@ -1110,6 +1110,9 @@ int configure_once() {
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, kWaveThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    // two 112 KB CTAs per SM need the largest shared-memory carveout (a hint the driver would otherwise derive per launch)
+    CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, kWaveThreads, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
