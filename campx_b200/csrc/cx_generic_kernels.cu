@@ -1152,15 +1152,18 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
     //  * a batch that needs slightly more warps per SM than 4-warp CTAs keep resident (Hello World, 65,536 envs: 27.7
     //    against 20-24) would run 1.2-1.4 waves; two fat CTAs per SM (up to 14 warps each, 72 registers) hold it in
     //    ONE wave instead;
-    //  * CX_GEN_MIN_CTAS + 1 resident CTAs per SM (80 registers) once the grid is several waves deep;
+    //  * CX_GEN_MIN_CTAS + 1 resident CTAs per SM (80 registers) once the grid is at least two waves deep;
     //  * CX_GEN_MIN_CTAS CTAs (96 registers) otherwise.
     const int64_t per_sm = (warps + g->sm_count - 1) / g->sm_count;
-    const int fat = (int)((per_sm + 1) / 2);  // warps per CTA with two CTAs per SM
-    if (per_sm > (int64_t)wpc * CX_GEN_MIN_CTAS && fat * 32 <= kWaveThreads &&
+    int fat = (int)((per_sm + 1) / 2);  // warps per CTA with two CTAs per SM
+    int force = 0;                       // development knob: 1 = 5 CTAs x 96 regs, 2 = 6 x 80, 3 = fat CTAs
+    if (const char* dbg = getenv("CX_GEN_BUILD")) force = atoi(dbg);
+    if (force == 3) fat = kWaveThreads / 32;
+    if (force != 1 && force != 2 && (force == 3 || per_sm > (int64_t)wpc * CX_GEN_MIN_CTAS) && fat * 32 <= kWaveThreads &&
         2 * (gen_smem_bytes(g, fat) + 1024 + 512) <= (size_t)g->smem_per_sm) {
       const int64_t fgrid = (warps + fat - 1) / fat;
       k_generic_rollout<true, kWaveThreads, 2><<<(unsigned)fgrid, fat * 32, gen_smem_bytes(g, fat), s>>>(P);
-    } else if (grid >= 4 * (int64_t)g->sm_count * (CX_GEN_MIN_CTAS + 1)) {
+    } else if (force == 2 || (force != 1 && grid >= 2 * (int64_t)g->sm_count * (CX_GEN_MIN_CTAS + 1))) {
       k_generic_rollout<true, NT, CX_GEN_MIN_CTAS + 1><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
     } else {
       k_generic_rollout<true, NT, CX_GEN_MIN_CTAS><<<(unsigned)grid, wpc * 32, gen_smem_bytes(g, wpc), s>>>(P);
