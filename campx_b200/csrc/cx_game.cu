@@ -924,7 +924,14 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     return CX_ERR_INVALID_ARG;
   }
   if (g->path == CX_PATH_AGENT) {
-    if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS)  // large boards: lane-per-env kernel, board only
+    // k_agent_rollout gives every warp 256 envs: below half a wave of its 1,024-env CTAs (7 per SM) the batch is
+    // bound by the per-warp step latency, and the lane-per-env kernel (32 envs per warp, 8x the warps) is faster --
+    // measured on Demo 1: 16,384 envs 0.052 -> 0.020 ms per 32 steps, 65,536 0.052 -> 0.043, 2^18 0.111 -> 0.070,
+    // equal at 2^19, and 0.185 against 0.276 at 2^20 (scripts/small_batch_time.py).  CX_AGENT_SMALL_N overrides the
+    // threshold (0: always k_agent_rollout).
+    int64_t small_n = (int64_t)g->sm_count * 7 * 1024 / 2;
+    if (const char* dbg = getenv("CX_AGENT_SMALL_N")) small_n = atoll(dbg);
+    if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS || n < small_n)  // large boards, small batches: lane-per-env kernel, board only
       return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                          nullptr, (cudaStream_t)stream);
     return cx_launch_agent_rollout(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,

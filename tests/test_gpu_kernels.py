@@ -15,6 +15,16 @@ pytestmark = pytest.mark.gpu
 WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
 
 
+@pytest.fixture(autouse=True, params=["auto", "warp_tile"])
+def agent_kernel(request, monkeypatch):
+    """Single-agent worlds run on two kernels: small batches take the lane-per-env kernel (cx_rollout's default below
+    half a wave), large ones k_agent_rollout (256 envs per warp: the bench kernel).  Every test of this module runs
+    on both: CX_AGENT_SMALL_N=0 sends small batches to k_agent_rollout as well."""
+    if request.param == "warp_tile":
+        monkeypatch.setenv("CX_AGENT_SMALL_N", "0")
+    return request.param
+
+
 def _game(world, n, **kw):
     from campx_b200.runtime import NativeGame
     return NativeGame(expected_spec(world, **kw), n)
