@@ -101,6 +101,8 @@ class GraphedRollout(object):
         self.all_envs = torch.ones(n, dtype=torch.uint8, device=dev)
         self.board = game.reset(self.all_envs).board.clone()   # board the next rollout starts from
         self.graph = None
+        self.step_kernel = "cx_layers_from_board_f32 + cx_step"
+        self.kernels_per_step = None
 
     def _body(self):
         nat, game, n = self.game.native, self.game, self.game.num_envs
