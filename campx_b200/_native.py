@@ -7,7 +7,7 @@ compute entry point is needed, this module raises.  The library is built in-tree
 import ctypes
 import os
 
-CX_ABI_VERSION = 2
+CX_ABI_VERSION = 3
 CX_MAX_ENTITIES = 16
 CX_MAX_ACTIONS = 8
 CX_MAX_CHARS = 32
@@ -29,6 +29,8 @@ CX_FLAG_TRUNCATED = 0x02
 CX_FLAG_REWARD_NONE = 0x04
 CX_FLAG_ALREADY_OVER = 0x08
 CX_FLAG_BAD_ACTION = 0x80
+
+CX_DTYPE_U8, CX_DTYPE_F32, CX_DTYPE_BF16 = 0, 1, 2
 
 CX_STATS_DOUBLES = 8
 STAT_NAMES = ("episodes", "return_sum", "return_sumsq", "length_sum", "return_max", "neg_return_min",
@@ -119,6 +121,8 @@ PROTOTYPES = {
     "cx_rollout": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "cx_rollout_synth": (ctypes.c_int, [_P, _P, _I64, _I32, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P]),
     "cx_rollout_observations": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "cx_step_observations": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "cx_sample_actions": (ctypes.c_int, [_P, _I64, _I32, _I32, _U64, _U64, _P, _U64, _P, _P, _P]),
     "cx_layers_from_board": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_layers_from_board_f32": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "cx_board_mapper_create": (ctypes.c_int, [_P, _P, _I32, _I32, ctypes.POINTER(_P)]),

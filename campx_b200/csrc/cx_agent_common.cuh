@@ -68,6 +68,11 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the source bytes of every committed bulk store have been read: the tile may be modified again
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... of all but the N most recently committed groups (a ring of N + 1 tiles)
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_pending() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (the TMA engine)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

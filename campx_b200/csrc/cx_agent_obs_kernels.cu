@@ -21,6 +21,8 @@
 // are too large for k_agent_rollout's 256-env warp tiles (97..254 cells): at >= 100 bytes per env-step a
 // lane-per-env warp saturates HBM as well.  It also takes ragged batches (N not a multiple of 32) and
 // unaligned buffers (coalesced byte stores instead of the bulk stores) and in-kernel Philox actions.
+#include <stdlib.h>
+
 #include "cx_agent_common.cuh"
 #include "cx_philox.cuh"
 
@@ -51,7 +53,12 @@ constexpr int OBS_WARPS = 4;
 constexpr int OBS_THREADS = OBS_WARPS * 32;
 constexpr int OBS_TILE = 32;  // envs per warp: lane = env
 
-template <bool TRACK>
+// RING: tiles per warp.  A warp may not touch a tile again before the bulk store that shipped it has READ it; with one
+// tile that wait (TMA issue -> shared-memory read, ~1 us) sits on every step's critical path, which is what bounds
+// small batches (65,536 envs = 14 warps per SM: there is nothing else to run meanwhile).  With RING tiles used round
+// robin the warp waits for the store issued RING steps ago (`cp.async.bulk.wait_group.read RING-1`), i.e. almost
+// never, and a step's chain is table lookup -> 2 byte pokes -> fence -> issue.
+template <bool TRACK, int RING>
 __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_constant__ ObsParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CxAgentHeader& H = P.h;
@@ -85,30 +92,35 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
   const bool auto_reset = H.auto_reset != 0, want_discount = P.discount != nullptr;
 
-  // per warp: [board tile 32*cells][layered tile 32*chars*cells (if wanted)], both multiples of 16 bytes
+  // per warp: RING x { [board tile 32*cells][layered tile 32*chars*cells (if wanted)] }, all multiples of 16 bytes
   const int per_env = cells + (layers ? lay_bytes : 0);
-  uint8_t* wbase = smem + H.blob_bytes_ext + (size_t)warp * OBS_TILE * per_env;
-  uint8_t* btile = wbase;
-  uint8_t* ltile = wbase + OBS_TILE * cells;
-  uint8_t* myb = btile + lane * cells;
-  uint8_t* myl = ltile + lane * lay_bytes;
-  for (int c = 0; c < cells; ++c) myb[c] = s_basech[c];       // every lane stages its own env's static scene
-  if (layers)
-    for (int j = 0; j < lay_bytes; ++j) myl[j] = s_baselay[j];
+  const int slot_bytes = OBS_TILE * per_env;
+  uint8_t* wbase = smem + H.blob_bytes_ext + (size_t)warp * RING * slot_bytes;
+  for (int r = 0; r < RING; ++r) {                              // every lane stages its own env's static scene
+    uint8_t* myb = wbase + r * slot_bytes + lane * cells;
+    uint8_t* myl = wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes;
+    for (int c = 0; c < cells; ++c) myb[c] = s_basech[c];
+    if (layers)
+      for (int j = 0; j < lay_bytes; ++j) myl[j] = s_baselay[j];
+  }
   __syncwarp();
 
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  auto draw = [&](uint32_t c) {  // paint the agent at visible cell c
+  auto draw = [&](int r, uint32_t c) {  // paint the agent at visible cell c of ring slot r
+    uint8_t* myb = wbase + r * slot_bytes + lane * cells;
     myb[c] = (uint8_t)agent_char;
     if (layers) {
+      uint8_t* myl = wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes;
       const uint32_t k = s_basek[c];
       if (k != 0xFF) myl[k * cells + c] = 0;
       myl[agent_k * cells + c] = 1;
     }
   };
-  auto erase = [&](uint32_t c) {  // back to the static scene at cell c
+  auto erase = [&](int r, uint32_t c) {  // back to the static scene at cell c
+    uint8_t* myb = wbase + r * slot_bytes + lane * cells;
     myb[c] = s_basech[c];
     if (layers) {
+      uint8_t* myl = wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes;
       myl[agent_k * cells + c] = 0;
       const uint32_t k = s_basek[c];
       if (k != 0xFF) myl[k * cells + c] = 1;
@@ -116,8 +128,13 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   };
 
   uint32_t cell = mine ? min((uint32_t)P.cell[env], none) : none;
-  uint32_t drawn = s_shown[cell];
-  if (drawn != none) draw(drawn);
+  uint32_t shown = s_shown[cell];   // where the agent is drawn in the most recent frame
+  uint32_t drawn[RING];             // ... and in each ring slot (a slot is RING frames behind when it comes up again)
+#pragma unroll
+  for (int r = 0; r < RING; ++r) {
+    drawn[r] = shown;
+    if (shown != none) draw(r, shown);
+  }
   uint32_t ts = 0;
   float rt = 0.0f;
   if (TRACK && mine) {
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
     rt = P.ret[env];
   }
   LaneStats& stats =
-      reinterpret_cast<LaneStats*>(smem + H.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env)[tid];
+      reinterpret_cast<LaneStats*>(smem + H.blob_bytes_ext + (size_t)OBS_WARPS * RING * slot_bytes)[tid];
   if (TRACK) stats.clear();
 
   // whole tiles over TMA when the rows are 16-byte aligned and the warp owns 32 envs; else byte stores
@@ -140,77 +157,94 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
     return P.actions[(int64_t)t * n + env];
   };
   const uint64_t l2pol = l2_evict_first_policy();
-  uint32_t act = fetch_action(0), act_next = fetch_action(1);
+  // the loop is unrolled by UNR steps so that ring slots and the action registers are indexed statically; actions
+  // are fetched one whole group (UNR steps) ahead of their use
+  constexpr int UNR = 4;
+  static_assert(UNR % RING == 0, "ring slots are indexed by the unrolled step");
+  uint32_t act[UNR], act_next[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) act[u] = fetch_action(u);
 
-  for (int t = 0; t < P.T; ++t) {
-    const int64_t row = (int64_t)t * n + env0;
-    // ---- phase A: the env's step (same table as k_agent_rollout) ----
-    const uint32_t a = min(act, n_actions);
-    const uint32_t idx = a * stride + cell;
-    uint32_t e = s_tt[idx];
-    float r = s_tr[idx];
-    float dc = want_discount ? s_td[a] : 1.0f;
-    if (TRACK && (ts & CX_OVER_BIT)) {
-      e = cell | (drawn << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
-      r = 0.0f;
-      dc = 0.0f;
-    }
-    uint32_t p = e & 0xFF;
-    const uint32_t show = mine ? (e >> 8) & 0xFF : none;
-    uint32_t f = e >> 16;
-    if (TRACK && mine && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
-      const uint32_t steps = ts + 1u;
-      rt += r;
-      if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
-      ts = steps;
-      if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
-        stats.episode(rt, steps);
-        if (auto_reset) {
-          p = H.init_cell;
-          ts = 0;
-          rt = 0.0f;
-        } else {
-          ts |= CX_OVER_BIT;
+  for (int t0 = 0; t0 < P.T; t0 += UNR) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) act_next[u] = fetch_action(t0 + UNR + u);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int t = t0 + u;
+      if (t >= P.T) break;
+      const int r = u % RING;
+      const int64_t row = (int64_t)t * n + env0;
+      // ---- phase A: the env's step (same table as k_agent_rollout) ----
+      const uint32_t a = min(act[u], n_actions);
+      const uint32_t idx = a * stride + cell;
+      uint32_t e = s_tt[idx];
+      float rw = s_tr[idx];
+      float dc = want_discount ? s_td[a] : 1.0f;
+      if (TRACK && (ts & CX_OVER_BIT)) {
+        e = cell | (shown << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+        rw = 0.0f;
+        dc = 0.0f;
+      }
+      uint32_t p = e & 0xFF;
+      const uint32_t show = mine ? (e >> 8) & 0xFF : none;
+      uint32_t f = e >> 16;
+      if (TRACK && mine && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
+        const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);   // 15-bit counter saturates (bit 15 = OVER)
+        rt += rw;
+        if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
+        ts = steps;
+        if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
+          stats.episode(rt, steps);
+          if (auto_reset) {
+            p = H.init_cell;
+            ts = 0;
+            rt = 0.0f;
+          } else {
+            ts |= CX_OVER_BIT;
+          }
         }
       }
-    }
-    if (mine) {
-      cell = p;
-      __stcs(P.reward + row + lane, r);
-      if (want_discount) __stcs(P.discount + row + lane, dc);
-      P.flags[row + lane] = (uint8_t)f;
-    }
-    act = act_next;
-    act_next = fetch_action(t + 2);
+      if (mine) {
+        cell = p;
+        __stcs(P.reward + row + lane, rw);
+        if (want_discount) __stcs(P.discount + row + lane, dc);
+        P.flags[row + lane] = (uint8_t)f;
+      }
+      shown = show;
 
-    // ---- phase B: re-compose the tiles (2 + 4 byte stores when the agent moved) and send them out ----
-    if (bulk) {
-      if (lane == 0) bulk_wait_read();  // the previous step's bulk stores have read the tiles
-      __syncwarp();
-    }
-    if (drawn != show) {
-      if (drawn != none) erase(drawn);
-      if (show != none) draw(show);
-      drawn = show;
-    }
-    uint8_t* bdst = P.board + row * cells;
-    if (bulk) {
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_store_s2g(bdst, btile, (uint32_t)(OBS_TILE * cells), l2pol);
-        if (layers) bulk_store_s2g(P.layered + row * lay_bytes, ltile, (uint32_t)(OBS_TILE * lay_bytes), l2pol);
-        bulk_commit();
+      // ---- phase B: bring ring slot r up to date (2 + 4 byte stores when the agent moved) and send it out ----
+      if (bulk) {
+        if (lane == 0) bulk_wait_read_pending<RING - 1>();  // the store that last shipped slot r has read it
+        __syncwarp();
       }
-    } else {
-      __syncwarp();
-      for (int k = lane; k < nenv * cells; k += 32) bdst[k] = btile[k];
-      if (layers) {
-        uint8_t* ldst = P.layered + row * lay_bytes;
-        for (int k = lane; k < nenv * lay_bytes; k += 32) ldst[k] = ltile[k];
+      if (drawn[r] != show) {
+        if (drawn[r] != none) erase(r, drawn[r]);
+        if (show != none) draw(r, show);
+        drawn[r] = show;
       }
-      __syncwarp();
+      const uint8_t* btile = wbase + r * slot_bytes;
+      const uint8_t* ltile = btile + OBS_TILE * cells;
+      uint8_t* bdst = P.board + row * cells;
+      if (bulk) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_store_s2g(bdst, btile, (uint32_t)(OBS_TILE * cells), l2pol);
+          if (layers) bulk_store_s2g(P.layered + row * lay_bytes, ltile, (uint32_t)(OBS_TILE * lay_bytes), l2pol);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int k = lane; k < nenv * cells; k += 32) bdst[k] = btile[k];
+        if (layers) {
+          uint8_t* ldst = P.layered + row * lay_bytes;
+          for (int k = lane; k < nenv * lay_bytes; k += 32) ldst[k] = ltile[k];
+        }
+        __syncwarp();
+      }
     }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) act[u] = act_next[u];
   }
   if (lane == 0) bulk_wait_read();
   __syncwarp();
@@ -239,19 +273,17 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   }
 }
 
-size_t obs_smem_bytes(const cx_game* g, bool layers) {
+size_t obs_smem_bytes(const cx_game* g, bool layers, int ring = 1) {
   const size_t per_env = (size_t)g->ah.cells * (1 + (layers ? g->ah.n_chars : 0));
-  return (size_t)g->ah.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env +
+  return (size_t)g->ah.blob_bytes_ext + (size_t)OBS_WARPS * OBS_TILE * per_env * ring +
          (g->ah.track ? OBS_THREADS * sizeof(LaneStats) : 0);
 }
 
-template <bool TRACK>
+template <bool TRACK, int RING>
 int launch_obs(const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_obs<TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  // the cap on dynamic shared memory is a per-device function attribute: set it on every launch (it reserves nothing)
+  CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_obs<TRACK, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(OBS_THREADS);
@@ -262,8 +294,15 @@ int launch_obs(const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout_obs<TRACK>, P));
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout_obs<TRACK, RING>, P));
   return CX_OK;
+}
+
+template <bool TRACK>
+int launch_obs_ring(int ring, const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  if (ring >= 4) return launch_obs<TRACK, 4>(P, grid, smem, s);
+  if (ring >= 2) return launch_obs<TRACK, 2>(P, grid, smem, s);
+  return launch_obs<TRACK, 1>(P, grid, smem, s);
 }
 
 }  // namespace
@@ -310,6 +349,22 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
     cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  const size_t smem = obs_smem_bytes(g, d_layered != nullptr);
-  return g->ah.track ? launch_obs<true>(P, (unsigned)grid, smem, s) : launch_obs<false>(P, (unsigned)grid, smem, s);
+  // ring depth: as many tiles per warp as keep the CTA's shared memory small enough for the occupancy the batch can
+  // use (the tiles of a 5x5 world are 800 B per warp and slot; a layered 5x5 slot is 6.4 KB)
+  const bool lay = d_layered != nullptr;
+  int ring = 1;
+  if (P.bulk && T > 1) {
+    const size_t budget = lay ? 56 * 1024 : 32 * 1024;   // 4 resp. 7 CTAs per SM
+    if (obs_smem_bytes(g, lay, 4) <= budget) ring = 4;
+    else if (obs_smem_bytes(g, lay, 2) <= budget) ring = 2;
+  }
+  if (const char* dbg = getenv("CX_OBS_RING")) ring = atoi(dbg);   // development knob: 1, 2 or 4
+  ring = ring >= 4 ? 4 : (ring >= 2 ? 2 : 1);
+  const size_t smem = obs_smem_bytes(g, lay, ring);
+  if (smem > 227 * 1024) {
+    cx_set_error("cx_rollout: board too large for the lane-per-env kernel with %d tiles per warp", ring);
+    return CX_ERR_INVALID_ARG;
+  }
+  return g->ah.track ? launch_obs_ring<true>(ring, P, (unsigned)grid, smem, s)
+                     : launch_obs_ring<false>(ring, P, (unsigned)grid, smem, s);
 }

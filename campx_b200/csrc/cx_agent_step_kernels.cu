@@ -1,0 +1,304 @@
+// Single-agent fast path, ONE Engine.play() per launch (cx_step / cx_step_observations): the kernel an on-device
+// policy loop calls once per env-batch step (examples/actor_critic.py:146-173: state = layered_board.float(),
+// action = policy(state), game.play(action)).
+//
+// The fused rollout kernels (cx_agent_kernels.cu, cx_agent_obs_kernels.cu) keep a pre-tiled byte image of their
+// envs' boards in shared memory and patch it step by step; staging that image costs more than the single step it
+// would serve (15 us for one step of 2^20 envs against 5.5 us of HBM traffic).  For T = 1 nothing needs to persist,
+// so this kernel is a stateless COMPOSER over the flat output streams:
+//   phase 1  thread = env: the step itself -- one lookup in the (action, cell) transition table built by
+//            cx_game_create (action dispatch, toroidal move, wall gate against the last render, first-entry
+//            rewards, plot directives: the same table k_agent_rollout uses, so the kernels cannot disagree),
+//            time limit / auto reset / episode statistics, state write-back; the cell where the agent is drawn
+//            afterwards goes to shared memory (one byte per env);
+//   phase 2  the CTA's slice of every output stream is written in 16-byte pieces of the FLAT arrays, a warp store
+//            being one aligned 512-byte run: a piece of the board is the static scene at that phase (a 16-byte row
+//            of the tiling pattern, L1-resident) with the agent byte patched in when it falls inside the piece;
+//            a piece of the layered board (campx/rendering.py:204-215, layers[ch] = board == ord(ch), canonical
+//            channel order) is the static layered image at that phase with at most two patches per env (agent
+//            plane on, the plane of the character it covers off), emitted as uint8, float32 or bfloat16 -- the
+//            float planes ARE the policy input (actor_critic.py:147,173 `layered_board.view(-1).float()`), so no
+//            second pass over HBM converts them.
+// No table staging (tables are a few hundred bytes, read through L1), one block barrier, no tensor cores (nothing
+// here is a contraction).  Envs per CTA are chosen by the launcher so that the grid is a few waves deep at any
+// batch size: 32 envs per CTA for a 4,096-env policy loop (128 CTAs), 1,024 for 2^20 envs.
+#include "cx_agent_common.cuh"
+
+namespace {
+
+struct StepParams {
+  CxAgentHeader h;
+  const uint8_t* blob;
+  uint8_t* cell;
+  uint16_t* tstep;
+  float* ret;
+  double* stats;
+  const uint8_t* actions;  // [n]
+  float* reward;           // [n]
+  float* discount;         // [n] or null
+  uint8_t* flags;          // [n]
+  uint8_t* board;          // [n, cells]
+  void* layered;           // [n, chars, cells] of the LAY element type, or null
+  int64_t n;
+  int32_t envs_per_cta;    // multiple of 32
+};
+
+constexpr int ST_THREADS = 128;
+
+// four consecutive bytes of a table starting at any byte offset: two aligned words and a funnel shift
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* base, uint32_t off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (off >> 2);
+  const uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+  return __funnelshift_r(lo, hi, (off & 3u) * 8u);
+}
+
+// set byte `pos` (0..15) of a 16-byte piece held in four words
+__device__ __forceinline__ void put_byte(uint32_t (&w)[4], uint32_t pos, uint32_t v) {
+  const uint32_t sh = (pos & 3u) * 8u, word = pos >> 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (word == (uint32_t)j) w[j] = (w[j] & ~(0xFFu << sh)) | (v << sh);
+}
+
+// LAY: 0 no layered board, 1 uint8, 2 float32, 4 bfloat16 (the value is the element size except for "none")
+template <bool TRACK, int LAY>
+__global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_constant__ StepParams P) {
+  extern __shared__ __align__(16) uint8_t s_show[];  // [envs_per_cta] cell where the agent is drawn after the step
+  const CxAgentHeader& H = P.h;
+  const int tid = threadIdx.x;
+  const uint32_t cells = H.cells, none = cells;
+  const int E = P.envs_per_cta;
+  const int64_t env0 = (int64_t)blockIdx.x * E;
+  const int nenv = (int)min((int64_t)E, P.n - env0);
+
+  asm volatile("griddepcontrol.launch_dependents;");
+  const uint32_t* __restrict__ g_tt = reinterpret_cast<const uint32_t*>(P.blob + H.off_tt);
+  const float* __restrict__ g_tr = reinterpret_cast<const float*>(P.blob + H.off_tr);
+  const float* __restrict__ g_td = reinterpret_cast<const float*>(P.blob + H.off_td);
+  const uint8_t* __restrict__ g_basech = P.blob + H.off_basech;
+  const uint8_t* __restrict__ g_basek = P.blob + H.off_basek;
+  const uint4* __restrict__ g_pat = reinterpret_cast<const uint4*>(P.blob + H.off_pat);
+  const uint8_t* __restrict__ g_lay = P.blob + H.off_baselay_wrap;
+  const uint32_t stride = H.stride, n_actions = H.n_actions, agent_char = H.agent_char;
+  const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
+  const bool auto_reset = H.auto_reset != 0, want_discount = P.discount != nullptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous step's state and outputs are complete
+
+  // ---- phase 1: the step of every env of this CTA ----
+  LaneStats st;
+  if (TRACK) st.clear();
+  for (int el = tid; el < nenv; el += ST_THREADS) {
+    const int64_t env = env0 + el;
+    const uint32_t cell = min((uint32_t)P.cell[env], none);
+    const uint32_t a = min((uint32_t)P.actions[env], n_actions);
+    const uint32_t idx = a * stride + cell;
+    uint32_t e = __ldg(g_tt + idx);
+    float r = __ldg(g_tr + idx);
+    float dc = want_discount ? __ldg(g_td + a) : 1.0f;
+    uint32_t ts = 0;
+    float rt = 0.0f;
+    if (TRACK) {
+      ts = P.tstep[env];
+      rt = P.ret[env];
+      if (ts & CX_OVER_BIT) {  // auto_reset == 0 and the episode ended: frozen env, board stays as it was drawn
+        e = cell | ((uint32_t)__ldg(P.blob + H.off_shown + cell) << 8) |
+            ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+        r = 0.0f;
+        dc = 0.0f;
+      }
+    }
+    uint32_t p = e & 0xFF;
+    const uint32_t show = (e >> 8) & 0xFF;
+    uint32_t f = e >> 16;
+    if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
+      const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);
+      rt += r;
+      if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
+      ts = steps;
+      if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
+        st.episode(rt, steps);
+        if (auto_reset) {
+          p = H.init_cell;
+          ts = 0;
+          rt = 0.0f;
+        } else {
+          ts |= CX_OVER_BIT;
+        }
+      }
+    }
+    P.cell[env] = (uint8_t)p;
+    if (TRACK) {
+      P.tstep[env] = (uint16_t)ts;
+      P.ret[env] = rt;
+    }
+    P.reward[env] = r;
+    if (want_discount) P.discount[env] = dc;
+    P.flags[env] = (uint8_t)f;
+    s_show[el] = (uint8_t)show;
+  }
+  __syncthreads();  // the only block barrier
+
+  // ---- phase 2a: boards, 16 bytes of the flat [n, cells] array per thread and iteration ----
+  {
+    const uint32_t nbytes = (uint32_t)nenv * cells, nfull = nbytes >> 4;
+    uint8_t* out = P.board + env0 * cells;
+    for (uint32_t k = tid; k < nfull; k += ST_THREADS) {
+      const uint32_t b0 = k << 4, e_lo = b0 / cells, ph = b0 - e_lo * cells;
+      const uint4 v = __ldg(g_pat + ph);  // the static scene from phase `ph` on, 16 bytes (wraps)
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      // last env the piece touches (boards of 16 cells or more: at most the next one)
+      const uint32_t e_hi = min(cells >= 16u ? e_lo + (ph + 15u >= cells ? 1u : 0u) : (b0 + 15u) / cells, (uint32_t)nenv - 1u);
+      for (uint32_t e = e_lo; e <= e_hi; ++e) {
+        const uint32_t sh = s_show[e], pos = e * cells + sh - b0;  // unsigned: a cell before the piece wraps high
+        if (sh != none && pos < 16u) put_byte(w, pos, agent_char);
+      }
+      *reinterpret_cast<uint4*>(out + b0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (uint32_t b = (nfull << 4) + tid; b < nbytes; b += ST_THREADS) {  // ragged tail of the last CTA
+      const uint32_t e = b / cells, c = b - e * cells;
+      out[b] = c == s_show[e] ? (uint8_t)agent_char : __ldg(g_basech + c);
+    }
+  }
+
+  // ---- phase 2b: layered boards, 16 bytes (16 / 4 / 8 elements) of the flat [n, chars, cells] array per piece ----
+  if (LAY != 0) {
+    constexpr uint32_t ES = LAY == 1 ? 1u : (LAY == 2 ? 4u : 2u);  // element size
+    constexpr uint32_t EPC = 16u / ES;                              // elements per 16-byte piece
+    const uint32_t LC = (uint32_t)H.n_chars * cells, agent_off = (uint32_t)H.agent_k * cells;
+    const uint32_t nelem = (uint32_t)nenv * LC, nfull = nelem / EPC;
+    uint8_t* out = static_cast<uint8_t*>(P.layered) + env0 * (int64_t)LC * ES;
+    // byte image of EPC elements starting at flat element i0 (static layered image + the agent's two patches)
+    auto piece = [&](uint32_t i0, uint32_t count, uint32_t (&w)[4]) {
+      const uint32_t e_lo = i0 / LC, rem = i0 - e_lo * LC;
+#pragma unroll
+      for (uint32_t j = 0; j < EPC / 4; ++j) w[j] = ldg_u32_unaligned(g_lay, rem + 4u * j);
+      const uint32_t e_hi = min(LC >= EPC ? e_lo + (rem + count - 1u >= LC ? 1u : 0u) : (i0 + count - 1u) / LC, (uint32_t)nenv - 1u);
+      for (uint32_t e = e_lo; e <= e_hi; ++e) {
+        const uint32_t sh = s_show[e];
+        if (sh == none) continue;
+        const uint32_t at = e * LC + sh - i0;          // + plane offset = position inside the piece (wraps high)
+        const uint32_t kb = __ldg(g_basek + sh);       // plane of the character the agent covers (0xFF: none)
+        const uint32_t off = at + kb * cells, on = at + agent_off;
+        if (kb != 0xFFu && off < EPC) put_byte(w, off, 0u);
+        if (on < EPC) put_byte(w, on, 1u);
+      }
+    };
+    for (uint32_t k = tid; k < nfull; k += ST_THREADS) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      piece(k * EPC, EPC, w);
+      uint4 v;
+      if (LAY == 1) {
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      } else if (LAY == 2) {  // 4 bytes -> 4 floats (0.0f / 1.0f)
+        v = make_uint4((w[0] & 1u) * 0x3F800000u, ((w[0] >> 8) & 1u) * 0x3F800000u,
+                       ((w[0] >> 16) & 1u) * 0x3F800000u, (w[0] >> 24) * 0x3F800000u);
+      } else {                // 8 bytes -> 8 bfloat16 (0x0000 / 0x3F80)
+        v = make_uint4(((w[0] & 1u) | ((w[0] << 8) & 0x10000u)) * 0x3F80u,
+                       (((w[0] >> 16) & 1u) | ((w[0] >> 8) & 0x10000u)) * 0x3F80u,
+                       ((w[1] & 1u) | ((w[1] << 8) & 0x10000u)) * 0x3F80u,
+                       (((w[1] >> 16) & 1u) | ((w[1] >> 8) & 0x10000u)) * 0x3F80u);
+      }
+      *reinterpret_cast<uint4*>(out + (size_t)k * 16u) = v;
+    }
+    for (uint32_t i = nfull * EPC + tid; i < nelem; i += ST_THREADS) {  // ragged tail of the last CTA
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      piece(i, 1u, w);
+      const uint32_t b = w[0] & 1u;
+      if (LAY == 1)
+        out[i] = (uint8_t)b;
+      else if (LAY == 2)
+        reinterpret_cast<uint32_t*>(out)[i] = b * 0x3F800000u;
+      else
+        reinterpret_cast<uint16_t*>(out)[i] = (uint16_t)(b * 0x3F80u);
+    }
+  }
+
+  if (TRACK) {
+    const double cnt = warp_sum((double)st.cnt);
+    if (cnt > 0.0) {  // warp-uniform: rare (an episode ended in this warp's envs)
+      const double len = warp_sum((double)st.len), sum = warp_sum(st.sum), sumsq = warp_sum(st.sumsq);
+      const float mx = warp_max(st.mx), ngmn = warp_max(st.negmn);
+      if ((tid & 31) == 0) {
+        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
+        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)P.n);
+  }
+}
+
+template <bool TRACK, int LAY>
+int launch_step(const StepParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ST_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_step_flat<TRACK, LAY>, P));
+  return CX_OK;
+}
+
+template <bool TRACK>
+int launch_step_lay(int lay, const StepParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+  switch (lay) {
+    case 0: return launch_step<TRACK, 0>(P, grid, smem, s);
+    case 1: return launch_step<TRACK, 1>(P, grid, smem, s);
+    case 2: return launch_step<TRACK, 2>(P, grid, smem, s);
+    default: return launch_step<TRACK, 4>(P, grid, smem, s);
+  }
+}
+
+}  // namespace
+
+// The composer writes whole 16-byte pieces: every output array must start 16-byte aligned (CTA slices then do too,
+// because a CTA owns a multiple of 32 envs).  Callers fall back to the tile kernels otherwise.
+bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_layered) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return g->path == CX_PATH_AGENT && al16(d_board) && al16(d_layered);
+}
+
+int cx_launch_agent_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
+                         float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* d_layered, int lay_dtype,
+                         cudaStream_t s) {
+  const CxStateLayout L = cx_layout(g, n);
+  uint8_t* base = static_cast<uint8_t*>(d_state);
+  StepParams P;
+  P.h = g->ah;
+  P.blob = g->d_blob;
+  P.cell = base + L.off_dyn;
+  P.tstep = reinterpret_cast<uint16_t*>(base + L.off_tstep);
+  P.ret = reinterpret_cast<float*>(base + L.off_ret);
+  P.stats = reinterpret_cast<double*>(base + L.off_stats);
+  P.actions = d_actions;
+  P.reward = d_reward;
+  P.discount = d_discount;
+  P.flags = d_flags;
+  P.board = d_board;
+  P.layered = d_layered;
+  P.n = n;
+  // envs per CTA: a multiple of 32 that makes the grid about four CTAs per SM deep, at most 1,024 (2^20 envs: one
+  // resident wave of 1,024 CTAs), at least 32 (a 4,096-env policy loop still spreads over 128 CTAs)
+  int64_t per = (n + (int64_t)g->sm_count * 4 - 1) / ((int64_t)g->sm_count * 4);
+  per = (per + 31) / 32 * 32;
+  if (per < 32) per = 32;
+  if (per > 1024) per = 1024;
+  P.envs_per_cta = (int32_t)per;
+  const int64_t grid = (n + per - 1) / per;
+  if (grid > 0x7fffffff) {
+    cx_set_error("cx_step: too many environments for one launch");
+    return CX_ERR_INVALID_ARG;
+  }
+  const int lay = d_layered ? (lay_dtype == CX_DTYPE_U8 ? 1 : (lay_dtype == CX_DTYPE_F32 ? 2 : 4)) : 0;
+  const size_t smem = (size_t)per;
+  return g->ah.track ? launch_step_lay<true>(lay, P, (unsigned)grid, smem, s)
+                     : launch_step_lay<false>(lay, P, (unsigned)grid, smem, s);
+}

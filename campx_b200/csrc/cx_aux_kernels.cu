@@ -432,6 +432,44 @@ __global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, 
   out[i] = (uint8_t)cx_synth_action(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t, (uint32_t)A);
 }
 
+// examples/actor_critic.py:90-98: `m = Categorical(probs); action = m.sample()`.  Inverse-CDF sampling, one thread
+// per env: u from the counter-based Philox stream (reproducible per (seed, env, step), independent of the launch
+// geometry), the first action whose cumulative weight exceeds u * total.  With logits the weights are
+// exp(l - max l) -- the softmax the policy head would otherwise run as its own kernel.
+__global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, int A, int is_logits, uint64_t seed,
+                                 uint64_t env_offset, const uint64_t* __restrict__ d_step, uint64_t step_offset,
+                                 uint8_t* __restrict__ actions, float* __restrict__ logp) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  float w[CX_MAX_ACTIONS];
+  float mx = -INFINITY;
+  for (int a = 0; a < A; ++a) {
+    w[a] = scores[i * A + a];
+    mx = fmaxf(mx, w[a]);
+  }
+  float total = 0.0f;
+  for (int a = 0; a < A; ++a) {
+    if (is_logits) w[a] = __expf(w[a] - mx);
+    w[a] = w[a] > 0.0f ? w[a] : 0.0f;   // negative / NaN weights count as zero
+    total += w[a];
+  }
+  const uint64_t g = env_offset + (uint64_t)i, step = (d_step ? *d_step : 0ull) + step_offset;
+  const CxPhilox4 p = cx_philox4(seed ^ 0x5A4D504C45ull, g >> 2, step);   // a stream apart from cx_fill_actions
+  const float u = (float)(p.w[g & 3] >> 8) * (1.0f / 16777216.0f) * total;   // [0, total)
+  int pick = A - 1;
+  float cum = 0.0f;
+  for (int a = 0; a < A; ++a) {
+    cum += w[a];
+    if (u < cum) {
+      pick = a;
+      break;
+    }
+  }
+  while (pick > 0 && !(w[pick] > 0.0f)) --pick;   // rounding at the top end must not select a zero-weight action
+  actions[i] = (uint8_t)pick;
+  if (logp) logp[i] = __logf(w[pick] / total);
+}
+
 // examples/actor_critic.py:119-122: `R = r + gamma * R` backwards; one thread per env, coalesced over envs
 __global__ void k_discounted_returns(const float* __restrict__ reward, const float* __restrict__ discount,
                                      const uint8_t* __restrict__ flags, const float* __restrict__ bootstrap, int T,
@@ -612,6 +650,19 @@ extern "C" int cx_onehot_to_index(const float* d_onehot, int64_t n, int32_t A, u
     return CX_ERR_INVALID_ARG;
   }
   k_onehot_to_index<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_onehot, A, d_index, d_bad, n);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_sample_actions(const float* d_scores, int64_t n, int32_t A, int32_t is_logits, uint64_t seed,
+                                 uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, uint8_t* d_actions,
+                                 float* d_logp, void* stream) {
+  if (!d_scores || !d_actions || n < 1 || A < 1 || A > CX_MAX_ACTIONS) {
+    cx_set_error("cx_sample_actions: bad argument (n_actions must be in 1..%d)", CX_MAX_ACTIONS);
+    return CX_ERR_INVALID_ARG;
+  }
+  k_sample_actions<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_scores, n, A, is_logits, seed, env_offset, d_step,
+                                                                   step_offset, d_actions, d_logp);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

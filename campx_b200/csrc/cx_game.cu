@@ -438,6 +438,10 @@ static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* or
   }
   B->pad();
   H->blob_bytes_ext = (int32_t)B->bytes.size();
+  H->off_baselay_wrap = B->reserve((size_t)L * cells + 24);
+  for (int i = 0; i < L * cells + 24; ++i)
+    B->bytes[H->off_baselay_wrap + i] = B->bytes[H->off_baselay + i % (L * cells)];
+  B->pad();
 }
 
 static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHeader* H, Blob* B) {
@@ -906,6 +910,12 @@ extern "C" int cx_render(const cx_game* g, const void* d_state, int64_t n, uint8
   return cx_launch_render(g, d_state, n, d_board, (cudaStream_t)stream);
 }
 
+// CX_AGENT_STEP_FLAT=0 (development knob) sends single steps through the tile kernels again
+static bool step_composer_enabled() {
+  const char* e = getenv("CX_AGENT_STEP_FLAT");   // read per call: tests flip it to compare the two routes
+  return !(e && atoi(e) == 0);
+}
+
 static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                           const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                           uint8_t* d_board, void* stream, const char* who) {
@@ -923,6 +933,10 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     cx_set_error("%s: env_offset must be a multiple of 4", who);
     return CX_ERR_INVALID_ARG;
   }
+  if (g->path == CX_PATH_AGENT && T == 1 && !synth.on && step_composer_enabled() &&
+      cx_agent_step_applies(g, d_board, nullptr))   // one step: the stateless composer (cx_agent_step_kernels.cu)
+    return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, nullptr, CX_DTYPE_U8,
+                                (cudaStream_t)stream);
   if (g->path == CX_PATH_AGENT) {
     // k_agent_rollout gives every warp 256 envs: below half a wave of its 1,024-env CTAs (7 per SM) the batch is
     // bound by the per-warp step latency, and the lane-per-env kernel (32 envs per warp, 8x the warps) is faster --
@@ -969,6 +983,13 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
     cx_set_error("cx_rollout_observations: layered must not be NULL");
     return CX_ERR_INVALID_ARG;
   }
+  if (g && d_actions && d_reward && d_flags && d_board && T == 1 && step_composer_enabled() &&
+      cx_agent_step_applies(g, d_board, d_layered)) {
+    int rc = check_common(g, d_state, n, "cx_rollout_observations");
+    if (rc) return rc;
+    return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, d_layered,
+                                CX_DTYPE_U8, (cudaStream_t)stream);
+  }
   if (g && d_actions && d_reward && d_flags && d_board && T >= 1 && cx_agent_obs_applies(g, true)) {
     int rc = check_common(g, d_state, n, "cx_rollout_observations");
     if (rc) return rc;
@@ -986,6 +1007,35 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
 extern "C" int cx_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
                        float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
   return cx_rollout(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board, stream);
+}
+
+extern "C" int cx_step_observations(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions,
+                                    float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board,
+                                    void* d_layered, int32_t dtype, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_step_observations");
+  if (rc) return rc;
+  if (!d_actions || !d_reward || !d_flags || !d_board || !d_layered) {
+    cx_set_error("cx_step_observations: actions/reward/flags/board/layered must not be NULL");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (dtype != CX_DTYPE_U8 && dtype != CX_DTYPE_F32 && dtype != CX_DTYPE_BF16) {
+    cx_set_error("cx_step_observations: unknown layered_dtype %d", dtype);
+    return CX_ERR_INVALID_ARG;
+  }
+  if (step_composer_enabled() && cx_agent_step_applies(g, d_board, d_layered))
+    return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, d_layered, dtype,
+                                (cudaStream_t)stream);
+  if (dtype == CX_DTYPE_U8)
+    return cx_rollout_observations(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board,
+                                   static_cast<uint8_t*>(d_layered), stream);
+  if (dtype == CX_DTYPE_BF16) {
+    cx_set_error("cx_step_observations: bfloat16 planes are emitted by the single-agent step kernel only "
+                 "(16-byte aligned buffers); use CX_DTYPE_F32 for this game");
+    return CX_ERR_UNSUPPORTED;
+  }
+  rc = cx_rollout(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board, stream);
+  if (rc) return rc;
+  return cx_layers_from_board_f32(g, d_board, n, static_cast<float*>(d_layered), stream);
 }
 
 extern "C" int cx_get_entity_state(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_cells,

@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(BLK, OCC) k_generic_rollout(const __grid_const
           generic_env_step(X, a, dyn[lane], W.prev[lane], plane + lane * cells, rw, f, dc);
       }
       if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
-        const uint32_t steps = ts + 1u;
+        const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);   // 15-bit counter saturates (bit 15 = OVER)
         rt += rw;
         if (!(f & CX_FLAG_TERMINATED) && H.max_steps > 0 && steps >= (uint32_t)H.max_steps) f |= CX_FLAG_TRUNCATED;
         ts = steps;

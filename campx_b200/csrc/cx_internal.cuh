@@ -12,6 +12,8 @@
 
 #define CX_EMPTY_CELL16 0xFFFFu  // generic path
 #define CX_OVER_BIT 0x8000u      // in the per-env step counter: episode ended and auto_reset == 0
+#define CX_STEP_MAX 0x7FFFu      // the counter proper saturates here (15 bits): an episode without a time limit that
+                                 // runs longer keeps stepping, its reported length stops at 32,767
 
 #define CX_AGENT_TILE_MAX_CELLS 96  // k_agent_rollout: warp tile of 256 envs * cells bytes must fit shared memory
 #define CX_AGENT_MAX_CELLS 254      // single-agent path: cells and "no cell" must fit a byte; boards above
@@ -60,6 +62,9 @@ struct CxAgentHeader {
   int32_t off_basek;        // u8  [cells+1]  channel of basech[c] (0xFF: not a game character)
   int32_t off_baselay;      // u8  [n_chars][cells]  layered board of the static scene (no agent)
   int32_t blob_bytes_ext;   // blob_bytes + the extension
+  // read through L1 by the single-step composer (k_agent_step_flat), never staged:
+  int32_t off_baselay_wrap; // u8  [n_chars * cells + 24]  baselay followed by its own first 24 bytes, so that a
+                            //     16-byte piece may start at any phase of the per-env layered image
   CxActionTable act;        // host copy
 };
 
@@ -194,6 +199,11 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
                                 const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                                 uint8_t* d_board, uint8_t* d_layered /* or null */, cudaStream_t s);
 bool cx_agent_obs_applies(const cx_game* g, bool layers);
+// one Engine.play() per launch, stateless composer (cx_agent_step_kernels.cu); lay_dtype: CX_DTYPE_* of d_layered
+bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_layered);
+int cx_launch_agent_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
+                         float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* d_layered, int lay_dtype,
+                         cudaStream_t s);
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                               uint8_t* d_board, cudaStream_t s);

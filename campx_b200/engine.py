@@ -208,15 +208,26 @@ class Engine(object):
         # together) instead of a step kernel plus `cx_layers_from_board`; a caller that only reads boards never
         # pays for the layers (they stay lazy).  Same values either way.
         last = self._last_obs
-        if self._batched and self.fused_observation_steps and last is not None and last.layers_were_read:
+        want = last.read_dtype if (self._batched and self.fused_observation_steps and last is not None) else None
+        if want is not None and want not in (torch.uint8, torch.float32) and not (
+                want == torch.bfloat16 and nat.info.path == N.CX_PATH_AGENT):
+            want = None                 # a dtype the step kernel does not emit for this game: stays lazy
+        if want is not None:
+            # board and layered board (uint8, or float32 / bfloat16 planes: the policy input of
+            # examples/actor_critic.py:147,173) leave the step kernel together: cx_step_observations
             if self._layered_sets is None:
+                self._layered_sets = {}
+            key = (want, self._out_index)
+            if key not in self._layered_sets:
                 shape = (self._num_envs, nat.n_chars, self._rows, self._cols)
-                self._layered_sets = [torch.empty(shape, dtype=torch.uint8, device=nat.device) for _ in self._out_sets]
-            layered = self._layered_sets[self._out_index]
-            nat.rollout_observations(idx.unsqueeze(0), self._out_board.unsqueeze(0), layered.unsqueeze(0),
-                                     self._out_reward.unsqueeze(0), self._out_flags.unsqueeze(0),
-                                     None if self._out_discount is None else self._out_discount.unsqueeze(0))
-            obs = self._observation(self._out_board, layered)
+                self._layered_sets[key] = torch.empty(shape, dtype=want, device=nat.device)
+            layered = self._layered_sets[key]
+            nat.step_observations(idx, self._out_board, layered, self._out_reward, self._out_flags, self._out_discount)
+            if want == torch.uint8:
+                obs = self._observation(self._out_board, layered)
+            else:
+                obs = self._observation(self._out_board)
+                obs._planes[want] = layered
         else:
             nat.step(idx, self._out_board, self._out_reward, self._out_flags, self._out_discount)
             obs = self._observation(self._out_board)

@@ -52,11 +52,14 @@ class Observation(object):
         self._layer_fn = layer_fn
         self._layered = layered_board
         self._layers = None
+        self._planes = {}               # dtype -> layered board in that dtype (pre-filled by the fused step kernel)
         self.layers_were_read = False   # Engine.play() emits whole Observations for callers that read the layers
+        self.read_dtype = None          # dtype of the layered board the caller asked for last
 
     @property
     def layered_board(self):
         self.layers_were_read = True
+        self.read_dtype = torch.uint8
         if self._layered is None:
             self._layered = self._layer_fn(self.board)
         return self._layered
@@ -71,7 +74,10 @@ class Observation(object):
         """layered_board in another dtype straight from the board (float32: policy input)."""
         if dtype == torch.uint8:
             return self.layered_board
-        return self._layer_fn(self.board, dtype)
+        self.read_dtype = dtype
+        if dtype not in self._planes:
+            self._planes[dtype] = self._layer_fn(self.board, dtype)
+        return self._planes[dtype]
 
     def __iter__(self):
         yield self.board

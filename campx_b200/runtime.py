@@ -141,6 +141,50 @@ class NativeGame(object):
                                                       _ptr(reward), _ptr(discount), _ptr(flags), _ptr(board),
                                                       _ptr(layered), _stream()))
 
+    _DTYPES = {torch.uint8: N.CX_DTYPE_U8, torch.float32: N.CX_DTYPE_F32, torch.bfloat16: N.CX_DTYPE_BF16}
+
+    def step_observations(self, actions, board, layered, reward, flags, discount=None):
+        """One play() that also writes the layered board [n, n_chars, rows, cols] as uint8, float32 or bfloat16
+        (the policy input of examples/actor_critic.py:147,173) from the step kernel itself."""
+        n = self.num_envs
+        self._check(actions, torch.uint8, (n,), "actions")
+        self._check(board, torch.uint8, (n, self.rows, self.cols), "board")
+        if not isinstance(layered, torch.Tensor) or layered.dtype not in self._DTYPES:
+            raise ValueError("layered must be a uint8, float32 or bfloat16 tensor")
+        if layered.numel() != n * self.n_chars * self.cells:
+            raise ValueError("layered must hold %d x %d x %d elements (got shape %s)"
+                             % (n, self.n_chars, self.cells, tuple(layered.shape)))
+        self._check(layered, layered.dtype, tuple(layered.shape), "layered")
+        self._check(reward, torch.float32, (n,), "reward")
+        self._check(flags, torch.uint8, (n,), "flags")
+        if discount is not None:
+            self._check(discount, torch.float32, (n,), "discount")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_step_observations(self._handle, _ptr(self.state), n, _ptr(actions), _ptr(reward),
+                                                   _ptr(discount), _ptr(flags), _ptr(board), _ptr(layered),
+                                                   self._DTYPES[layered.dtype], _stream()))
+
+    def sample_actions(self, scores, seed, step=None, step_offset=0, logits=False, env_offset=0, out=None, logp=None):
+        """Categorical(probs).sample() for every env (examples/actor_critic.py:90-98) -> uint8 [n] action indices.
+
+        scores: float32 [n, n_actions] probabilities (or logits with logits=True).  The uniform numbers come from
+        the Philox stream (seed; env_offset + env, step), step = step[0] + step_offset where `step` is an optional
+        int64 device tensor -- a captured CUDA graph advances it between replays."""
+        n = self.num_envs
+        self._check(scores, torch.float32, (n, self.n_actions), "scores")
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(out, torch.uint8, (n,), "actions")
+        if step is not None:
+            self._check(step, torch.int64, (1,), "step")
+        if logp is not None:
+            self._check(logp, torch.float32, (n,), "logp")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_sample_actions(_ptr(scores), n, self.n_actions, 1 if logits else 0, int(seed),
+                                                int(env_offset), _ptr(step), int(step_offset), _ptr(out), _ptr(logp),
+                                                _stream()))
+        return out
+
     def rollout_synth(self, n_steps, seed, board, reward, flags, discount=None, env_offset=0, t0=0, actions_out=None):
         """Fused rollout with uniform random actions generated inside the kernel (no action bytes read);
         identical to fill_actions(seed, env_offset, t0) + rollout."""

@@ -5,7 +5,7 @@ The reference's examples/actor_critic.py steps ONE environment on the CPU, build
 episode and runs its policy once per step.  Here 4,096 environments step together:
 
   state   = layered_board as float32 [N, 7*5*5=175]  (actor_critic.py:147,173 `layered_board.view(-1).float()`)
-            written by cx_layers_from_board_f32 straight from the step kernel's board
+            written by the step kernel itself (cx_step_observations), next to the board
   policy  = Linear(175,32) -> ReLU -> {Linear(32,5) softmax, Linear(32,1)}   (actor_critic.py:64-86)
   action  ~ Categorical(probs)                                                (actor_critic.py:90-98)
   step    = Engine.play(action indices)            one cx_step launch, time limit 100 + auto reset
@@ -39,6 +39,10 @@ class Policy(nn.Module):
     def forward(self, x):
         x = F.relu(self.affine1(x))
         return F.softmax(self.action_head(x), dim=-1), self.value_head(x).squeeze(-1)
+
+    def action_logits(self, x):
+        """The acting half only (no value head, no softmax): what a rollout step needs."""
+        return self.action_head(F.relu(self.affine1(x)))
 
 
 def run(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, log=print, device="cuda"):
@@ -81,46 +85,55 @@ def run(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, l
 
 
 class GraphedRollout(object):
-    """One T-step rollout (observation encoding -> policy -> sample -> Engine.play, T times) captured ONCE as a
-    CUDA graph and replayed per iteration: ~8 kernel launches per env-batch step collapse into one graph
-    launch, which is what a launch-bound inner loop at 4,096 environments needs on a B200.
+    """One T-step rollout (policy -> sample -> Engine.play, T times) captured ONCE as a CUDA graph and replayed
+    per iteration.  A 4,096-env step is launch-bound on a B200 (it moves 3 MB), so the loop is built from as few
+    launches as the reference's data flow allows -- five per env-batch step:
+
+        Linear(175,32)  ReLU  Linear(32,5)        the policy's action logits (ordinary torch)
+        cx_sample_actions                         softmax + Categorical.sample() in one kernel (actor_critic.py:90-98)
+        cx_step_observations                      Engine.play() that writes the NEXT policy input -- the layered
+                                                  board as float32 planes (actor_critic.py:147,173) -- together with
+                                                  board, reward and flags, straight into the rollout buffers
 
     The rollout runs under no_grad into static buffers (states, actions, rewards, flags); the learner then
     re-evaluates the policy on all T*N states in one batched forward pass (the usual A2C/PPO split).
     """
 
-    def __init__(self, game, policy, steps):
-        self.game, self.policy, self.T = game, policy, int(steps)
+    def __init__(self, game, policy, steps, seed=543):
+        self.game, self.policy, self.T, self.seed = game, policy, int(steps), int(seed)
         nat = game.native
         n, dev = game.num_envs, nat.device
         self.feat = nat.n_chars * nat.cells
-        self.states = torch.empty((self.T, n, self.feat), dtype=torch.float32, device=dev)
+        self._states = torch.empty((self.T + 1, n, self.feat), dtype=torch.float32, device=dev)
         self.actions = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self.rewards = torch.empty((self.T, n), dtype=torch.float32, device=dev)
         self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
+        self.board = torch.empty((n, nat.rows, nat.cols), dtype=torch.uint8, device=dev)
         self.all_envs = torch.ones(n, dtype=torch.uint8, device=dev)
-        self.board = game.reset(self.all_envs).board.clone()   # board the next rollout starts from
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)      # Philox step counter, advanced inside the graph
+        # every rollout starts from the its_showtime frame: its planes are the same for every env and rollout
+        first = game.reset(self.all_envs)
+        self._states[0].copy_(first.layered_board_as(torch.float32).view(n, -1))
         self.graph = None
-        self.step_kernel = "cx_layers_from_board_f32 + cx_step"
-        self.kernels_per_step = None
+        self.step_kernel = "cx_step_observations (k_agent_step_flat: board + float32 planes + reward + flags)"
+        self.kernels_per_step = 5
+
+    @property
+    def states(self):
+        """float32 [T, N, L*R*C]: states[t] is what the policy saw before action t."""
+        return self._states[:self.T]
 
     def _body(self):
         nat, game, n = self.game.native, self.game, self.game.num_envs
-        board = self.board
         with torch.no_grad():
             for t in range(self.T):
-                nat.layers_from_board(board, out=self.states[t].view(n, nat.n_chars, nat.rows, nat.cols),
-                                      dtype=torch.float32)
-                probs, _ = self.policy(self.states[t])
-                action = torch.multinomial(probs, 1).squeeze(1)
-                self.actions[t].copy_(action)
-                obs, reward, _ = game.play(self.actions[t])
-                self.rewards[t].copy_(reward)
-                self.flags[t].copy_(game.flags)
-                board = obs.board
+                logits = self.policy.action_logits(self._states[t])
+                nat.sample_actions(logits, self.seed, step=self.step, step_offset=t, logits=True, out=self.actions[t])
+                nat.step_observations(self.actions[t], self.board, self._states[t + 1], self.rewards[t], self.flags[t])
+            self.step.add_(self.T)
             # a fresh episode for every env, like the reference's make_game() per episode (actor_critic.py:146):
-            # the next rollout's first state is the its_showtime frame (a masked reset keeps the statistics)
-            self.board.copy_(game.reset(self.all_envs).board)
+            # a masked reset keeps the episode statistics
+            nat.reset(self.all_envs)
 
     def capture(self):
         side = torch.cuda.Stream()

@@ -21,6 +21,10 @@
  *                                          layered_board)                   campx/rendering.py:29,181-219
  *   cx_board_mapper_create/apply/destroy <- ObservationToArray (RGB / value rendering) and
  *                                          ObservationToFeatureArray        campx/rendering.py:461-594,597-712
+ *   cx_step_observations               <-  Engine.play() feeding a policy: the layered board as uint8, float32 or
+ *                                          bfloat16 planes straight from the step kernel
+ *                                          examples/actor_critic.py:147,173 (`layered_board.view(-1).float()`)
+ *   cx_sample_actions                  <-  Categorical(probs).sample()      examples/actor_critic.py:90-98
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
  *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
@@ -54,7 +58,7 @@ extern "C" {
 #define CX_API
 #endif
 
-#define CX_ABI_VERSION 2
+#define CX_ABI_VERSION 3
 
 #define CX_MAX_ENTITIES 16   /* sprites + drapes in one game                         */
 #define CX_MAX_ACTIONS 8     /* discrete actions                                     */
@@ -234,6 +238,23 @@ CX_API int cx_rollout_observations(const cx_game* game, void* d_state, int64_t n
                             const uint8_t* d_actions, float* d_reward, float* d_discount, uint8_t* d_flags,
                             uint8_t* d_board, uint8_t* d_layered, void* stream);
 
+/* Element type of a layered board written by cx_step_observations. */
+typedef enum cx_dtype {
+  CX_DTYPE_U8 = 0,   /* the reference's layers dtype (rendering.py:204-209)                        */
+  CX_DTYPE_F32 = 1,  /* `layered_board.float()`: the policy input of examples/actor_critic.py:147  */
+  CX_DTYPE_BF16 = 2  /* the same planes for a bf16 policy network                                  */
+} cx_dtype;
+
+/* One Engine.play() for every env that also writes the layered board (the whole Observation of
+ * campx/rendering.py:29,181-219) in the element type the consumer wants:
+ *   d_layered [n, n_chars, rows*cols] of `layered_dtype` (cx_dtype), channel k = (board == chars[k]) as 0 / 1.
+ * All other arguments as cx_step.  Single-agent games emit board and planes from ONE launch (a stateless composer
+ * over the flat output arrays: no board re-read, no conversion pass); every other game runs cx_step followed by
+ * cx_layers_from_board[_f32] (CX_DTYPE_BF16 is then CX_ERR_UNSUPPORTED).  Results are identical either way. */
+CX_API int cx_step_observations(const cx_game* game, void* d_state, int64_t n_envs, const uint8_t* d_actions,
+                         float* d_reward, float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* d_layered,
+                         int32_t layered_dtype, void* stream);
+
 /* layers / layered_board from finished boards (rendering.py:204-215): d_layered [n, n_chars, cells]
  * with channel k = (board == chars[k]).  n_boards may be T*n for rollout buffers. */
 CX_API int cx_layers_from_board(const cx_game* game, const uint8_t* d_board, int64_t n_boards, uint8_t* d_layered,
@@ -261,6 +282,16 @@ CX_API int cx_board_mapper_apply(const cx_board_mapper* mapper, const uint8_t* d
  * exactly one-hot (boat_race.py:48 `assert sum(act) == 1`) set *d_bad_count (int32, device) += 1. */
 CX_API int cx_onehot_to_index(const float* d_onehot, int64_t n_envs, int32_t n_actions, uint8_t* d_index,
                        int32_t* d_bad_count, void* stream);
+
+/* Sample one action per env from a categorical distribution (Categorical(probs).sample(), actor_critic.py:90-98):
+ *   d_scores [n, n_actions] float32 -- probabilities (is_logits = 0; they need not be normalised) or logits
+ *   (is_logits = 1: softmax is applied inside, so the policy head needs no softmax kernel);
+ *   u = uniform(0,1) from Philox4x32-10 keyed (seed; counter = env_offset + i, step), step = *d_step (a device
+ *   uint64, may be NULL = 0) + step_offset -- a CUDA graph that replays this call advances *d_step between replays;
+ *   action = first a with cumulative probability > u.  d_logp [n] (may be NULL) receives log p(action). */
+CX_API int cx_sample_actions(const float* d_scores, int64_t n_envs, int32_t n_actions, int32_t is_logits, uint64_t seed,
+                      uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, uint8_t* d_actions,
+                      float* d_logp, void* stream);
 
 /* Synthetic uniform actions from counter-based Philox4x32-10: with g = env_offset + i (global env id),
  *   out[t, i] = mulhi(philox(key = seed, counter = (g >> 2, t0 + t))[g & 3], n_actions). */
