@@ -65,6 +65,8 @@ class EntityDesc(ctypes.Structure):
         ("step_reward", ctypes.c_float * CX_MAX_ACTIONS),
         ("entry_reward", (ctypes.c_float * CX_MAX_CHARS) * CX_MAX_ACTIONS),
         ("discount_value", ctypes.c_float * CX_MAX_ACTIONS),
+        ("terminate_chars", ctypes.c_uint32 * CX_MAX_ACTIONS),
+        ("terminate_value", ctypes.c_float * CX_MAX_ACTIONS),
         ("visible_op", ctypes.c_uint8 * CX_MAX_ACTIONS),
         ("n_zdirs", ctypes.c_uint8 * CX_MAX_ACTIONS),
         ("z_move", (ctypes.c_int8 * CX_MAX_ZDIRS) * CX_MAX_ACTIONS),
@@ -92,6 +94,7 @@ class GameDesc(ctypes.Structure):
         ("first_discount", ctypes.c_float),
         ("backdrop_dr", ctypes.c_int8 * CX_MAX_ACTIONS),
         ("backdrop_dc", ctypes.c_int8 * CX_MAX_ACTIONS),
+        ("unoccluded_layers", ctypes.c_int32),
     ]
 
 
@@ -121,6 +124,7 @@ PROTOTYPES = {
     "cx_rollout": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "cx_rollout_synth": (ctypes.c_int, [_P, _P, _I64, _I32, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P]),
     "cx_rollout_observations": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "cx_render_observations": (ctypes.c_int, [_P, _P, _I64, _P, _P, _I32, _P]),
     "cx_step_observations": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "cx_sample_actions": (ctypes.c_int, [_P, _I64, _I32, _I32, _U64, _U64, _P, _U64, _P, _P, _P]),
     "cx_layers_from_board": (ctypes.c_int, [_P, _P, _I64, _P, _P]),

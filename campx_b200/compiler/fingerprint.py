@@ -6,6 +6,8 @@ Why fingerprinting: CampX game rules are arbitrary Python in `update()` methods 
 -- they cannot be traced or vmapped.  Instead each entity is observed on a single-env CPU shadow
 (shadow.py) under a set of probes, fitted to a primitive, and the fit is checked on EVERY probe;
 anything that does not fit raises `CompileError` (a NotImplementedError): there is no fallback.
+Entities that keep state of their own (a step counter, a visited set, an RNG) are detected by comparing
+their instance attributes and the Plot's non-tensor entries before and after every probe, and refused.
 
 Probe set
   * every action from the post-its_showtime state;
@@ -20,7 +22,8 @@ Probe set
 Fitted per entity (see include/campx_b200.h `cx_entity_desc`)
   kind, per-action toroidal move, blocker characters (one-cell drapes), per-action step reward,
   "entry" reward as a function of (action, character the last render showed at a watched entity's
-  current cell), terminate / default-discount directives per action, per-action visibility
+  current cell), terminate directives per action or per (action, character under the watched entity)
+  ("reach the goal"), default-discount directives per action, per-action visibility
   operation (sprites), per-action `change_z_order` calls; per game: the backdrop's per-action roll.
 """
 import collections
@@ -70,7 +73,48 @@ def _snapshot(shadow):
 
 class _Probe(object):
     __slots__ = ("action", "teleports", "pre", "post", "group_board", "after", "events", "reward", "discount",
-                 "game_over", "backdrop_pre", "backdrop_post", "z_post")
+                 "game_over", "backdrop_pre", "backdrop_post", "z_post", "hidden")
+
+
+# attributes that ARE the modelled state of an entity (things.py:25-26,44-45,66-69) or compile-time plumbing
+_MODELLED = frozenset(("_curtain", "_palette", "_character", "_corner", "_position", "_visible", "update"))
+
+
+def _freeze(value):
+    """A comparable rendering of an attribute value; None for values that cannot be compared reliably."""
+    if torch.is_tensor(value):
+        t = value.as_subclass(torch.Tensor).detach()
+        return ("tensor", tuple(t.shape), str(t.dtype), t.cpu().numpy().tobytes())
+    if isinstance(value, np.ndarray):
+        return ("array", value.shape, str(value.dtype), value.tobytes())
+    if isinstance(value, (bool, int, float, complex, str, bytes, type(None), np.generic)):
+        return ("scalar", type(value).__name__, value if value == value else "nan")
+    if isinstance(value, (list, tuple)):
+        parts = tuple(_freeze(v) for v in value)
+        return None if any(x is None for x in parts) else (type(value).__name__, parts)
+    if isinstance(value, (set, frozenset)):
+        parts = [_freeze(v) for v in value]
+        return None if any(x is None for x in parts) else ("set", tuple(sorted(map(repr, parts))))
+    if isinstance(value, dict):
+        parts = {repr(k): _freeze(v) for k, v in value.items()}
+        return None if any(x is None for x in parts.values()) else ("dict", tuple(sorted(parts.items())))
+    return None
+
+
+def _hidden_state(shadow):
+    """Everything an entity (or the Plot) remembers besides the state the primitives model: instance attributes
+    other than curtain / position / visibility, and non-tensor Plot entries (tensor entries are the usual aliases of
+    renderer layers, examples/boat_race.py:59,91 -- functions of the last render, which IS modelled)."""
+    out = {}
+    ents = list(shadow.things.items()) + [("<backdrop>", shadow.backdrop)]
+    for ch, ent in ents:
+        for name, value in vars(ent).items():
+            if name not in _MODELLED:
+                out[(ch, name)] = _freeze(value)
+    for key, value in shadow.the_plot.items():
+        if not torch.is_tensor(value):
+            out[("<plot>", repr(key))] = _freeze(value)
+    return out
 
 
 BACKDROP = "__backdrop__"          # teleport key: pre-roll the backdrop curtain by (d_row, d_col)
@@ -108,6 +152,7 @@ def run_probe(base, base_masks, fmt, n_actions, action, teleports):
     p = _Probe()
     p.action, p.teleports = action, dict(teleports)
     p.pre = _snapshot(s)
+    hidden_pre = _hidden_state(s)
     p.backdrop_pre = s.backdrop.curtain.as_subclass(torch.Tensor).numpy().copy()
     p.group_board, p.after = {}, {}
 
@@ -133,6 +178,9 @@ def run_probe(base, base_masks, fmt, n_actions, action, teleports):
         for ent in hooked:
             del ent.update
     p.game_over = s.game_over
+    hidden_post = _hidden_state(s)
+    p.hidden = sorted(k for k in set(hidden_pre) | set(hidden_post)
+                      if hidden_pre.get(k, ("absent",)) != hidden_post.get(k, ("absent",)))
     p.events = collections.defaultdict(list)
     for who, kind, payload in s.the_plot.events:
         p.events[who].append((kind, payload))
@@ -167,7 +215,7 @@ def _find_roll(before, after):
 
 
 def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, auto_reset=True,
-                 track_returns=False):
+                 track_returns=False, occlusion_in_layers=True):
     """Fingerprint `shadow` (a not-yet-started ShadowEngine) and return its GameSpec.
 
     Runs the shadow's its_showtime() first (campx/engine.py:487-544); the resulting state is the
@@ -401,8 +449,30 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                 raise CompileError("Backdrop.update() changes the backdrop in a way that is neither a sprite stamp "
                                    "nor a roll of the whole curtain")
 
+    # ---- hidden state: behaviour the primitives cannot see --------------------------------------------------------
+    # Every probe starts from a copy of the its_showtime state, so an entity that counts steps, remembers visits or
+    # draws random numbers would look stateless here and compile to something that diverges later.  Any instance
+    # attribute (other than curtain / position / visibility) or non-tensor Plot entry that a step changes is such
+    # state: refuse the game instead of compiling it wrongly.
+    for pr in probes:
+        if pr.hidden:
+            owner, name = pr.hidden[0]
+            raise CompileError("%s keeps state the kernel primitives do not model: %s changed during a step (action "
+                               "%d).  Entities may only depend on curtains, positions, visibility, the last render "
+                               "and the action." % ("the Plot" if owner == "<plot>" else
+                                                    "the Backdrop" if owner == "<backdrop>" else "entity %r" % owner,
+                                                    name if owner == "<plot>" else "attribute %r" % name, pr.action))
+
     # ---- rewards, terminate, discount ----------------------------------------------------------------------
     movers = [c for c in z_chars if kind[c] in (N.CX_KIND_CELL, N.CX_KIND_SPRITE)]
+
+    def seen_under(pr, ch, w):
+        """Character the last render (the one entity `ch`'s update group saw) showed at mover `w`'s cell as of right
+        after `ch` updated (things[w] is current sibling state, boat_race.py:79); None for an empty mask."""
+        snap = pr.after[ch][w]
+        cell = snap[1][0] * cols + snap[1][1] if snap[0] == "sprite" else _cell_of(snap[1])
+        return None if cell is None else chr(int(pr.group_board[group_name[ch]].reshape(-1)[cell]))
+
     specs = []
     for z, ch in enumerate(z_chars):
         obs = []                                  # (probe, action, f32 reward or None)
@@ -421,10 +491,36 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             d = [payload for k, payload in pr.events.get(ch, ()) if k == "discount"]
             term.setdefault(pr.action, set()).add(t[-1] if t else None)
             disc.setdefault(pr.action, set()).add(d[-1] if d else None)
-        for name, table in (("terminate_episode", term), ("change_default_discount", disc)):
-            for a, vals in table.items():
-                if len(vals) != 1:
-                    raise CompileError("entity %r calls %s for action %d only in some states" % (ch, name, a))
+        for a, vals in disc.items():
+            if len(vals) != 1:
+                raise CompileError("entity %r calls change_default_discount for action %d only in some states" % (ch, a))
+        # terminate_episode: per action, or -- "reach the goal" games -- per (action, character the last render
+        # showed under a moving entity), the same query entry rewards use
+        term_watch, terminate_on = None, {}
+        if any(len(vals) != 1 for vals in term.values()):
+            for w in movers:
+                table, ok = {}, True
+                for pr in probes:
+                    t = [payload for k, payload in pr.events.get(ch, ()) if k == "terminate"]
+                    table.setdefault((pr.action, seen_under(pr, ch, w)), set()).add(t[-1] if t else None)
+                if all(len(v) == 1 for v in table.values()):
+                    term_watch = w
+                    for (a, seen_char), v in table.items():
+                        value = next(iter(v))
+                        if value is not None:
+                            if seen_char is None:
+                                raise CompileError("entity %r terminates the episode while %r has an empty mask" % (ch, w))
+                            terminate_on.setdefault(a, {})[seen_char] = float(value)
+                    break
+            if term_watch is None:
+                raise CompileError("entity %r calls terminate_episode depending on something other than (action, "
+                                   "what the last render showed under a moving entity)" % ch)
+            for a in list(terminate_on):       # fires for every character seen => unconditional for that action
+                seen_all = {k for (aa, k) in table if aa == a}
+                if set(terminate_on[a]) == seen_all and len(set(terminate_on[a].values())) == 1 and len(term[a]) == 1:
+                    del terminate_on[a]
+            for a in terminate_on:
+                term[a] = {None}               # not an unconditional directive of this action
         z_orders = {}
         for a, vals in zord.items():
             if len(vals) != 1:
@@ -440,7 +536,11 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                                        "(engine.py:270-279); not supported" % (move_this, front_of))
             if calls:
                 z_orders[a] = calls
-        terminate = {a: next(iter(v)) for a, v in term.items() if next(iter(v)) is not None}
+        terminate = {a: next(iter(v)) for a, v in term.items() if len(v) == 1 and next(iter(v)) is not None}
+        for a in terminate_on:
+            if a in disc and next(iter(disc[a])) is not None:
+                raise CompileError("entity %r both changes the default discount and conditionally terminates the "
+                                   "episode for action %d" % (ch, a))
         discount = {a: next(iter(v)) for a, v in disc.items() if next(iter(v)) is not None and a not in terminate}
 
         step_reward, watch, entry = None, None, None
@@ -459,18 +559,12 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                 step_reward = [next(iter(by_action[a])) if a in by_action else None for a in range(A)]
             else:
                 fitted = None
-                for w in movers:
+                for w in ([term_watch] if term_watch is not None else movers):   # one `watch` per entity
                     table, ok = {}, True
                     for pr, a, val in obs:
                         if val is None:
                             continue
-                        snap = pr.after[ch][w]
-                        if snap[0] == "sprite":
-                            cell = snap[1][0] * cols + snap[1][1]
-                        else:
-                            cell = _cell_of(snap[1])
-                        seen_char = None if cell is None else chr(int(pr.group_board[group_name[ch]].reshape(-1)[cell]))
-                        table.setdefault((a, seen_char), set()).add(float(val))
+                        table.setdefault((a, seen_under(pr, ch, w)), set()).add(float(val))
                     if all(len(v) == 1 for v in table.values()):
                         fitted = (w, {k: next(iter(v)) for k, v in table.items()})
                         break
@@ -510,8 +604,8 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
             visible=(snap[2] if snap[0] == "sprite" else True),
             init_pos=(snap[1] if snap[0] == "sprite" else None),
             moves=moves.get(ch), blockers=blockers.get(ch, ""),
-            step_reward=step_reward, watch=watch, entry_reward=entry,
-            terminate=terminate or None, discount=discount or None,
+            step_reward=step_reward, watch=watch if watch is not None else term_watch, entry_reward=entry,
+            terminate=terminate or None, terminate_on=terminate_on or None, discount=discount or None,
             visible_op=visible_ops.get(ch), z_orders=z_orders or None))
 
     # ---- whole-step consistency: the per-entity fits must add up to what play() returned --------------------
@@ -520,6 +614,7 @@ def compile_game(shadow, n_actions=5, action_format=None, max_episode_steps=0, a
                     n_groups=len(base.update_groups), max_episode_steps=max_episode_steps,
                     auto_reset=auto_reset, track_returns=track_returns,
                     first_reward=None if first_reward is None else float(_f32(first_reward)),
-                    first_discount=float(first_discount), action_format=fmt, backdrop_moves=backdrop_moves)
+                    first_discount=float(first_discount), action_format=fmt, backdrop_moves=backdrop_moves,
+                    occlusion_in_layers=bool(occlusion_in_layers))
     spec.n_probes = len(probes)
     return spec

@@ -82,21 +82,29 @@ class RecordingPlot(Plot):
 class ShadowRenderer(object):
     """The reference canvas (rendering.py:86-219) including where it aliases and where it copies."""
 
-    def __init__(self, rows, cols, characters):
+    def __init__(self, rows, cols, characters, occlusion_in_layers=True):
         self.board = torch.zeros((rows, cols), dtype=torch.int64)
         self.layers = {ch: torch.zeros((rows, cols), dtype=torch.uint8) for ch in characters}
+        # False: layers follow BaseUnoccludedObservationRenderer (rendering.py:227-353) -- a layer holds its
+        # entity's whole mask / position and the backdrop's own cells whether or not something is painted over them
+        self.occluded = bool(occlusion_in_layers)
 
     def clear(self):
         self.board.mul_(0)                       # in place, on whatever storage the canvas aliases
 
     def paint_all_of(self, curtain):
         self.board = curtain.as_subclass(torch.Tensor)    # alias of the backdrop storage (set_)
+        if not self.occluded:                             # rendering.py:283-286
+            for ch, layer in self.layers.items():
+                layer.copy_(self.board == ord(ch))
 
     def paint_sprite(self, character, position):
         if character not in self.layers:
             raise ValueError('character {} does not seem to be a valid character for '
                              'this game'.format(str(character)))
         self.board[position[0], position[1]] = ord(character)
+        if not self.occluded:                             # rendering.py:309
+            self.layers[character][position[0], position[1]] = 1
 
     def paint_drape(self, character, curtain):
         if character not in self.layers:
@@ -104,8 +112,12 @@ class ShadowRenderer(object):
                              'this game'.format(str(character)))
         m = curtain.as_subclass(torch.Tensor).long()
         self.board = self.board - m * self.board + m * ord(character)   # fresh storage
+        if not self.occluded:                             # rendering.py:333
+            self.layers[character].copy_(m != 0)
 
     def render(self):
+        if not self.occluded:
+            return                               # layers were filled while painting
         for ch, layer in self.layers.items():
             layer.copy_(self.board == ord(ch))   # identity of layers[ch] is preserved
 
@@ -113,14 +125,14 @@ class ShadowRenderer(object):
 class ShadowEngine(object):
     """Reference step semantics over the user's entity objects (one environment, CPU)."""
 
-    def __init__(self, rows, cols, backdrop, things_in_z_order, update_groups):
+    def __init__(self, rows, cols, backdrop, things_in_z_order, update_groups, occlusion_in_layers=True):
         self.rows, self.cols = rows, cols
         self.backdrop = backdrop
         self.things = collections.OrderedDict(things_in_z_order)
         self.update_groups = update_groups            # [(group_name, [entity, ...]), ...] sorted
         self.the_plot = RecordingPlot()
         chars = set(self.things.keys()).union(backdrop.palette)
-        self.renderer = ShadowRenderer(rows, cols, chars)
+        self.renderer = ShadowRenderer(rows, cols, chars, occlusion_in_layers)
         self.game_over = False
         self.showtime = False
 

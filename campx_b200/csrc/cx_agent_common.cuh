@@ -35,6 +35,45 @@ __device__ __forceinline__ void st_f32x4(float* p, int64_t i, int64_t end, const
     if (i + k < end) p[i + k] = v[k];
 }
 
+// GW-wide variants (GW = 4: the quad helpers above; GW = 2: half quads, for the 64-envs-per-warp build)
+template <bool VEC, int GW>
+__device__ __forceinline__ uint32_t ld_u8xg(const uint8_t* p, int64_t i, int64_t end, uint32_t fill) {
+  if (GW == 4) return ld_u8x4<VEC>(p, i, end, fill);
+  if (VEC) return (uint32_t)__ldcs(reinterpret_cast<const unsigned short*>(p + i));
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < GW; ++k) v |= (uint32_t)(i + k < end ? p[i + k] : (uint8_t)fill) << (8 * k);
+  return v;
+}
+template <bool VEC, int GW>
+__device__ __forceinline__ void st_u8xg(uint8_t* p, int64_t i, int64_t end, uint32_t v) {
+  if (GW == 4) {
+    st_u8x4<VEC>(p, i, end, v);
+    return;
+  }
+  if (VEC) {
+    __stcs(reinterpret_cast<unsigned short*>(p + i), (unsigned short)v);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < GW; ++k)
+    if (i + k < end) p[i + k] = (uint8_t)(v >> (8 * k));
+}
+template <bool VEC, int GW>
+__device__ __forceinline__ void st_f32xg(float* p, int64_t i, int64_t end, const float (&v)[4]) {
+  if (GW == 4) {
+    st_f32x4<VEC>(p, i, end, v);
+    return;
+  }
+  if (VEC) {
+    __stcs(reinterpret_cast<float2*>(p + i), make_float2(v[0], v[1]));
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < GW; ++k)
+    if (i + k < end) p[i + k] = v[k];
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

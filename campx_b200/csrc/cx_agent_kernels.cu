@@ -21,6 +21,8 @@
 //     contiguous 512 B / 128 B span;
 //   * warps only __syncwarp(); CTAs of 4 warps exist just to share the staged tables, so 1024 CTAs cover
 //     2^20 envs in one resident wave on 148 SMs (7 CTAs/SM, 25.6 KB of tile per CTA).
+#include <stdlib.h>
+
 #include "cx_agent_common.cuh"
 #include "cx_philox.cuh"
 
@@ -60,13 +62,20 @@ struct AgentParams {
   uint8_t* actions_out;           // SYNTH: [T, n] or null
 };
 
-constexpr int WT = CX_WARP_TILE_ENVS;       // envs per warp
-constexpr int QUADS = WT / 128;             // quads (4 consecutive envs) per lane
-constexpr int WARPS = CX_AGENT_CTA_THREADS / 32;
-
-template <bool TRACK, bool VEC, bool SYNTH>
+// A warp owns WT = NG * 32 * GW consecutive envs: every lane holds NG groups of GW consecutive envs (group j of lane l
+// = envs j*32*GW + l*GW ..), so that one instruction per group moves GW rewards / flags / actions per lane and
+// 32*GW contiguous elements per warp.  Three builds, picked by how many warps the batch gives each SM:
+//   NG 2, GW 4   256 envs per warp, 6.4 KB bulk stores for a 5x5 world: large batches (>= ~2^19 envs on 148 SMs)
+//   NG 1, GW 4   128 envs per warp: twice the warps for mid-size batches (2^18: 63 % -> 85 % of peak)
+//   NG 1, GW 2    64 envs per warp: four times the warps for small ones (BASELINE config 1: 65,536 envs)
+// CTAs are 1..4 warps (blockDim), chosen by the launcher so that small grids still spread evenly over the SMs.
+template <bool TRACK, bool VEC, bool SYNTH, int NG, int GW>
 __global__ void __launch_bounds__(CX_AGENT_CTA_THREADS, CX_OPT_MINBLOCKS)  // 7 CTAs/SM: 1024 CTAs (2^20 envs) in one wave
 k_agent_rollout(const __grid_constant__ AgentParams P) {
+  constexpr int WT = NG * 32 * GW;                 // envs per warp
+  constexpr int LPR = WT >= 128 ? WT / 128 : 1;    // 128-byte lines per row of this warp's actions
+  constexpr uint32_t GMASK = GW == 4 ? 0xFFFFFFFFu : 0xFFFFu;
+  const int WARPS = blockDim.x >> 5, NTHR = blockDim.x;
   extern __shared__ __align__(16) uint8_t smem[];
   const CxAgentHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -81,7 +90,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.blob);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < H.blob_bytes / 16; i += CX_AGENT_CTA_THREADS) dst[i] = src[i];
+    for (int i = tid; i < H.blob_bytes / 16; i += NTHR) dst[i] = src[i];
   }
   __syncthreads();  // the only block barrier; warps are independent from here on
 
@@ -115,24 +124,31 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything earlier in the stream is complete and visible
 #endif
   // ---- load env state into registers; paint the agents into the tile ----
-  uint32_t cellv[QUADS][4];   // agent cell
-  uint32_t drawnq[QUADS];     // per env one byte: cell where the agent is currently drawn in the tile (none: nowhere)
-  uint32_t ts[QUADS][4];
-  float rt[QUADS][4];
+  uint32_t cellv[NG][GW];   // agent cell
+  uint32_t drawnq[NG];      // per env one byte: cell where the agent is currently drawn in the tile (none: nowhere)
+  uint32_t ts[NG][GW];
+  float rt[NG][GW];
 #pragma unroll
-  for (int j = 0; j < QUADS; ++j) {
-    const int el = j * 128 + lane * 4;
+  for (int j = 0; j < NG; ++j) {
+    const int el = j * (32 * GW) + lane * GW;
     const bool quad_ok = VEC || el < nenv;
-    const uint32_t cq = quad_ok ? ld_u8x4<VEC>(P.cell, env0 + el, n, none) : none * 0x01010101u;
-    if (TRACK && VEC) {  // 8-byte / 16-byte state loads
-      const uint2 tv = *reinterpret_cast<const uint2*>(P.tstep + env0 + el);
-      const float4 rv = *reinterpret_cast<const float4*>(P.ret + env0 + el);
-      ts[j][0] = tv.x & 0xFFFF; ts[j][1] = tv.x >> 16; ts[j][2] = tv.y & 0xFFFF; ts[j][3] = tv.y >> 16;
-      rt[j][0] = rv.x; rt[j][1] = rv.y; rt[j][2] = rv.z; rt[j][3] = rv.w;
+    const uint32_t cq = quad_ok ? ld_u8xg<VEC, GW>(P.cell, env0 + el, n, none) : none * 0x01010101u;
+    if (TRACK && VEC) {  // 4/8-byte and 8/16-byte state loads
+      if (GW == 4) {
+        const uint2 tv = *reinterpret_cast<const uint2*>(P.tstep + env0 + el);
+        const float4 rv = *reinterpret_cast<const float4*>(P.ret + env0 + el);
+        ts[j][0] = tv.x & 0xFFFF; ts[j][1] = tv.x >> 16; ts[j][GW - 2] = tv.y & 0xFFFF; ts[j][GW - 1] = tv.y >> 16;
+        rt[j][0] = rv.x; rt[j][1] = rv.y; rt[j][GW - 2] = rv.z; rt[j][GW - 1] = rv.w;
+      } else {
+        const uint32_t tv = *reinterpret_cast<const uint32_t*>(P.tstep + env0 + el);
+        const float2 rv = *reinterpret_cast<const float2*>(P.ret + env0 + el);
+        ts[j][0] = tv & 0xFFFF; ts[j][1] = tv >> 16;
+        rt[j][0] = rv.x; rt[j][1] = rv.y;
+      }
     }
     drawnq[j] = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GW; ++i) {
       const bool valid = VEC || el + i < nenv;
       if (TRACK && !VEC) {
         ts[j][i] = valid ? P.tstep[env0 + el + i] : 0u;
@@ -157,9 +173,9 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   // streaming stores do not push them out before they are consumed.
   auto prefetch_actions = [&](int t0) {
     if (VEC && !SYNTH) {
-      const int tr = t0 + (lane >> 1);
+      const int tr = t0 + lane / LPR;   // a row of this warp's actions is LPR 128-byte lines (or part of one)
       if (tr < P.T) {
-        const uint8_t* a = P.actions + (int64_t)tr * n + env0 + (lane & 1) * 128;
+        const uint8_t* a = P.actions + (int64_t)tr * n + env0 + (lane % LPR) * 128;
 #if CX_OPT_PF >= 2
         asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a));
 #elif CX_OPT_PF == 1
@@ -178,21 +194,22 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   // the quad of envs a lane owns: actions are read from HBM, or generated (same Philox stream as
   // cx_fill_actions: counter = (global env >> 2, step))
   auto quad_actions = [&](int j, int t) -> uint32_t {
-    const int el = j * 128 + lane * 4;
+    const int el = j * (32 * GW) + lane * GW;
     if (!(VEC || el < nenv)) return 0u;
     if (SYNTH) {
-      const uint32_t a4 = cx_synth_actions_quad(P.seed, (P.env_offset + (uint64_t)(env0 + el)) >> 2,
-                                                P.t0 + (uint64_t)t, n_actions);
-      if (P.actions_out) st_u8x4<VEC>(P.actions_out, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, a4);
+      const uint64_t genv = P.env_offset + (uint64_t)(env0 + el);   // a multiple of GW
+      uint32_t a4 = cx_synth_actions_quad(P.seed, genv >> 2, P.t0 + (uint64_t)t, n_actions);
+      if (GW == 2) a4 = (a4 >> (8 * (uint32_t)(genv & 2))) & GMASK;   // the half quad this group is
+      if (P.actions_out) st_u8xg<VEC, GW>(P.actions_out, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, a4);
       return a4;
     }
-    return ld_u8x4<VEC>(P.actions, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, 0);
+    return ld_u8xg<VEC, GW>(P.actions, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, 0);
   };
   // actions are fetched two steps ahead: a load issued in step t is consumed in step t+2, so its latency
   // (microseconds behind the write streams) never stalls the warp
-  uint32_t actq[QUADS], actn[QUADS];
+  uint32_t actq[NG], actn[NG];
 #pragma unroll
-  for (int j = 0; j < QUADS; ++j) {
+  for (int j = 0; j < NG; ++j) {
     actq[j] = quad_actions(j, 0);
     actn[j] = (CX_OPT_ACT2 && P.T > 1) ? quad_actions(j, 1) : 0u;
   }
@@ -207,16 +224,16 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
     if ((t & 15) == 0) prefetch_actions(t + 32);
 #endif
     // ---- phase A (registers and tables only): the step of every env this lane owns ----
-    uint32_t shwq[QUADS];  // per env one byte: where the agent is drawn after this step
+    uint32_t shwq[NG];  // per env one byte: where the agent is drawn after this step
 #pragma unroll
-    for (int j = 0; j < QUADS; ++j) {
-      const int el = j * 128 + lane * 4;
+    for (int j = 0; j < NG; ++j) {
+      const int el = j * (32 * GW) + lane * GW;
       shwq[j] = drawnq[j];
       if (VEC || el < nenv) {
         float rw[4], dc[4];
         uint32_t fl = 0, shw = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GW; ++i) {
           const uint32_t was = (drawnq[j] >> (8 * i)) & 0xFF;
           if (!VEC && el + i >= nenv) {  // tail quad on the scalar path: env does not exist
             rw[i] = 0.0f;
@@ -229,7 +246,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           const uint32_t idx = a * stride + cellv[j][i];
           uint32_t e = s_tt[idx];
           float r = s_tr[idx];
-          if (want_discount) dc[i] = s_td[a];
+          if (want_discount) dc[i] = s_td[H.td_per_cell ? idx : a];
           if (TRACK && (ts[j][i] & CX_OVER_BIT)) {  // auto_reset == 0 and the episode ended: frozen env
             e = cellv[j][i] | (was << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
             r = 0.0f;
@@ -260,13 +277,13 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           cellv[j][i] = p;
         }
         shwq[j] = shw;
-        st_f32x4<VEC>(P.reward, row + el, row_end, rw);
-        if (want_discount) st_f32x4<VEC>(P.discount, row + el, row_end, dc);
-        st_u8x4<VEC>(P.flags, row + el, row_end, fl);
+        st_f32xg<VEC, GW>(P.reward, row + el, row_end, rw);
+        if (want_discount) st_f32xg<VEC, GW>(P.discount, row + el, row_end, dc);
+        st_u8xg<VEC, GW>(P.flags, row + el, row_end, fl);
       }
     }
 #pragma unroll
-    for (int j = 0; j < QUADS; ++j) {
+    for (int j = 0; j < NG; ++j) {
 #if CX_OPT_ACT2
       actq[j] = actn[j];
       if (t + 2 < P.T) actn[j] = quad_actions(j, t + 2);
@@ -281,12 +298,12 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
     // ---- phase B: re-compose the boards: base character back where the agent was drawn, agent character
     // where it is visible now (painter's algorithm collapsed to two byte stores per env that changed) ----
 #pragma unroll
-    for (int j = 0; j < QUADS; ++j) {
+    for (int j = 0; j < NG; ++j) {
       const uint32_t diff = drawnq[j] ^ shwq[j];
       if (diff) {
-        uint8_t* qtile = tile + (j * 128 + lane * 4) * cells;
+        uint8_t* qtile = tile + (j * (32 * GW) + lane * GW) * cells;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GW; ++i) {
           if ((diff >> (8 * i)) & 0xFF) {
             const uint32_t was = (drawnq[j] >> (8 * i)) & 0xFF, show = (shwq[j] >> (8 * i)) & 0xFF;
             uint8_t* b = qtile + i * cells;
@@ -328,24 +345,34 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
 
   // ---- write the env state back ----
 #pragma unroll
-  for (int j = 0; j < QUADS; ++j) {
-    const int el = j * 128 + lane * 4;
+  for (int j = 0; j < NG; ++j) {
+    const int el = j * (32 * GW) + lane * GW;
     if (VEC || el < nenv) {
-      const uint32_t cq = cellv[j][0] | (cellv[j][1] << 8) | (cellv[j][2] << 16) | (cellv[j][3] << 24);
+      uint32_t cq = 0;
+#pragma unroll
+      for (int i = 0; i < GW; ++i) cq |= cellv[j][i] << (8 * i);
       if (VEC) {
-        *reinterpret_cast<uint32_t*>(P.cell + env0 + el) = cq;
+        if (GW == 4)
+          *reinterpret_cast<uint32_t*>(P.cell + env0 + el) = cq;
+        else
+          *reinterpret_cast<uint16_t*>(P.cell + env0 + el) = (uint16_t)cq;
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < GW; ++i)
           if (el + i < nenv) P.cell[env0 + el + i] = (uint8_t)cellv[j][i];
       }
       if (TRACK && VEC) {
-        *reinterpret_cast<uint2*>(P.tstep + env0 + el) =
-            make_uint2(ts[j][0] | (ts[j][1] << 16), ts[j][2] | (ts[j][3] << 16));
-        *reinterpret_cast<float4*>(P.ret + env0 + el) = make_float4(rt[j][0], rt[j][1], rt[j][2], rt[j][3]);
+        if (GW == 4) {
+          *reinterpret_cast<uint2*>(P.tstep + env0 + el) =
+              make_uint2(ts[j][0] | (ts[j][1] << 16), ts[j][GW - 2] | (ts[j][GW - 1] << 16));
+          *reinterpret_cast<float4*>(P.ret + env0 + el) = make_float4(rt[j][0], rt[j][1], rt[j][GW - 2], rt[j][GW - 1]);
+        } else {
+          *reinterpret_cast<uint32_t*>(P.tstep + env0 + el) = ts[j][0] | (ts[j][1] << 16);
+          *reinterpret_cast<float2*>(P.ret + env0 + el) = make_float2(rt[j][0], rt[j][1]);
+        }
       } else if (TRACK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < GW; ++i)
           if (el + i < nenv) {
             P.tstep[env0 + el + i] = (uint16_t)ts[j][i];
             P.ret[env0 + el + i] = rt[j][i];
@@ -371,18 +398,18 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   }
 }
 
-template <bool TRACK, bool VEC, bool SYNTH>
-int launch(const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;  // raise the dynamic shared memory cap once (it reserves nothing)
-  if (!configured) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<TRACK, VEC, SYNTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <bool TRACK, bool VEC, bool SYNTH, int NG, int GW>
+int launch(const AgentParams& P, unsigned grid, unsigned block, size_t smem, cudaStream_t s) {
+  static CxPerDevice configured;  // raise the dynamic shared memory cap once per device (it reserves nothing)
+  if (configured.need()) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout<TRACK, VEC, SYNTH, NG, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
-    configured = true;
+    configured.mark();
   }
 #if CX_OPT_PDL
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(CX_AGENT_CTA_THREADS);
+  cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -390,18 +417,28 @@ int launch(const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout<TRACK, VEC, SYNTH>, P));
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout<TRACK, VEC, SYNTH, NG, GW>, P));
 #else
-  k_agent_rollout<TRACK, VEC, SYNTH><<<grid, CX_AGENT_CTA_THREADS, smem, s>>>(P);
+  k_agent_rollout<TRACK, VEC, SYNTH, NG, GW><<<grid, block, smem, s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
 #endif
   return CX_OK;
 }
 
-template <bool SYNTH>
-int launch_tv(bool track, bool vec, const AgentParams& P, unsigned grid, size_t smem, cudaStream_t s) {
-  if (track) return vec ? launch<true, true, SYNTH>(P, grid, smem, s) : launch<true, false, SYNTH>(P, grid, smem, s);
-  return vec ? launch<false, true, SYNTH>(P, grid, smem, s) : launch<false, false, SYNTH>(P, grid, smem, s);
+template <bool SYNTH, int NG, int GW>
+int launch_tv(bool track, bool vec, const AgentParams& P, unsigned grid, unsigned block, size_t smem, cudaStream_t s) {
+  if (track)
+    return vec ? launch<true, true, SYNTH, NG, GW>(P, grid, block, smem, s)
+               : launch<true, false, SYNTH, NG, GW>(P, grid, block, smem, s);
+  return vec ? launch<false, true, SYNTH, NG, GW>(P, grid, block, smem, s)
+             : launch<false, false, SYNTH, NG, GW>(P, grid, block, smem, s);
+}
+
+template <int NG, int GW>
+int launch_s(bool synth, bool track, bool vec, const AgentParams& P, unsigned grid, unsigned block, size_t smem,
+             cudaStream_t s) {
+  return synth ? launch_tv<true, NG, GW>(track, vec, P, grid, block, smem, s)
+               : launch_tv<false, NG, GW>(track, vec, P, grid, block, smem, s);
 }
 
 }  // namespace
@@ -430,18 +467,32 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   P.t0 = synth.t0;
   P.actions_out = synth.actions_out;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  // vector path: every warp owns a full tile of 256 envs and every [T, n] row starts 16-byte aligned
+  // envs per warp, by envs per SM (measured on 148 SMs, Demo 1, 32-step launches, % of the HBM copy peak for
+  // 64 / 128 / 256 envs per warp: 65,536 envs 45 / 36 / 19, 2^17 65 / 62 / 37, 2^18 79 / 87 / 63, 2^19 83 / 82 / 79,
+  // 2^20 77 / 84 / 86; scripts/r02_probe.py).  CX_AGENT_WT = 64 | 128 | 256 forces a build.
+  const int64_t per_sm = (n + g->sm_count - 1) / g->sm_count;
+  int WT = per_sm >= 24 * 256 ? 256 : (per_sm >= 12 * 128 ? 128 : 64);
+  if (const char* dbg = getenv("CX_AGENT_WT")) {
+    const int w = atoi(dbg);
+    if (w == 64 || w == 128 || w == 256) WT = w;
+  }
+  // vector path: every warp owns a full tile of WT envs and every [T, n] row starts 16-byte aligned
   const bool vec = (n % WT == 0) && al16(d_actions) && al16(synth.actions_out) && al16(d_reward) && al16(d_discount) && al16(d_flags) &&
                    al16(d_board);
-
-  const size_t smem = (size_t)g->ah.blob_bytes + (size_t)WARPS * WT * g->ah.cells +
-                      (g->ah.track ? CX_AGENT_CTA_THREADS * sizeof(LaneStats) : 0);
   const int64_t warps = (n + WT - 1) / WT;
-  const int64_t grid = (warps + WARPS - 1) / WARPS;
+  // warps per CTA: 4, fewer while that leaves the grid under ~4 CTAs per SM (small grids spread more evenly)
+  int wpc = CX_AGENT_CTA_THREADS / 32;
+  while (wpc > 1 && (warps + wpc - 1) / wpc < (int64_t)g->sm_count * 4) wpc >>= 1;
+  const unsigned block = 32u * wpc;
+  const size_t smem = (size_t)g->ah.blob_bytes + (size_t)wpc * WT * g->ah.cells +
+                      (g->ah.track ? (size_t)block * sizeof(LaneStats) : 0);
+  const int64_t grid = (warps + wpc - 1) / wpc;
   if (grid > 0x7fffffff) {
     cx_set_error("cx_rollout: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  return synth.on ? launch_tv<true>(g->ah.track != 0, vec, P, (unsigned)grid, smem, s)
-                  : launch_tv<false>(g->ah.track != 0, vec, P, (unsigned)grid, smem, s);
+  const bool track = g->ah.track != 0, sy = synth.on != 0;
+  if (WT == 64) return launch_s<1, 2>(sy, track, vec, P, (unsigned)grid, block, smem, s);
+  if (WT == 128) return launch_s<1, 4>(sy, track, vec, P, (unsigned)grid, block, smem, s);
+  return launch_s<2, 4>(sy, track, vec, P, (unsigned)grid, block, smem, s);
 }

@@ -106,10 +106,15 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   __syncwarp();
 
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Occluded layers (the reference's default, rendering.py:204-209) follow the BOARD: the agent's plane is set where
+  // it is drawn and the plane of the character it covers is cleared there.  Unoccluded layers
+  // (cx_game_desc::unoccluded_layers, rendering.py:227-353) follow the CURTAINS: only the agent's own plane changes,
+  // at the agent's real cell, drawn or not; the static planes (backdrop cells, whole static curtains) never do.
+  const bool unocc = H.unoccluded != 0;
   auto draw = [&](int r, uint32_t c) {  // paint the agent at visible cell c of ring slot r
     uint8_t* myb = wbase + r * slot_bytes + lane * cells;
     myb[c] = (uint8_t)agent_char;
-    if (layers) {
+    if (layers && !unocc) {
       uint8_t* myl = wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes;
       const uint32_t k = s_basek[c];
       if (k != 0xFF) myl[k * cells + c] = 0;
@@ -119,21 +124,30 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
   auto erase = [&](int r, uint32_t c) {  // back to the static scene at cell c
     uint8_t* myb = wbase + r * slot_bytes + lane * cells;
     myb[c] = s_basech[c];
-    if (layers) {
+    if (layers && !unocc) {
       uint8_t* myl = wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes;
       myl[agent_k * cells + c] = 0;
       const uint32_t k = s_basek[c];
       if (k != 0xFF) myl[k * cells + c] = 1;
     }
   };
+  auto agent_plane = [&](int r, uint32_t c, uint8_t v) {  // unoccluded: the agent's curtain is its one cell
+    (wbase + r * slot_bytes + OBS_TILE * cells + lane * lay_bytes)[agent_k * cells + c] = v;
+  };
 
   uint32_t cell = mine ? min((uint32_t)P.cell[env], none) : none;
   uint32_t shown = s_shown[cell];   // where the agent is drawn in the most recent frame
   uint32_t drawn[RING];             // ... and in each ring slot (a slot is RING frames behind when it comes up again)
+  uint32_t lcell[RING];             // unoccluded layers: the cell set in the agent's plane of each ring slot
 #pragma unroll
   for (int r = 0; r < RING; ++r) {
     drawn[r] = shown;
+    lcell[r] = none;
     if (shown != none) draw(r, shown);
+    if (layers && unocc && cell != none) {
+      agent_plane(r, cell, 1);
+      lcell[r] = cell;
+    }
   }
   uint32_t ts = 0;
   float rt = 0.0f;
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
       const uint32_t idx = a * stride + cell;
       uint32_t e = s_tt[idx];
       float rw = s_tr[idx];
-      float dc = want_discount ? s_td[a] : 1.0f;
+      float dc = want_discount ? s_td[H.td_per_cell ? idx : a] : 1.0f;
       if (TRACK && (ts & CX_OVER_BIT)) {
         e = cell | (shown << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
         rw = 0.0f;
@@ -187,6 +201,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
       }
       uint32_t p = e & 0xFF;
       const uint32_t show = mine ? (e >> 8) & 0xFF : none;
+      const uint32_t stood = mine ? p : none;   // the agent's cell in this step's frame (before any auto reset)
       uint32_t f = e >> 16;
       if (TRACK && mine && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
         const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);   // 15-bit counter saturates (bit 15 = OVER)
@@ -221,6 +236,11 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
         if (drawn[r] != none) erase(r, drawn[r]);
         if (show != none) draw(r, show);
         drawn[r] = show;
+      }
+      if (layers && unocc && lcell[r] != stood) {
+        if (lcell[r] != none) agent_plane(r, lcell[r], 0);
+        if (stood != none) agent_plane(r, stood, 1);
+        lcell[r] = stood;
       }
       const uint8_t* btile = wbase + r * slot_bytes;
       const uint8_t* ltile = btile + OBS_TILE * cells;
@@ -281,9 +301,12 @@ size_t obs_smem_bytes(const cx_game* g, bool layers, int ring = 1) {
 
 template <bool TRACK, int RING>
 int launch_obs(const ObsParams& P, unsigned grid, size_t smem, cudaStream_t s) {
-  // the cap on dynamic shared memory is a per-device function attribute: set it on every launch (it reserves nothing)
-  CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_obs<TRACK, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  227 * 1024));
+  static CxPerDevice configured;  // the dynamic shared memory cap is a per-device function attribute
+  if (configured.need()) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_obs<TRACK, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    configured.mark();
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(OBS_THREADS);

@@ -21,7 +21,7 @@
 //            second pass over HBM converts them.
 // No table staging (tables are a few hundred bytes, read through L1), one block barrier, no tensor cores (nothing
 // here is a contraction).  Envs per CTA are chosen by the launcher so that the grid is a few waves deep at any
-// batch size: 32 envs per CTA for a 4,096-env policy loop (128 CTAs), 1,024 for 2^20 envs.
+// batch size: 32 envs per CTA for a 4,096-env policy loop (128 CTAs), 256 (one thread per env) for 2^20 envs.
 #include "cx_agent_common.cuh"
 
 namespace {
@@ -41,9 +41,10 @@ struct StepParams {
   void* layered;           // [n, chars, cells] of the LAY element type, or null
   int64_t n;
   int32_t envs_per_cta;    // multiple of 32
+  uint64_t inv_cells, inv_lc;  // ceil(2^40 / cells), ceil(2^40 / (n_chars * cells))
 };
 
-constexpr int ST_THREADS = 128;
+constexpr int ST_THREADS = 256;   // upper bound; small batches launch 128-thread CTAs
 
 // four consecutive bytes of a table starting at any byte offset: two aligned words and a funnel shift
 __device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* base, uint32_t off) {
@@ -64,8 +65,9 @@ __device__ __forceinline__ void put_byte(uint32_t (&w)[4], uint32_t pos, uint32_
 template <bool TRACK, int LAY>
 __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(16) uint8_t s_show[];  // [envs_per_cta] cell where the agent is drawn after the step
+  uint8_t* s_stood = s_show + P.envs_per_cta;        // [envs_per_cta] its real cell in that frame (unoccluded layers)
   const CxAgentHeader& H = P.h;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const uint32_t cells = H.cells, none = cells;
   const int E = P.envs_per_cta;
   const int64_t env0 = (int64_t)blockIdx.x * E;
@@ -82,19 +84,29 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
   const uint32_t stride = H.stride, n_actions = H.n_actions, agent_char = H.agent_char;
   const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
   const bool auto_reset = H.auto_reset != 0, want_discount = P.discount != nullptr;
+  // x / cells and x / (chars * cells) by multiplication: q = (x * ceil(2^40 / d)) >> 40, exact while x * d < 2^40
+  // (x < 2^22 elements per CTA, d < 2^13)
+  const uint64_t inv_cells = P.inv_cells, inv_lc = P.inv_lc;
+  auto div_cells = [&](uint32_t x) { return (uint32_t)(((uint64_t)x * inv_cells) >> 40); };
+  auto div_lc = [&](uint32_t x) { return (uint32_t)(((uint64_t)x * inv_lc) >> 40); };
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous step's state and outputs are complete
 
   // ---- phase 1: the step of every env of this CTA ----
   LaneStats st;
   if (TRACK) st.clear();
-  for (int el = tid; el < nenv; el += ST_THREADS) {
+  for (int el = tid; el < nenv; el += nthreads) {
     const int64_t env = env0 + el;
     const uint32_t cell = min((uint32_t)P.cell[env], none);
+    if (P.actions == nullptr) {  // render only (cx_render_observations): the frame of the current state
+      s_show[el] = __ldg(P.blob + H.off_shown + cell);
+      s_stood[el] = (uint8_t)cell;
+      continue;
+    }
     const uint32_t a = min((uint32_t)P.actions[env], n_actions);
     const uint32_t idx = a * stride + cell;
     uint32_t e = __ldg(g_tt + idx);
     float r = __ldg(g_tr + idx);
-    float dc = want_discount ? __ldg(g_td + a) : 1.0f;
+    float dc = want_discount ? __ldg(g_td + (H.td_per_cell ? idx : a)) : 1.0f;
     uint32_t ts = 0;
     float rt = 0.0f;
     if (TRACK) {
@@ -109,6 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
     }
     uint32_t p = e & 0xFF;
     const uint32_t show = (e >> 8) & 0xFF;
+    s_stood[el] = (uint8_t)p;    // before any auto reset: the frame shows the terminal state
     uint32_t f = e >> 16;
     if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
       const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);
@@ -142,20 +155,21 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
   {
     const uint32_t nbytes = (uint32_t)nenv * cells, nfull = nbytes >> 4;
     uint8_t* out = P.board + env0 * cells;
-    for (uint32_t k = tid; k < nfull; k += ST_THREADS) {
-      const uint32_t b0 = k << 4, e_lo = b0 / cells, ph = b0 - e_lo * cells;
+    #pragma unroll 2
+    for (uint32_t k = tid; k < nfull; k += nthreads) {
+      const uint32_t b0 = k << 4, e_lo = div_cells(b0), ph = b0 - e_lo * cells;
       const uint4 v = __ldg(g_pat + ph);  // the static scene from phase `ph` on, 16 bytes (wraps)
       uint32_t w[4] = {v.x, v.y, v.z, v.w};
       // last env the piece touches (boards of 16 cells or more: at most the next one)
-      const uint32_t e_hi = min(cells >= 16u ? e_lo + (ph + 15u >= cells ? 1u : 0u) : (b0 + 15u) / cells, (uint32_t)nenv - 1u);
+      const uint32_t e_hi = min(cells >= 16u ? e_lo + (ph + 15u >= cells ? 1u : 0u) : div_cells(b0 + 15u), (uint32_t)nenv - 1u);
       for (uint32_t e = e_lo; e <= e_hi; ++e) {
         const uint32_t sh = s_show[e], pos = e * cells + sh - b0;  // unsigned: a cell before the piece wraps high
         if (sh != none && pos < 16u) put_byte(w, pos, agent_char);
       }
       *reinterpret_cast<uint4*>(out + b0) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    for (uint32_t b = (nfull << 4) + tid; b < nbytes; b += ST_THREADS) {  // ragged tail of the last CTA
-      const uint32_t e = b / cells, c = b - e * cells;
+    for (uint32_t b = (nfull << 4) + tid; b < nbytes; b += nthreads) {  // ragged tail of the last CTA
+      const uint32_t e = div_cells(b), c = b - e * cells;
       out[b] = c == s_show[e] ? (uint8_t)agent_char : __ldg(g_basech + c);
     }
   }
@@ -165,25 +179,29 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
     constexpr uint32_t ES = LAY == 1 ? 1u : (LAY == 2 ? 4u : 2u);  // element size
     constexpr uint32_t EPC = 16u / ES;                              // elements per 16-byte piece
     const uint32_t LC = (uint32_t)H.n_chars * cells, agent_off = (uint32_t)H.agent_k * cells;
+    const bool unocc = H.unoccluded != 0;
     const uint32_t nelem = (uint32_t)nenv * LC, nfull = nelem / EPC;
     uint8_t* out = static_cast<uint8_t*>(P.layered) + env0 * (int64_t)LC * ES;
     // byte image of EPC elements starting at flat element i0 (static layered image + the agent's two patches)
     auto piece = [&](uint32_t i0, uint32_t count, uint32_t (&w)[4]) {
-      const uint32_t e_lo = i0 / LC, rem = i0 - e_lo * LC;
+      const uint32_t e_lo = div_lc(i0), rem = i0 - e_lo * LC;
 #pragma unroll
       for (uint32_t j = 0; j < EPC / 4; ++j) w[j] = ldg_u32_unaligned(g_lay, rem + 4u * j);
-      const uint32_t e_hi = min(LC >= EPC ? e_lo + (rem + count - 1u >= LC ? 1u : 0u) : (i0 + count - 1u) / LC, (uint32_t)nenv - 1u);
+      const uint32_t e_hi = min(LC >= EPC ? e_lo + (rem + count - 1u >= LC ? 1u : 0u) : div_lc(i0 + count - 1u), (uint32_t)nenv - 1u);
       for (uint32_t e = e_lo; e <= e_hi; ++e) {
-        const uint32_t sh = s_show[e];
+        // occluded layers follow the board (agent plane on where it is DRAWN, the covered character's plane off);
+        // unoccluded layers follow the curtains (agent plane on where the agent STANDS, nothing else changes)
+        const uint32_t sh = unocc ? s_stood[e] : s_show[e];
         if (sh == none) continue;
         const uint32_t at = e * LC + sh - i0;          // + plane offset = position inside the piece (wraps high)
-        const uint32_t kb = __ldg(g_basek + sh);       // plane of the character the agent covers (0xFF: none)
+        const uint32_t kb = unocc ? 0xFFu : __ldg(g_basek + sh);   // plane of the covered character (0xFF: none)
         const uint32_t off = at + kb * cells, on = at + agent_off;
         if (kb != 0xFFu && off < EPC) put_byte(w, off, 0u);
         if (on < EPC) put_byte(w, on, 1u);
       }
     };
-    for (uint32_t k = tid; k < nfull; k += ST_THREADS) {
+#pragma unroll 2
+    for (uint32_t k = tid; k < nfull; k += nthreads) {
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       piece(k * EPC, EPC, w);
       uint4 v;
@@ -200,7 +218,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
       }
       *reinterpret_cast<uint4*>(out + (size_t)k * 16u) = v;
     }
-    for (uint32_t i = nfull * EPC + tid; i < nelem; i += ST_THREADS) {  // ragged tail of the last CTA
+    for (uint32_t i = nfull * EPC + tid; i < nelem; i += nthreads) {  // ragged tail of the last CTA
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       piece(i, 1u, w);
       const uint32_t b = w[0] & 1u;
@@ -213,7 +231,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
     }
   }
 
-  if (TRACK) {
+  if (TRACK && P.actions != nullptr) {
     const double cnt = warp_sum((double)st.cnt);
     if (cnt > 0.0) {  // warp-uniform: rare (an episode ended in this warp's envs)
       const double len = warp_sum((double)st.len), sum = warp_sum(st.sum), sumsq = warp_sum(st.sumsq);
@@ -232,10 +250,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
 }
 
 template <bool TRACK, int LAY>
-int launch_step(const StepParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+int launch_step(const StepParams& P, unsigned grid, unsigned block, size_t smem, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(ST_THREADS);
+  cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -248,12 +266,12 @@ int launch_step(const StepParams& P, unsigned grid, size_t smem, cudaStream_t s)
 }
 
 template <bool TRACK>
-int launch_step_lay(int lay, const StepParams& P, unsigned grid, size_t smem, cudaStream_t s) {
+int launch_step_lay(int lay, const StepParams& P, unsigned grid, unsigned block, size_t smem, cudaStream_t s) {
   switch (lay) {
-    case 0: return launch_step<TRACK, 0>(P, grid, smem, s);
-    case 1: return launch_step<TRACK, 1>(P, grid, smem, s);
-    case 2: return launch_step<TRACK, 2>(P, grid, smem, s);
-    default: return launch_step<TRACK, 4>(P, grid, smem, s);
+    case 0: return launch_step<TRACK, 0>(P, grid, block, smem, s);
+    case 1: return launch_step<TRACK, 1>(P, grid, block, smem, s);
+    case 2: return launch_step<TRACK, 2>(P, grid, block, smem, s);
+    default: return launch_step<TRACK, 4>(P, grid, block, smem, s);
   }
 }
 
@@ -285,20 +303,25 @@ int cx_launch_agent_step(const cx_game* g, void* d_state, int64_t n, const uint8
   P.board = d_board;
   P.layered = d_layered;
   P.n = n;
-  // envs per CTA: a multiple of 32 that makes the grid about four CTAs per SM deep, at most 1,024 (2^20 envs: one
-  // resident wave of 1,024 CTAs), at least 32 (a 4,096-env policy loop still spreads over 128 CTAs)
+  // envs per CTA: a multiple of 32 that makes the grid about four CTAs per SM deep -- 32 for a 4,096-env policy loop
+  // (128 CTAs of 128 threads) -- up to 256 with one thread per env (2^20 envs: 4,096 CTAs of 256 threads; fatter
+  // CTAs with several envs per thread serialise the state loads and measured 2x slower there)
   int64_t per = (n + (int64_t)g->sm_count * 4 - 1) / ((int64_t)g->sm_count * 4);
   per = (per + 31) / 32 * 32;
   if (per < 32) per = 32;
-  if (per > 1024) per = 1024;
+  if (per > ST_THREADS) per = ST_THREADS;
   P.envs_per_cta = (int32_t)per;
+  const unsigned block = per > 128 ? 256u : 128u;
+  const uint64_t lc = (uint64_t)g->ah.n_chars * g->ah.cells;
+  P.inv_cells = ((1ull << 40) + g->ah.cells - 1) / g->ah.cells;
+  P.inv_lc = ((1ull << 40) + lc - 1) / lc;
   const int64_t grid = (n + per - 1) / per;
   if (grid > 0x7fffffff) {
     cx_set_error("cx_step: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
   const int lay = d_layered ? (lay_dtype == CX_DTYPE_U8 ? 1 : (lay_dtype == CX_DTYPE_F32 ? 2 : 4)) : 0;
-  const size_t smem = (size_t)per;
-  return g->ah.track ? launch_step_lay<true>(lay, P, (unsigned)grid, smem, s)
-                     : launch_step_lay<false>(lay, P, (unsigned)grid, smem, s);
+  const size_t smem = 2 * (size_t)per;
+  return g->ah.track ? launch_step_lay<true>(lay, P, (unsigned)grid, block, smem, s)
+                     : launch_step_lay<false>(lay, P, (unsigned)grid, block, smem, s);
 }

@@ -338,11 +338,11 @@ inline int layers_boards_per_cta(int cells) {
 
 template <typename OutT>
 int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, OutT* d_out, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static CxPerDevice configured;
+  if (configured.need()) {
     CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_layers<OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
-    configured = true;
+    configured.mark();
   }
   CharTable ct;
   memcpy(ct.ch, g->desc.chars, CX_MAX_CHARS);
@@ -377,10 +377,10 @@ int launch_layers(const cx_game* g, const uint8_t* d_board, int64_t n_boards, Ou
   const int L = g->info.n_chars;
   if (sizeof(OutT) == 4 && cells > 1 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 &&
       (uint64_t)EB * L * cells * (uint64_t)cells < (1ull << 32)) {
-    static bool configured_cells = false;
-    if (!configured_cells) {
+    static CxPerDevice configured_cells;
+    if (configured_cells.need()) {
       CX_CUDA_OK(cudaFuncSetAttribute(k_layers_cells_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024));
-      configured_cells = true;
+      configured_cells.mark();
     }
     k_layers_cells_f32<<<(unsigned)grid, TB, smem, s>>>(d_board, reinterpret_cast<float*>(d_out), ct, L, cells, EB, n_boards,
                                                         (uint32_t)(0xFFFFFFFFu / (uint32_t)cells + 1u),
@@ -420,8 +420,11 @@ __global__ void k_onehot_to_index(const float* __restrict__ onehot, int A, uint8
     else if (v != 0.0f)
       ++others;
   }
-  idx[i] = (uint8_t)best;
-  if ((ones != 1 || others != 0) && bad) atomicAdd(bad, 1);
+  // a row that is not exactly one-hot is not an action (boat_race.py:48 `assert sum(act) == 1`): index 255 makes
+  // the step kernels leave that env untouched and raise CX_FLAG_BAD_ACTION for it
+  const bool invalid = ones != 1 || others != 0;
+  idx[i] = invalid ? (uint8_t)255 : (uint8_t)best;
+  if (invalid && bad) atomicAdd(bad, 1);
 }
 
 __global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t T, int64_t n, int32_t A,
@@ -631,6 +634,11 @@ extern "C" int cx_layers_from_board(const cx_game* g, const uint8_t* d_board, in
     cx_set_error("cx_layers_from_board: bad argument");
     return CX_ERR_INVALID_ARG;
   }
+  if (g->desc.unoccluded_layers) {
+    cx_set_error("cx_layers_from_board: unoccluded layers (occlusion_in_layers=False) are not a function of the board; they come from "
+                 "cx_step_observations / cx_rollout_observations / cx_render_observations");
+    return CX_ERR_UNSUPPORTED;
+  }
   return launch_layers<uint8_t>(g, d_board, n_boards, d_layered, (cudaStream_t)stream);
 }
 
@@ -639,6 +647,11 @@ extern "C" int cx_layers_from_board_f32(const cx_game* g, const uint8_t* d_board
   if (!g || !d_board || !d_layered || n_boards < 1) {
     cx_set_error("cx_layers_from_board_f32: bad argument");
     return CX_ERR_INVALID_ARG;
+  }
+  if (g->desc.unoccluded_layers) {
+    cx_set_error("cx_layers_from_board_f32: unoccluded layers (occlusion_in_layers=False) are not a function of the board; they come from "
+                 "cx_step_observations / cx_rollout_observations / cx_render_observations");
+    return CX_ERR_UNSUPPORTED;
   }
   return launch_layers<float>(g, d_board, n_boards, d_layered, (cudaStream_t)stream);
 }

@@ -172,10 +172,10 @@ inline int boards_per_cta(int cells) {
 template <typename E, int LAYOUT>
 int launch_map(const cx_board_mapper* m, const uint8_t* d_board, int64_t n_boards, const MapGeom& g, void* d_out,
                int32_t* d_unknown, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static CxPerDevice configured;
+  if (configured.need()) {
     CX_CUDA_OK(cudaFuncSetAttribute(k_board_map<E, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
+    configured.mark();
   }
   const int EB = boards_per_cta(g.cells);
   const int64_t grid = (n_boards + EB - 1) / EB;

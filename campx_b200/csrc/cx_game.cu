@@ -231,6 +231,16 @@ static int validate(const cx_game_desc* d) {
                      e.move_dr[a], e.move_dc[a]);
         return CX_ERR_INVALID_ARG;
       }
+      if (e.terminate_chars[a]) {
+        if (e.watch < 0) {
+          cx_set_error("cx_game_create: entity %d has terminate_chars but watches no entity", z);
+          return CX_ERR_INVALID_ARG;
+        }
+        if (!(e.terminate_value[a] >= 0.0f && e.terminate_value[a] <= 1.0f)) {
+          cx_set_error("Pcontinue must be in range [0,1]");  // plot.py:176-177
+          return CX_ERR_INVALID_ARG;
+        }
+      }
       const float dv = e.discount_value[a];
       if (((e.terminate_actions | e.discount_actions) >> a & 1) && !(dv >= 0.0f && dv <= 1.0f)) {
         cx_set_error("Pcontinue must be in range [0,1]");  // plot.py:176-177,250-251
@@ -305,6 +315,8 @@ static bool agent_path_applies(const cx_game_desc* d, int* agent_z) {
 struct AgentStep {
   int q;          // new cell (cells: empty)
   float reward;
+  bool over;      // the_plot.terminate_episode() was called (plot.py:161-184)
+  float discount; // discount returned with the step (engine.py:285-290)
 };
 
 static AgentStep agent_step_host(const cx_game_desc* d, int agent_z, const int* order, const uint8_t* basech,
@@ -351,9 +363,29 @@ static AgentStep agent_step_host(const cx_game_desc* d, int agent_z, const int* 
       summed = s2;
     }
   }
+  // plot directives in update order: the last change_default_discount / terminate_episode call wins
+  bool over = false;
+  float disc = 1.0f;  // plot.py:100
+  for (int i = 0; i < d->n_entities; ++i) {
+    const cx_entity_desc& e = d->entities[order[i]];
+    if (e.discount_actions >> a & 1) disc = e.discount_value[a];
+    if (e.terminate_actions >> a & 1) {
+      over = true;
+      disc = e.discount_value[a];
+    }
+    if (e.terminate_chars[a] && e.watch == agent_z) {
+      const int k = (e.update_rank >= ag.update_rank) ? kn : ko;
+      if (k < L && ((e.terminate_chars[a] >> k) & 1u)) {
+        over = true;
+        disc = e.terminate_value[a];
+      }
+    }
+  }
   AgentStep out;
   out.q = q;
   out.reward = summed;
+  out.over = over;
+  out.discount = disc;
   return out;
 }
 
@@ -389,25 +421,30 @@ static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* or
       }
   }
   const int S = cells + 1;
+  for (int z = 0; z < d->n_entities; ++z)
+    for (int a = 0; a < A; ++a)
+      if (d->entities[z].terminate_chars[a]) H->td_per_cell = 1;
   H->off_tt = B->reserve((size_t)(A + 1) * S * 4);
   H->off_tr = B->reserve((size_t)(A + 1) * S * 4);
-  H->off_td = B->reserve((size_t)(A + 1) * 4);
+  H->off_td = B->reserve((size_t)(A + 1) * (H->td_per_cell ? S : 1) * 4);
   {
     uint32_t* tt = (uint32_t*)&B->bytes[H->off_tt];
     float* tr = (float*)&B->bytes[H->off_tr];
     float* td = (float*)&B->bytes[H->off_td];
     for (int a = 0; a <= A; ++a) {
-      td[a] = a < A ? H->act.discount[a] : 1.0f;
+      if (!H->td_per_cell) td[a] = a < A ? H->act.discount[a] : 1.0f;
       for (int p = 0; p <= cells; ++p) {
         int q = p;
-        float reward = 0.0f;
+        float reward = 0.0f, disc = 1.0f;
         uint32_t flags = CX_FLAG_BAD_ACTION | CX_FLAG_REWARD_NONE;  // row A: env left untouched
         if (a < A) {
           const AgentStep st = agent_step_host(d, agent_z, order, basech.data(), vis.data(), a, p);
           q = st.q;
           reward = st.reward;
-          flags = (H->act.over[a] ? CX_FLAG_TERMINATED : 0) | (H->act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+          disc = st.discount;
+          flags = (st.over ? CX_FLAG_TERMINATED : 0) | (H->act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
         }
+        if (H->td_per_cell) td[a * S + p] = disc;
         const int shown = (q < cells && vis[q]) ? q : cells;
         tt[a * S + p] = (uint32_t)q | ((uint32_t)shown << 8) | (flags << 16);
         tr[a * S + p] = reward;
@@ -432,9 +469,24 @@ static void build_agent_tables(const cx_game_desc* d, int agent_z, const int* or
     B->bytes[H->off_basek + c] = (uint8_t)(k < 0 ? 0xFF : k);
   }
   H->off_baselay = B->reserve((size_t)L * cells);
-  for (int c = 0; c < cells; ++c) {
-    const int k = char_index(d, basech[c]);
-    if (k >= 0) B->bytes[H->off_baselay + (size_t)k * cells + c] = 1;
+  H->unoccluded = d->unoccluded_layers ? 1 : 0;
+  if (!H->unoccluded) {
+    for (int c = 0; c < cells; ++c) {
+      const int k = char_index(d, basech[c]);
+      if (k >= 0) B->bytes[H->off_baselay + (size_t)k * cells + c] = 1;
+    }
+  } else {  // rendering.py:283-286,333: the backdrop's own cells, then every static drape's whole curtain
+    for (int c = 0; c < cells; ++c) {
+      const int k = char_index(d, d->backdrop[c]);
+      if (k >= 0) B->bytes[H->off_baselay + (size_t)k * cells + c] = 1;
+    }
+    for (int z = 0; z < d->n_entities; ++z) {
+      if (z == agent_z) continue;
+      const int k = char_index(d, d->entities[z].character);
+      for (int c = 0; c < cells; ++c) B->bytes[H->off_baselay + (size_t)k * cells + c] = d->masks[(size_t)z * cells + c] ? 1 : 0;
+    }
+    const int ka = char_index(d, ag.character);   // the agent's plane holds the agent only
+    for (int c = 0; c < cells; ++c) B->bytes[H->off_baselay + (size_t)ka * cells + c] = 0;
   }
   B->pad();
   H->blob_bytes_ext = (int32_t)B->bytes.size();
@@ -485,6 +537,13 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
     memcpy(g.dc, e.move_dc, CX_MAX_ACTIONS);
     memcpy(g.step_reward, e.step_reward, sizeof(g.step_reward));
     memcpy(g.vis_op, e.visible_op, CX_MAX_ACTIONS);
+    g.terminate_actions = e.terminate_actions;
+    g.discount_actions = e.discount_actions;
+    memcpy(g.discount_value, e.discount_value, sizeof(g.discount_value));
+    memcpy(g.term_chars, e.terminate_chars, sizeof(g.term_chars));
+    memcpy(g.term_value, e.terminate_value, sizeof(g.term_value));
+    for (int a = 0; a < d->n_actions; ++a)
+      if (e.terminate_chars[a]) H->cond_term = 1;
     g.dyn_slot = 0xFF;
     if (e.kind != CX_KIND_STATIC) {
       if (n_dyn >= CX_MAX_DYN) {
@@ -814,6 +873,12 @@ extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
     build_agent_tables(desc, agent_z, order, &g->ah, &blob);
   } else {
     g->path = CX_PATH_GENERIC;
+    if (desc->unoccluded_layers) {
+      cx_set_error("occlusion_in_layers=False is implemented for single-agent games (one moving one-cell drape over "
+                   "static entities); this game needs the generic kernels");
+      delete g;
+      return CX_ERR_UNSUPPORTED;
+    }
     rc = build_generic_tables(desc, order, &g->gh, &blob);
     if (rc != CX_OK) {
       delete g;
@@ -822,7 +887,10 @@ extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
   }
   const CxActionTable& act = g->path == CX_PATH_AGENT ? g->ah.act : g->gh.act;
   bool can_term = false;
-  for (int a = 0; a < desc->n_actions; ++a) can_term |= act.over[a] != 0;
+  for (int a = 0; a < desc->n_actions; ++a) {
+    can_term |= act.over[a] != 0;
+    for (int z = 0; z < desc->n_entities; ++z) can_term |= desc->entities[z].terminate_chars[a] != 0;
+  }
   const int tracks = (can_term || desc->max_episode_steps > 0 || desc->track_returns) ? 1 : 0;
   if (g->path == CX_PATH_AGENT)
     g->ah.track = tracks;
@@ -933,8 +1001,10 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     cx_set_error("%s: env_offset must be a multiple of 4", who);
     return CX_ERR_INVALID_ARG;
   }
-  if (g->path == CX_PATH_AGENT && T == 1 && !synth.on && step_composer_enabled() &&
-      cx_agent_step_applies(g, d_board, nullptr))   // one step: the stateless composer (cx_agent_step_kernels.cu)
+  // one step of a small batch: the stateless composer (cx_agent_step_kernels.cu) -- 2.5 against 3.1 us at 4,096 envs,
+  // equal at 65,536; large batches amortise the tile staging over enough envs (2^20: 11 us against 28 us)
+  if (g->path == CX_PATH_AGENT && T == 1 && !synth.on && n < 65536 && step_composer_enabled() &&
+      cx_agent_step_applies(g, d_board, nullptr))
     return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, nullptr, CX_DTYPE_U8,
                                 (cudaStream_t)stream);
   if (g->path == CX_PATH_AGENT) {
@@ -943,7 +1013,7 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     // measured on Demo 1: 16,384 envs 0.052 -> 0.020 ms per 32 steps, 65,536 0.052 -> 0.043, 2^18 0.111 -> 0.070,
     // equal at 2^19, and 0.185 against 0.276 at 2^20 (scripts/small_batch_time.py).  CX_AGENT_SMALL_N overrides the
     // threshold (0: always k_agent_rollout).
-    int64_t small_n = (int64_t)g->sm_count * 7 * 1024 / 2;
+    int64_t small_n = 32768;
     if (const char* dbg = getenv("CX_AGENT_SMALL_N")) small_n = atoll(dbg);
     if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS || n < small_n)  // large boards, small batches: lane-per-env kernel, board only
       return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
@@ -998,6 +1068,11 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
     return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, none, d_reward, d_discount, d_flags, d_board,
                                        d_layered, (cudaStream_t)stream);
   }
+  if (g && g->desc.unoccluded_layers) {
+    cx_set_error("cx_rollout_observations: unoccluded layers need the fused kernels (16-byte aligned buffers, "
+                 "boards that fit the lane-per-env kernel)");
+    return CX_ERR_UNSUPPORTED;
+  }
   // any other game or geometry: the step kernel, then the layers from the finished boards
   int rc = cx_rollout(g, d_state, n, T, d_actions, d_reward, d_discount, d_flags, d_board, stream);
   if (rc) return rc;
@@ -1028,6 +1103,10 @@ extern "C" int cx_step_observations(const cx_game* g, void* d_state, int64_t n, 
   if (dtype == CX_DTYPE_U8)
     return cx_rollout_observations(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board,
                                    static_cast<uint8_t*>(d_layered), stream);
+  if (g->desc.unoccluded_layers) {
+    cx_set_error("cx_step_observations: unoccluded float planes need 16-byte aligned buffers");
+    return CX_ERR_UNSUPPORTED;
+  }
   if (dtype == CX_DTYPE_BF16) {
     cx_set_error("cx_step_observations: bfloat16 planes are emitted by the single-agent step kernel only "
                  "(16-byte aligned buffers); use CX_DTYPE_F32 for this game");
@@ -1036,6 +1115,28 @@ extern "C" int cx_step_observations(const cx_game* g, void* d_state, int64_t n, 
   rc = cx_rollout(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board, stream);
   if (rc) return rc;
   return cx_layers_from_board_f32(g, d_board, n, static_cast<float*>(d_layered), stream);
+}
+
+extern "C" int cx_render_observations(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board,
+                                      void* d_layered, int32_t dtype, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_render_observations");
+  if (rc) return rc;
+  if (!d_board || !d_layered || (dtype != CX_DTYPE_U8 && dtype != CX_DTYPE_F32 && dtype != CX_DTYPE_BF16)) {
+    cx_set_error("cx_render_observations: board/layered must not be NULL, layered_dtype must be a cx_dtype");
+    return CX_ERR_INVALID_ARG;
+  }
+  if (cx_agent_step_applies(g, d_board, d_layered))   // the composer with nothing to step
+    return cx_launch_agent_step(g, const_cast<void*>(d_state), n, nullptr, nullptr, nullptr, nullptr, d_board, d_layered,
+                                dtype, (cudaStream_t)stream);
+  if (g->desc.unoccluded_layers || dtype == CX_DTYPE_BF16) {
+    cx_set_error("cx_render_observations: this game / element type needs the single-agent composer (16-byte aligned "
+                 "buffers)");
+    return CX_ERR_UNSUPPORTED;
+  }
+  rc = cx_launch_render(g, d_state, n, d_board, (cudaStream_t)stream);
+  if (rc) return rc;
+  return dtype == CX_DTYPE_U8 ? cx_layers_from_board(g, d_board, n, static_cast<uint8_t*>(d_layered), stream)
+                              : cx_layers_from_board_f32(g, d_board, n, static_cast<float*>(d_layered), stream);
 }
 
 extern "C" int cx_get_entity_state(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_cells,

@@ -228,6 +228,12 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
   }
   float summed = 0.0f;
   bool first = true;
+  bool over = H.act.over[a] != 0;      // directives: per-action tables, unless some terminate_episode call depends
+  float pdisc = H.act.discount[a];     // on where a watched entity stands (then replayed in update order below)
+  if (H.cond_term) {
+    over = false;
+    pdisc = 1.0f;
+  }
   int group = H.n_ent > 0 ? H.ent[H.update_order[0]].group : 0;
   for (int i = 0; i < H.n_ent; ++i) {
     const int z = H.update_order[i];
@@ -282,6 +288,23 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
       summed = first ? r : __fadd_rn(r, summed);  // plot.py:208-211
       first = false;
     }
+    if (H.cond_term) {  // plot.py:161-184,232-257: the last call of the step wins
+      if ((e.discount_actions >> a) & 1u) pdisc = e.discount_value[a];
+      if ((e.terminate_actions >> a) & 1u) {
+        over = true;
+        pdisc = e.discount_value[a];
+      }
+      if (e.term_chars[a] && e.watch != 0xFF) {
+        const uint32_t wc = st[H.ent[e.watch].dyn_slot];
+        if (wc != CX_EMPTY_CELL16) {
+          const uint8_t k = X.chidx[overlay(X, prev, (int)wc, backdrop_at(X, prev, plane, (int)wc))];
+          if (k != 0xFF && ((e.term_chars[a] >> k) & 1u)) {
+            over = true;
+            pdisc = e.term_value[a];
+          }
+        }
+      }
+    }
   }
   stamp(X, st, plane);  // the render that produces this step's observation
   if (H.slot_zperm >= 0 && H.n_zdir[a]) {  // engine.py:242-281, then the re-render of engine.py:163
@@ -292,8 +315,8 @@ __device__ void generic_env_step(const Ctx& X, uint32_t a, uint16_t* st, uint16_
     stamp(X, st, plane);
   }
   reward = summed;
-  disc = H.act.discount[a];
-  flags = (H.act.over[a] ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
+  disc = pdisc;
+  flags = (over ? CX_FLAG_TERMINATED : 0) | (H.act.reward_none[a] ? CX_FLAG_REWARD_NONE : 0);
 }
 
 // Engine.play() of a game whose entities never consult the last render (CxGenHeader::simple_step): every
@@ -1104,8 +1127,8 @@ bool gen_vec_ok(const cx_game* g, int64_t n, const void* d_board) {
 }
 
 int configure_once() {
-  static bool configured = false;
-  if (!configured) {
+  static CxPerDevice configured;
+  if (configured.need()) {
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<false, NT, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, NT, CX_GEN_MIN_CTAS + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1114,7 +1137,7 @@ int configure_once() {
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_rollout<true, kWaveThreads, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     (int)cudaSharedmemCarveoutMaxShared));
     CX_CUDA_OK(cudaFuncSetAttribute(k_generic_render, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
+    configured.mark();
   }
   return CX_OK;
 }

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "campx_b200.h"
 
 #define CX_PATH_AGENT 1    // exactly one moving one-cell drape over a static scene (boat_race, Demo 1-5)
@@ -52,7 +54,11 @@ struct CxAgentHeader {
   int32_t off_tt;           // u32 [n_actions+1][cells+1]: bits 0-7 new cell, 8-15 cell where the agent is drawn
                             //     afterwards (cells: not drawn), 16-23 CX_FLAG_* of the step
   int32_t off_tr;           // f32 [n_actions+1][cells+1]: step reward
-  int32_t off_td;           // f32 [n_actions+1]: plot discount returned with the action
+  int32_t off_td;           // f32 [n_actions+1]: plot discount returned with the action; or, when td_per_cell,
+                            //     f32 [n_actions+1][cells+1] like off_tr (games that terminate on reaching a cell)
+  int32_t td_per_cell;
+  int32_t unoccluded;       // cx_game_desc::unoccluded_layers: baselay is the UNOCCLUDED static image (backdrop cells +
+                            // whole static curtains) and the agent only ever toggles its own plane, at its real cell
   int32_t off_basech;       // u8  [cells+1]  board character without the agent
   int32_t off_shown;        // u8  [cells+1]  cell where an agent standing on c is drawn (cells: occluded/none)
   int32_t off_pat;          // u8  [cells][16]  base board bytes starting at phase o (wraps): tile fill pattern
@@ -81,6 +87,11 @@ struct CxGenEntity {
   uint16_t init_state;      // cell / linear offset after its_showtime
   uint16_t pad2;
   uint8_t vis_op[CX_MAX_ACTIONS];  // sprites: cx_visible_op per action
+  // directives evaluated per step only by games with a conditional terminate_episode (CxGenHeader::cond_term)
+  uint8_t terminate_actions, discount_actions, pad3[2];
+  float discount_value[CX_MAX_ACTIONS];
+  uint32_t term_chars[CX_MAX_ACTIONS];   // cx_entity_desc::terminate_chars
+  float term_value[CX_MAX_ACTIONS];
 };
 
 struct CxGenHeader {
@@ -88,7 +99,8 @@ struct CxGenHeader {
   int32_t mask_words;       // ceil(cells / 32)
   int32_t has_dynbd;        // quirk Q1(i): per-env backdrop plane
   int32_t zero_backdrop;    // quirk Q1(ii): no drape at all => canvas is zeroed every render
-  int32_t needs_prev;       // some entity consults the last render (blockers / entry rewards)
+  int32_t needs_prev;       // some entity consults the last render (blockers / entry rewards / conditional terminate)
+  int32_t cond_term;        // some entity terminates the episode depending on what its watched entity reached
   int32_t max_steps, auto_reset, track;
   uint8_t update_order[CX_MAX_ENTITIES];  // z-indices in update order
   uint8_t chars[CX_MAX_CHARS];
@@ -184,6 +196,22 @@ void cx_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// Function attributes (the dynamic shared-memory cap) are set per DEVICE: remember, per call site, on which devices
+// it has been done (bit = device ordinal; ordinals >= 64 are configured on every launch).  Safe to use from several
+// host threads: configuring twice is harmless, launching unconfigured is not.
+struct CxPerDevice {
+  std::atomic<uint64_t> done{0};
+  int dev = -1;
+  bool need() {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    return !(done.load(std::memory_order_acquire) & (1ull << dev));
+  }
+  void mark() {
+    int d = -1;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) done.fetch_or(1ull << d, std::memory_order_release);
+  }
+};
+
 // synthetic-action request: when `on`, kernels generate actions (cx_philox.cuh) instead of reading them
 struct CxSynth {
   int on;
@@ -201,6 +229,7 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
 bool cx_agent_obs_applies(const cx_game* g, bool layers);
 // one Engine.play() per launch, stateless composer (cx_agent_step_kernels.cu); lay_dtype: CX_DTYPE_* of d_layered
 bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_layered);
+// d_actions == nullptr: render only (nothing is stepped, the state is not written)
 int cx_launch_agent_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
                          float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* d_layered, int lay_dtype,
                          cudaStream_t s);

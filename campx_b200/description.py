@@ -31,6 +31,8 @@ class EntitySpec:
     watch: Optional[str] = None           # character of the watched CELL/SPRITE entity
     entry_reward: Optional[Dict[int, Dict[str, float]]] = None   # action -> {char seen: extra reward}
     terminate: Optional[Dict[int, float]] = None          # action -> discount passed to terminate_episode
+    terminate_on: Optional[Dict[int, Dict[str, float]]] = None   # action -> {char seen under `watch`: discount}:
+                                                          # terminate_episode called only there ("reach the goal")
     discount: Optional[Dict[int, float]] = None           # action -> change_default_discount value
     visible_op: Optional[List[int]] = None                # sprites, per action: CX_VIS_* applied to Sprite.visible
     z_orders: Optional[Dict[int, List[tuple]]] = None     # action -> [(move_this, in_front_of_that or None), ...]
@@ -49,6 +51,9 @@ class EntitySpec:
             out["entry_reward"] = {a: dict(sorted(v.items())) for a, v in sorted((self.entry_reward or {}).items()) if v}
         if self.terminate:
             out["terminate"] = dict(self.terminate)
+        if self.terminate_on:
+            out["watch"] = self.watch
+            out["terminate_on"] = {a: dict(sorted(v.items())) for a, v in sorted(self.terminate_on.items())}
         if self.discount:
             out["discount"] = dict(self.discount)
         if self.kind == N.CX_KIND_SPRITE:
@@ -77,6 +82,7 @@ class GameSpec:
     first_discount: float = 1.0
     action_format: str = "index"          # how the world's update() methods take actions (host side only)
     backdrop_moves: Optional[List[tuple]] = None   # per action (d_row, d_col): Backdrop.update() rolls its curtain
+    occlusion_in_layers: bool = True      # False: unoccluded layers (engine.py:31, rendering.py:227-353)
 
     def summary(self):
         return {"rows": self.rows, "cols": self.cols, "chars": self.chars, "n_actions": self.n_actions,
@@ -147,6 +153,15 @@ class GameSpec:
                     ta |= 1 << a
                     c.discount_value[a] = float(e.terminate[a])
             c.reward_actions, c.terminate_actions, c.discount_actions = ra, ta, da
+            for a, table in (e.terminate_on or {}).items():
+                values = set(table.values())
+                if len(values) != 1:
+                    raise NotImplementedError("terminate_episode discounts that depend on the character reached")
+                c.terminate_value[a] = float(values.pop())
+                bits = 0
+                for ch in table:
+                    bits |= 1 << self.chars.index(ch)
+                c.terminate_chars[a] = bits
             for a in range(self.n_actions):
                 c.visible_op[a] = int(e.visible_op[a]) if e.visible_op else N.CX_VIS_KEEP
                 zd = (e.z_orders or {}).get(a) or []
@@ -168,4 +183,5 @@ class GameSpec:
         d.first_discount = float(self.first_discount)
         for a, (dr, dc) in enumerate(self.backdrop_moves or []):
             d.backdrop_dr[a], d.backdrop_dc[a] = int(dr), int(dc)
+        d.unoccluded_layers = 0 if self.occlusion_in_layers else 1
         return d, (backdrop, masks)

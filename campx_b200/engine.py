@@ -43,10 +43,12 @@ class Engine(object):
 
     def __init__(self, rows, cols, occlusion_in_layers=True, num_envs=None, device=None, num_actions=5,
                  action_format=None, max_episode_steps=0, auto_reset=None, track_returns=False, verify=True):
-        if not occlusion_in_layers:
-            # the reference's unoccluded renderer is itself broken (rendering.py:227-353 returns a
-            # 2-field Observation); SURVEY section 2 row 5 puts it out of scope
-            raise NotImplementedError('occlusion_in_layers=False is not supported')
+        # occlusion_in_layers=False (engine.py:31,528): layers follow the intent of the reference's
+        # BaseUnoccludedObservationRenderer (rendering.py:227-353) -- a layer is its entity's whole curtain / cell, or
+        # the backdrop's own cells, occluded or not; the board is unchanged.  The reference's implementation cannot
+        # run (numpy calls on tensors, a 2-field Observation at :348); here the Observation keeps its three fields.
+        # Implemented for single-agent games (the kernels write such layers themselves: they are not a function of
+        # the board); other games raise NotImplementedError at its_showtime().
         self._rows = int(rows)
         self._cols = int(cols)
         self._backdrop = None
@@ -155,11 +157,12 @@ class Engine(object):
                   for key in sorted(self._update_groups.keys(), key=lambda k: ('' if k is None else str(k)))]
         self._update_groups = groups
         self._current_update_group = None
-        self._shadow = ShadowEngine(self._rows, self._cols, self._backdrop, self._sprites_and_drapes, groups)
+        self._shadow = ShadowEngine(self._rows, self._cols, self._backdrop, self._sprites_and_drapes, groups,
+                                    occlusion_in_layers=self._occlusion_in_layers)
         self._the_plot = self._shadow.the_plot
         self._spec = compile_game(self._shadow, n_actions=self._num_actions, action_format=self._action_format,
                                   max_episode_steps=self._max_episode_steps, auto_reset=self._auto_reset,
-                                  track_returns=self._track_returns)
+                                  track_returns=self._track_returns, occlusion_in_layers=self._occlusion_in_layers)
         return self._spec
 
     def its_showtime(self):
@@ -182,7 +185,7 @@ class Engine(object):
         self._last_obs = None
         self._out_board, self._out_reward, self._out_flags, self._out_discount = self._out_sets[0]
         self._ones = None
-        nat.render(self._out_board)
+        first_layered = self._render_first_frame()
         self._game_over = False
         reward = self._spec.first_reward
         if self._batched and reward is not None:
@@ -190,8 +193,28 @@ class Engine(object):
         discount = self._spec.first_discount
         if self._batched:
             discount = torch.full((self._num_envs,), discount, dtype=torch.float32, device=nat.device)
-        self._last_obs = self._observation(self._out_board)
+        self._last_obs = self._observation(self._out_board, first_layered)
         return self._last_obs, reward, discount
+
+    def _render_first_frame(self):
+        """Board of the current state into the current output set; unoccluded games also get their layers here
+        (they cannot be derived from the board later).  Returns the layered board or None (lazy)."""
+        nat = self._native
+        if self._occlusion_in_layers:
+            nat.render(self._out_board)
+            return None
+        layered = self._layered_buffer(torch.uint8)
+        nat.render_observations(self._out_board, layered)
+        return layered
+
+    def _layered_buffer(self, dtype):
+        if self._layered_sets is None:
+            self._layered_sets = {}
+        key = (dtype, self._out_index)
+        if key not in self._layered_sets:
+            shape = (self._num_envs, self._native.n_chars, self._rows, self._cols)
+            self._layered_sets[key] = torch.empty(shape, dtype=dtype, device=self._native.device)
+        return self._layered_sets[key]
 
     def play(self, actions):
         if not self._showtime:
@@ -212,16 +235,13 @@ class Engine(object):
         if want is not None and want not in (torch.uint8, torch.float32) and not (
                 want == torch.bfloat16 and nat.info.path == N.CX_PATH_AGENT):
             want = None                 # a dtype the step kernel does not emit for this game: stays lazy
+        if not self._occlusion_in_layers:
+            want = torch.uint8          # unoccluded layers are not a function of the board: always written by the
+                                        # step kernel (uint8; other dtypes are conversions of these planes)
         if want is not None:
             # board and layered board (uint8, or float32 / bfloat16 planes: the policy input of
             # examples/actor_critic.py:147,173) leave the step kernel together: cx_step_observations
-            if self._layered_sets is None:
-                self._layered_sets = {}
-            key = (want, self._out_index)
-            if key not in self._layered_sets:
-                shape = (self._num_envs, nat.n_chars, self._rows, self._cols)
-                self._layered_sets[key] = torch.empty(shape, dtype=want, device=nat.device)
-            layered = self._layered_sets[key]
+            layered = self._layered_buffer(want)
             nat.step_observations(idx, self._out_board, layered, self._out_reward, self._out_flags, self._out_discount)
             if want == torch.uint8:
                 obs = self._observation(self._out_board, layered)
@@ -302,8 +322,7 @@ class Engine(object):
             mask = mask.to(torch.uint8)
         self._native.reset(mask)
         self._game_over = False
-        self._native.render(self._out_board)
-        return self._observation(self._out_board)
+        return self._observation(self._out_board, self._render_first_frame())
 
     # ------------------------------------------------------------------------------------------------
     # introspection
@@ -377,6 +396,11 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------------
     def _observation(self, board, layered=None):
         nat = self._native
+        if not self._occlusion_in_layers:
+            # pre-filled by the kernel that made the frame; other dtypes are conversions of those uint8 planes
+            lay = layered if self._batched else layered[0]
+            return Observation(board if self._batched else board[0], self._spec.chars,
+                               lambda b, dtype=torch.uint8: lay.to(dtype), lay)
         if self._batched:
             return Observation(board, self._spec.chars,
                                lambda b, dtype=torch.uint8: nat.layers_from_board(b, dtype=dtype), layered)
@@ -406,12 +430,23 @@ class Engine(object):
                 raise ValueError('expected {} action indices, got shape {}'.format(n, tuple(actions.shape)))
             if actions.dtype.is_floating_point:
                 raise ValueError('action indices must be integers; pass one-hot actions as [num_envs, num_actions]')
-            return actions.contiguous() if actions.dtype == torch.uint8 else actions.to(torch.uint8)
+            if actions.dtype == torch.uint8:
+                return actions.contiguous()
+            # indices that do not fit a byte must not wrap into the action set: 255 = "outside" (CX_FLAG_BAD_ACTION)
+            if actions.dtype == torch.bool:
+                return actions.to(torch.uint8)
+            return actions.masked_fill((actions < 0) | (actions > 255), 255).to(torch.uint8)
         if tuple(actions.shape) != (n, A):
             raise ValueError('expected one-hot actions of shape ({}, {}), got {}'.format(n, A, tuple(actions.shape)))
-        idx, bad = nat.onehot_to_index(actions.to(torch.float32).contiguous())
-        self._bad_onehot = bad          # int32[1] on device; checked lazily (no sync on the step path)
+        # rows that are not exactly one-hot come back as index 255: those envs are left untouched and flagged
+        # CX_FLAG_BAD_ACTION (the single-env mode and the reference's `assert sum(act) == 1` raise instead)
+        idx, self._bad_onehot = nat.onehot_to_index(actions.to(torch.float32).contiguous())
         return idx
+
+    def bad_action_count(self):
+        """Number of one-hot rows of the last batched play() that were not exactly one-hot (synchronises)."""
+        bad = getattr(self, '_bad_onehot', None)
+        return 0 if bad is None else int(bad.item())
 
     def _single_action_index(self, actions):
         A = self._num_actions

@@ -164,6 +164,17 @@ class NativeGame(object):
                                                    _ptr(discount), _ptr(flags), _ptr(board), _ptr(layered),
                                                    self._DTYPES[layered.dtype], _stream()))
 
+    def render_observations(self, board, layered):
+        """The frame of the CURRENT state with its layered board (first Observation / after a reset); no step."""
+        n = self.num_envs
+        self._check(board, torch.uint8, (n, self.rows, self.cols), "board")
+        if not isinstance(layered, torch.Tensor) or layered.dtype not in self._DTYPES:
+            raise ValueError("layered must be a uint8, float32 or bfloat16 tensor")
+        self._check(layered, layered.dtype, (n, self.n_chars, self.rows, self.cols), "layered")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_render_observations(self._handle, _ptr(self.state), n, _ptr(board), _ptr(layered),
+                                                     self._DTYPES[layered.dtype], _stream()))
+
     def sample_actions(self, scores, seed, step=None, step_offset=0, logits=False, env_offset=0, out=None, logp=None):
         """Categorical(probs).sample() for every env (examples/actor_critic.py:90-98) -> uint8 [n] action indices.
 

@@ -4,6 +4,11 @@
     ghost    sprites that hide and show themselves              campx/things.py:320,390-392, engine.py:315
     scroll   a `Backdrop` subclass whose `update()` scrolls it  campx/things.py:103-148
 
+plus two "reach the goal" worlds (`terminate_episode` that depends on where the agent stands):
+
+    goal     an agent, an exit `G` (reward 10, episode over) and a pit `X` (reward -5, over with discount 0.25)
+    goal2    the same with a drifting sprite, so that the game runs on the generic kernels
+
 written, like examples/worlds.py, as ordinary single-environment `Sprite` / `Drape` / `Backdrop`
 subclasses.  The same three worlds exist against the reference API (oracle/gen_golden.py, executed on the
 unmodified reference to record tests/golden/generality_*.json) and as numpy oracle entities
@@ -32,6 +37,19 @@ SCROLL_ART = ['A.~~.^',
               '.~..^.',
               '~..^..',
               '..^..~']
+
+
+GOAL_ART = ['######',
+            '#A  G#',
+            '# #  #',
+            '#   X#',
+            '######']
+
+GOAL2_ART = ['######',
+             '#A  G#',
+             '# #  #',
+             '#S  X#',
+             '######']
 
 
 def _rolled(curtain, shift, axis):
@@ -122,8 +140,43 @@ class Panorama(things.Backdrop):
             self.curtain.set_(_rolled(self.curtain, shift, axis))
 
 
+class Exit(things.Drape):
+    """A cell that ends the episode when the agent steps onto it: pays `prize` and calls
+    `terminate_episode(pcontinue)` (plot.py:161-184) -- the PyColab "reach the goal" idiom, written the way
+    boat_race's tiles watch the agent (boat_race.py:79-82)."""
+
+    def __init__(self, curtain, character, prize, pcontinue=0.0, agent='A'):
+        super(Exit, self).__init__(curtain, character)
+        self.prize, self.pcontinue, self.agent = prize, pcontinue, agent
+
+    def update(self, actions, board, layers, backdrop, all_things, the_plot):
+        if actions is None:
+            return
+        here = (all_things[self.agent].curtain * layers[self.character]).sum()
+        the_plot.add_reward(here * self.prize)
+        if here > 0:
+            the_plot.terminate_episode(self.pcontinue)
+
+
+class Drifter(things.Sprite):
+    """Moves one cell to the right (toroidally) every step."""
+
+    def update(self, actions, board, layers, backdrop, all_things, the_plot):
+        if actions is None:
+            return
+        self._position = self.Position(self.position.row, (self.position.col + 1) % self.corner.col)
+
+
 def make_generality_world(name, **engine_kwargs):
-    """Un-started Engine for one of: zswap, ghost, scroll."""
+    """Un-started Engine for one of: zswap, ghost, scroll, goal, goal2."""
+    if name in ('goal', 'goal2'):
+        drapes = {'A': Partial(Walker, walls='#', per_step=-1, strict=True), '#': things.FixedDrape,
+                  'G': Partial(Exit, 10), 'X': Partial(Exit, -5, 0.25)}
+        if name == 'goal':
+            return ascii_art_to_game(GOAL_ART, ' ', drapes=drapes, update_schedule='AGX#', z_order='GXA#',
+                                     **engine_kwargs)
+        return ascii_art_to_game(GOAL2_ART, ' ', sprites={'S': Drifter}, drapes=drapes,
+                                 update_schedule='ASGX#', z_order='GXAS#', **engine_kwargs)
     if name == 'zswap':
         return ascii_art_to_game(ZSWAP_ART, '.', sprites={'S': Climber},
                                  drapes={'X': Shuffler, 'Y': things.FixedDrape},

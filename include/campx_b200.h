@@ -118,6 +118,12 @@ typedef struct cx_entity_desc {
                               at the watched entity's current cell (boat_race.py:79-87: k == own
                               char; Demo 3 cell 3: k in reward_chars)                            */
   float discount_value[CX_MAX_ACTIONS]; /* argument of terminate_episode / change_default_discount */
+  uint32_t terminate_chars[CX_MAX_ACTIONS];
+                           /* "reach the goal" games: bit k set => for action a update() calls
+                              the_plot.terminate_episode(terminate_value[a]) (plot.py:161-184) when game char k was
+                              visible, in the last render, at the watched entity's current cell (same `watch`
+                              and same cell query as entry_reward)                                             */
+  float terminate_value[CX_MAX_ACTIONS]; /* discount passed by that conditional terminate_episode call     */
   /* --- engine generality: state that the six reference worlds keep constant --- */
   uint8_t visible_op[CX_MAX_ACTIONS];
                            /* SPRITE: what update() does to Sprite.visible (things.py:320,390-392) for
@@ -158,6 +164,13 @@ typedef struct cx_game_desc {
   float first_discount;    /* ... and discount                                                    */
   int8_t backdrop_dr[CX_MAX_ACTIONS]; /* Backdrop.update() (things.py:103-148) rolls its curtain toroidally */
   int8_t backdrop_dc[CX_MAX_ACTIONS]; /*   by this much for action a (scrolling scenery); 0: static         */
+  int32_t unoccluded_layers; /* Engine(occlusion_in_layers=False) (engine.py:31,528): layers follow the intent of
+                              BaseUnoccludedObservationRenderer (rendering.py:227-353) -- layers[ch] is the whole
+                              curtain of drape ch / the cell of sprite ch / the backdrop cells holding ch, whether or
+                              not something is painted over them; the board is unchanged.  Such layers are not a
+                              function of the board: they are written by cx_step_observations /
+                              cx_rollout_observations / cx_render_observations only (single-agent games; others are
+                              CX_ERR_UNSUPPORTED), and cx_layers_from_board refuses the game.  0: occluded (default) */
 } cx_game_desc;
 
 typedef struct cx_game cx_game; /* opaque */
@@ -238,6 +251,11 @@ CX_API int cx_rollout_observations(const cx_game* game, void* d_state, int64_t n
                             const uint8_t* d_actions, float* d_reward, float* d_discount, uint8_t* d_flags,
                             uint8_t* d_board, uint8_t* d_layered, void* stream);
 
+/* Render the current state with its layered board (the whole first Observation of its_showtime / after a reset):
+ * d_board [n, rows*cols] uint8 and d_layered [n, n_chars, rows*cols] of `layered_dtype`.  Nothing is stepped. */
+CX_API int cx_render_observations(const cx_game* game, const void* d_state, int64_t n_envs, uint8_t* d_board,
+                           void* d_layered, int32_t layered_dtype, void* stream);
+
 /* Element type of a layered board written by cx_step_observations. */
 typedef enum cx_dtype {
   CX_DTYPE_U8 = 0,   /* the reference's layers dtype (rendering.py:204-209)                        */
@@ -278,8 +296,10 @@ CX_API int cx_board_mapper_destroy(cx_board_mapper* mapper);
 CX_API int cx_board_mapper_apply(const cx_board_mapper* mapper, const uint8_t* d_board, int64_t n_boards, int32_t rows,
                           int32_t cols, const int32_t* permute, void* d_out, int32_t* d_unknown, void* stream);
 
-/* One-hot (or any argmax-able) float actions [n, n_actions] -> uint8 indices; rows that are not
- * exactly one-hot (boat_race.py:48 `assert sum(act) == 1`) set *d_bad_count (int32, device) += 1. */
+/* One-hot float actions [n, n_actions] -> uint8 indices.  A row that is not exactly one-hot (boat_race.py:48
+ * `assert sum(act) == 1`: no 1, several 1s, fractional entries) becomes index 255, which every step kernel treats as
+ * "outside the action set" (env untouched, CX_FLAG_BAD_ACTION), and adds 1 to *d_bad_count (int32, device, may be
+ * NULL). */
 CX_API int cx_onehot_to_index(const float* d_onehot, int64_t n_envs, int32_t n_actions, uint8_t* d_index,
                        int32_t* d_bad_count, void* stream);
 

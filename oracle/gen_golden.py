@@ -60,7 +60,7 @@ def encode_action(world, index):
         return int(index)
     onehot = [0] * 5
     onehot[int(index)] = 1
-    if world in ("boat_race", "demo4", "scroll"):
+    if world in ("boat_race", "demo4", "scroll", "goal", "goal2"):
         return torch.FloatTensor(onehot)
     return onehot
 
@@ -91,7 +91,9 @@ SCROLL_ART = ["A.~~.^",
               ".~..^.",
               "~..^..",
               "..^..~"]
-GENERALITY_WORLDS = ("zswap", "ghost", "scroll")
+GOAL_ART = ["######", "#A  G#", "# #  #", "#   X#", "######"]
+GOAL2_ART = ["######", "#A  G#", "# #  #", "#S  X#", "######"]
+GENERALITY_WORLDS = ("zswap", "ghost", "scroll", "goal", "goal2")
 
 
 def make_ref_generality_game(world):
@@ -170,6 +172,41 @@ def make_ref_generality_game(world):
         return ascii_art_to_game(GHOST_ART, ".",
                                  sprites={"G": Partial(Ghost, True, 1, 1), "H": Partial(Ghost, False, 1, -1)},
                                  drapes={"@": Rain}, update_schedule="GH@", z_order="GH@")
+    if world in ("goal", "goal2"):
+        # "reach the goal": a tile watches the agent (like boat_race.py:79-82) and calls terminate_episode
+        # (plot.py:161-184) when the agent stands on it
+        import boat_race
+
+        class Seeker(boat_race.AgentDrape):       # the reference's own agent, walls '#'
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                super(Seeker, self).update(actions, board, layers, backdrop, all_things, the_plot)
+                if actions is not None:
+                    the_plot.add_reward(-1)
+
+        class Exit(things.Drape):
+            def __init__(self, curtain, character, prize, pcontinue=0.0):
+                super(Exit, self).__init__(curtain, character)
+                self.prize, self.pcontinue = prize, pcontinue
+
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                here = (all_things["A"].curtain * layers[self.character]).sum()
+                the_plot.add_reward(here * self.prize)
+                if here > 0:
+                    the_plot.terminate_episode(self.pcontinue)
+
+        class Drifter(things.Sprite):
+            def update(self, actions, board, layers, backdrop, all_things, the_plot):
+                if actions is None:
+                    return
+                self._position = self.Position(self.position.row, (self.position.col + 1) % self.corner.col)
+
+        drapes = {"A": Seeker, "#": things.FixedDrape, "G": Partial(Exit, 10), "X": Partial(Exit, -5, 0.25)}
+        if world == "goal":
+            return ascii_art_to_game(GOAL_ART, " ", drapes=drapes, update_schedule="AGX#", z_order="GXA#")
+        return ascii_art_to_game(GOAL2_ART, " ", sprites={"S": Drifter}, drapes=drapes,
+                                 update_schedule="ASGX#", z_order="GXAS#")
     if world == "scroll":
         import boat_race
 
@@ -371,6 +408,11 @@ def main():
         "scroll": dict(scripted=[("each_action", [0, 1, 1, 2, 3, 3, 4, 1, 1, 1, 3, 0, 2, 2])],
                        n_random=3, random_len=60, seed=23, action_hi=5),
     }
+    # paths to the exit (3 x right) and to the pit (down, down, right x 3), then random walks that end early
+    gen_jobs["goal"] = dict(scripted=[("to_exit", [1, 1, 1, 4]), ("to_pit", [3, 3, 1, 1, 1, 4]), ("bump", [0, 2, 4, 1, 3, 3])],
+                            n_random=6, random_len=40, seed=24, action_hi=5)
+    gen_jobs["goal2"] = dict(scripted=[("to_exit", [1, 1, 1, 4]), ("to_pit", [3, 3, 1, 1, 1, 4])],
+                             n_random=6, random_len=40, seed=25, action_hi=5)
     for world, kw in gen_jobs.items():
         fx = world_fixture(world, **kw)
         path = os.path.join(GOLDEN_DIR, "generality_" + world + ".json")

@@ -1,0 +1,101 @@
+"""Development aid (round 2): single-step latency and small/mid-batch throughput of the single-agent kernels.
+Usage: python scripts/r02_probe.py [step|ring|obs]..."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from campx_b200.runtime import NativeGame
+from tests.expected_specs import expected_spec
+
+
+def timed(fn, lead, count):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    for i in range(lead): fn(i)
+    e0.record()
+    for i in range(count): fn(lead + i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / count
+
+
+def graph_of(fn, k):
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(k): fn(i)
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(k): fn(i)
+    return g
+
+
+def step_probe():
+    for n in (4096, 65536, 1 << 20):
+        for flat in ("1", "0"):
+            os.environ["CX_AGENT_STEP_FLAT"] = flat
+            g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+            nb = max(2, int(300e6 // (n * 31)) + 1)
+            bufs = [g.alloc_outputs() for _ in range(nb)]
+            acts = g.fill_actions(nb, seed=1)
+            gr = graph_of(lambda i: g.step(acts[i % nb], *bufs[i % nb]), nb)
+            ms = timed(lambda i: gr.replay(), 1, max(3, int(20 / (nb * 0.01)))) / nb
+            print("cx_step n=%d flat=%s: %.2f us/step  %.1f GB/s" % (n, flat, ms * 1e3, n * 31 / ms / 1e6), flush=True)
+        os.environ["CX_AGENT_STEP_FLAT"] = "1"
+        for dt in (torch.uint8, torch.float32, torch.bfloat16):
+            g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+            es = torch.empty((), dtype=dt).element_size()
+            per = 31 + 175 * es
+            nb = max(2, int(300e6 // (n * per)) + 1)
+            bufs = [g.alloc_outputs() for _ in range(nb)]
+            lay = [torch.empty((n, 7, 5, 5), dtype=dt, device="cuda") for _ in range(nb)]
+            acts = g.fill_actions(nb, seed=1)
+            gr = graph_of(lambda i: g.step_observations(acts[i % nb], bufs[i % nb][0], lay[i % nb], bufs[i % nb][1], bufs[i % nb][2]), nb)
+            ms = timed(lambda i: gr.replay(), 1, max(3, int(20 / (nb * 0.01)))) / nb
+            print("cx_step_observations n=%d %s: %.2f us/step  %.1f GB/s" % (n, dt, ms * 1e3, n * per / ms / 1e6), flush=True)
+
+
+def ring_probe():
+    T = 32
+    modes = {"tile256": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="256"), "tile128": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="128"),
+             "tile64": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="64"),
+             "lane_ring2": dict(CX_AGENT_SMALL_N=str(1 << 40), CX_OBS_RING="2"), "auto": dict()}
+    for world in ("demo1",):
+        for n in (4096, 16384, 32768, 65536, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
+            for mode, env in modes.items():
+                for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING"):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                g = NativeGame(expected_spec(world, max_episode_steps=100, track_returns=True), n)
+                nb = max(2, int(400e6 // (n * T * 31)) + 1)
+                bufs = [g.alloc_outputs(T) for _ in range(nb)]
+                acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+                gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), nb)
+                ms = timed(lambda i: gr.replay(), 1, max(3, int(30 / (nb * 0.03)))) / nb
+                print("%s n=%d T=%d %s: %.4f ms/launch  %.3e env-steps/s  %.0f GB/s (%.1f%%)" % (
+                    world, n, T, mode, ms, n * T / ms * 1e3, n * T * 31.44 / ms / 1e6, n * T * 31.44 / ms / 1e6 / 65.341), flush=True)
+                del g, bufs, acts, gr
+    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING"):
+        os.environ.pop(k, None)
+
+
+def obs_probe():
+    T = 16
+    for n in (4096, 65536, 1 << 18, 1 << 20):
+        for ring in ("1", "2"):
+            os.environ["CX_OBS_RING"] = ring
+            g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+            nb = max(2, int(400e6 // (n * T * 206)) + 1)
+            bufs = [g.alloc_outputs(T) for _ in range(nb)]
+            lay = [torch.empty((T, n, 7, 5, 5), dtype=torch.uint8, device="cuda") for _ in range(nb)]
+            acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+            gr = graph_of(lambda i: g.rollout_observations(acts[i % nb], bufs[i % nb][0], lay[i % nb], bufs[i % nb][1], bufs[i % nb][2]), nb)
+            ms = timed(lambda i: gr.replay(), 1, max(3, int(30 / (nb * 0.05)))) / nb
+            print("obs n=%d T=%d ring=%s: %.4f ms/launch  %.0f GB/s (%.1f%%)" % (n, T, ring, ms, n * T * 206 / ms / 1e6, n * T * 206 / ms / 1e6 / 65.341), flush=True)
+            del g, bufs, lay, acts, gr
+    os.environ.pop("CX_OBS_RING", None)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["step", "ring", "obs"]
+    if "step" in what: step_probe()
+    if "ring" in what: ring_probe()
+    if "obs" in what: obs_probe()

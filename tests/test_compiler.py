@@ -134,6 +134,71 @@ def test_engine_generality_primitives():
     assert s["backdrop_moves"] == [(0, -1), (0, 1), (-1, 0), (1, 0), (0, 0)]
 
 
+def test_reach_the_goal_games_compile_to_conditional_terminate():
+    """terminate_episode that depends on where the agent stands is fitted per (action, character under the
+    watched entity), like entry rewards; the pit passes its own discount."""
+    from examples.generality_worlds import make_generality_world
+    for world in ("goal", "goal2"):
+        s = make_generality_world(world).compile().summary()
+        ent = {e["char"]: e for e in s["entities"]}
+        assert ent["G"]["watch"] == "A" and ent["G"]["terminate_on"] == {1: {"G": 0.0}, 2: {"G": 0.0}}
+        assert ent["G"]["entry_reward"] == {1: {"G": 10.0}, 2: {"G": 10.0}} and "terminate" not in ent["G"]
+        assert ent["X"]["terminate_on"] == {1: {"X": 0.25}, 3: {"X": 0.25}}
+        assert ent["A"]["blockers"] == "#" and ent["A"]["step_reward"] == [-1.0] * 5
+    # the C ABI receives them as per-action character bit sets
+    desc, keep = make_generality_world("goal").compile().to_ctypes()
+    chars = make_generality_world("goal").compile().chars
+    g = [desc.entities[z] for z in range(desc.n_entities) if chr(desc.entities[z].character) == "G"][0]
+    assert [g.terminate_chars[a] for a in range(5)] == [0, 1 << chars.index("G"), 1 << chars.index("G"), 0, 0]
+    assert g.terminate_value[1] == 0.0
+
+
+def test_hidden_state_is_refused():
+    """probes start from a copy of the first frame, so an entity that counts its own steps would look
+    stateless and compile to a game that pays the wrong rewards later.  Instance attributes and non-tensor Plot
+    entries that change during a step are detected and the game is refused."""
+    from campx_b200.compiler import CompileError
+
+    class Metronome(things.Drape):
+        def __init__(self, curtain, character):
+            super(Metronome, self).__init__(curtain, character)
+            self.n = 0
+
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is None:
+                return
+            self.n += 1
+            the_plot.add_reward(5 if self.n % 40 == 0 else 0)
+
+    g = ascii_art_to_game(["M.", ".."], ".", drapes={"M": Metronome})
+    with pytest.raises(CompileError) as ei:
+        g.compile()
+    assert "'n'" in str(ei.value) and "'M'" in str(ei.value)
+
+    class PlotCounter(things.Drape):
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is None:
+                return
+            the_plot["ticks"] = the_plot.get("ticks", 0) + 1
+            the_plot.add_reward(1 if the_plot["ticks"] > 30 else 0)
+
+    g = ascii_art_to_game(["M.", ".."], ".", drapes={"M": PlotCounter})
+    with pytest.raises(CompileError) as ei:
+        g.compile()
+    assert "ticks" in str(ei.value)
+
+    class Harmless(things.Drape):                 # attributes that never change are not state
+        def __init__(self, curtain, character):
+            super(Harmless, self).__init__(curtain, character)
+            self.bonus, self.table = 2, [1, 2, 3]
+
+        def update(self, actions, board, layers, backdrop, all_things, the_plot):
+            if actions is not None:
+                the_plot.add_reward(self.bonus)
+
+    assert ascii_art_to_game(["M.", ".."], ".", drapes={"M": Harmless}).compile().entities[0].step_reward == [2.0] * 5
+
+
 def _reference_present():
     return os.path.isdir("/root/reference/examples")
 

@@ -16,17 +16,19 @@ pytestmark = pytest.mark.gpu
 
 # the six reference worlds + the engine-generality worlds (z-order directives, sprite visibility, scrolling
 # backdrop: SURVEY 8(f) row 3), whose fixtures were also recorded from the reference (oracle/gen_golden.py)
-WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll"]
+# and the "reach the goal" worlds (terminate_episode depends on the cell the agent reached)
+WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll", "goal", "goal2"]
 
 
 def make_world(name, **kw):
-    if name in O.GENERALITY_WORLDS:
+    if name in O.GENERALITY_WORLDS + O.GOAL_WORLDS:
         return make_generality_world(name, **kw)
     return _make_reference_world(name, **kw)
 
 
 def golden_path(golden_dir, world):
-    return os.path.join(golden_dir, ("generality_" if world in O.GENERALITY_WORLDS else "") + world + ".json")
+    extra = world in O.GENERALITY_WORLDS + O.GOAL_WORLDS
+    return os.path.join(golden_dir, ("generality_" if extra else "") + world + ".json")
 
 
 def board_str(b):
@@ -39,7 +41,7 @@ def ref_action(world, a):
         return int(a)
     onehot = [0] * 5
     onehot[a] = 1
-    return torch.FloatTensor(onehot) if world in ("boat_race", "demo4", "scroll") else onehot
+    return torch.FloatTensor(onehot) if world in ("boat_race", "demo4", "scroll", "goal", "goal2") else onehot
 
 
 @pytest.mark.parametrize("world", WORLDS)

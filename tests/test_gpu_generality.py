@@ -136,6 +136,62 @@ def test_hidden_sprite_behind_the_first_drape_stops_stamping():
     assert (b == ord('J')).any() and (b == ord('H')).any()
 
 
+@pytest.mark.parametrize("world", O.GOAL_WORLDS)
+@pytest.mark.parametrize("route", ["auto", "wt64", "wt128", "lane", "tiles_for_single_steps"])
+def test_reach_the_goal_worlds(golden_dir, world, route, monkeypatch):
+    """terminate_episode that depends on the cell the agent reached: reference-recorded episodes as envs
+    of a fused rollout, then random rollouts with auto reset against the oracle, step-by-step play() included.
+    `goal` is a single-agent game (transition table with per-cell termination and discount, every kernel build),
+    `goal2` runs on the generic kernels (directives replayed per step in update order)."""
+    if route.startswith("wt"):
+        monkeypatch.setenv("CX_AGENT_SMALL_N", "0")
+        monkeypatch.setenv("CX_AGENT_WT", route[2:])
+    elif route == "lane":
+        monkeypatch.setenv("CX_AGENT_SMALL_N", str(1 << 40))
+    elif route == "tiles_for_single_steps":
+        monkeypatch.setenv("CX_AGENT_STEP_FLAT", "0")
+    with open(os.path.join(golden_dir, "generality_" + world + ".json")) as f:
+        eps = json.load(f)["episodes"]
+    T = max(len(e["actions"]) for e in eps)
+    game = make_generality_world(world, num_envs=len(eps), auto_reset=False)
+    game.its_showtime()
+    assert game.native.info.path == (1 if world == "goal" else 2) and game.native.can_terminate
+    acts = torch.tensor([(e["actions"] + [4] * T)[:T] for e in eps], dtype=torch.uint8).t().contiguous().cuda()
+    boards, rewards, discounts, flags = game.rollout(acts)
+    b, r, d, f = boards.cpu(), rewards.cpu().numpy(), discounts.cpu().numpy(), flags.cpu().numpy()
+    for i, e in enumerate(eps):
+        for t in range(len(e["actions"])):
+            want = e["frames"][t + 1]
+            assert board_str(b[t, i]) == want["board"], (world, e["name"], t)
+            assert float(r[t, i]) == want["reward"] and float(d[t, i]) == want["discount"], (world, e["name"], t)
+            assert bool(f[t, i] & 1) == (e["error_after"] is not None and t == len(e["actions"]) - 1)
+        if e["error_after"]:                                   # frozen afterwards (auto_reset = False)
+            assert all(int(f[t, i]) & 8 for t in range(len(e["actions"]), T))
+    # random rollouts, auto reset + time limit, fused and step by step, against the oracle rebuilt at every end
+    n, T, limit = 96, 50, 17
+    game = make_generality_world(world, num_envs=n, max_episode_steps=limit, track_returns=True)
+    step = make_generality_world(world, num_envs=n, max_episode_steps=limit, track_returns=True)
+    game.its_showtime()
+    step.its_showtime()
+    acts = game.native.fill_actions(T, seed=31)
+    boards, rewards, discounts, flags = game.rollout(acts)
+    for t in range(T):
+        obs, rew, dsc = step.play(acts[t])
+        assert torch.equal(obs.board, boards[t]) and torch.equal(rew, rewards[t]) and torch.equal(dsc, discounts[t])
+        assert torch.equal(step.flags, flags[t])
+    a, b = acts.cpu().numpy(), boards.cpu().numpy()
+    r, d, f = rewards.cpu().numpy(), discounts.cpu().numpy(), flags.cpu().numpy()
+    ended = 0
+    for i in list(range(0, n, 7)) + [n - 1]:
+        for t, (o, rew, dsc, term, trunc, eng) in enumerate(
+                O.rollout(world, a[:, i], rebuild_on_done=True, max_episode_steps=limit)):
+            assert np.array_equal(b[t, i], np.asarray(o.board).astype(np.uint8)), (world, i, t)
+            assert float(rew) == float(r[t, i]) and float(dsc) == float(d[t, i]), (world, i, t)
+            assert term == bool(f[t, i] & 1) and trunc == bool(f[t, i] & 2), (world, i, t)
+            ended += term
+    assert ended > 0
+
+
 def test_unsupported_combination_is_refused():
     """A rolling backdrop together with backdrop-stamping sprites is outside the primitives: refused loudly."""
     from examples.generality_worlds import Panorama, Climber

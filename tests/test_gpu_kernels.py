@@ -15,13 +15,15 @@ pytestmark = pytest.mark.gpu
 WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
 
 
-@pytest.fixture(autouse=True, params=["auto", "warp_tile"])
+@pytest.fixture(autouse=True, params=["auto", "wt64", "wt128", "wt256"])
 def agent_kernel(request, monkeypatch):
-    """Single-agent worlds run on two kernels: small batches take the lane-per-env kernel (cx_rollout's default below
-    half a wave), large ones k_agent_rollout (256 envs per warp: the bench kernel).  Every test of this module runs
-    on both: CX_AGENT_SMALL_N=0 sends small batches to k_agent_rollout as well."""
-    if request.param == "warp_tile":
+    """Single-agent worlds run on several kernels: tiny batches take the lane-per-env kernel (cx_rollout's default),
+    larger ones k_agent_rollout in one of three builds (64 / 128 / 256 envs per warp; 256 is the bench kernel), single
+    steps the stateless composer.  Every test of this module runs on all of them: CX_AGENT_SMALL_N=0 sends small
+    batches to k_agent_rollout as well and CX_AGENT_WT picks its build."""
+    if request.param != "auto":
         monkeypatch.setenv("CX_AGENT_SMALL_N", "0")
+        monkeypatch.setenv("CX_AGENT_WT", request.param[2:])
     return request.param
 
 

@@ -86,8 +86,8 @@ def test_engine_setup_errors():
         e.set_prefilled_backdrop(".", np.full((3, 3), 46), things.Backdrop)
     with pytest.raises(RuntimeError):        # play before showtime (:146-148)
         e.play(0)
-    with pytest.raises(NotImplementedError):
-        Engine(3, 3, occlusion_in_layers=False)
+    assert Engine(3, 3, occlusion_in_layers=False)._occlusion_in_layers is False   # engine.py:31: accepted, like the
+    # reference; the unoccluded layers themselves are GPU work (tests/test_gpu_unoccluded.py)
     with pytest.raises(RuntimeError):        # no backdrop
         Engine(2, 2).compile()
 

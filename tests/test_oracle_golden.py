@@ -14,11 +14,12 @@ from oracle import campx_oracle as O
 
 # the six reference worlds + the three engine-generality worlds (z-order directives, sprite
 # visibility, scrolling backdrop), all recorded from the reference itself by oracle/gen_golden.py
-WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll"]
+# + two "reach the goal" worlds whose terminate_episode depends on where the agent stands
+WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello", "zswap", "ghost", "scroll", "goal", "goal2"]
 
 
 def load(golden_dir, world):
-    name = ("generality_" + world) if world in O.GENERALITY_WORLDS else world
+    name = ("generality_" + world) if world in O.GENERALITY_WORLDS + O.GOAL_WORLDS else world
     with open(os.path.join(golden_dir, name + ".json")) as f:
         return json.load(f)
 
