@@ -13,13 +13,13 @@
 //            afterwards goes to shared memory (one byte per env);
 //   phase 2  the CTA's slice of every output stream is written in 16-byte pieces of the FLAT arrays, a warp store
 //            being one aligned 512-byte run: a piece of the board is the static scene at that phase (a 16-byte row
-//            of the tiling pattern, L1-resident) with the agent byte patched in when it falls inside the piece;
-//            a piece of the layered board (campx/rendering.py:204-215, layers[ch] = board == ord(ch), canonical
-//            channel order) is the static layered image at that phase with at most two patches per env (agent
-//            plane on, the plane of the character it covers off), emitted as uint8, float32 or bfloat16 -- the
-//            float planes ARE the policy input (actor_critic.py:147,173 `layered_board.view(-1).float()`), so no
-//            second pass over HBM converts them.
-// No table staging (tables are a few hundred bytes, read through L1), one block barrier, no tensor cores (nothing
+//            of the tiling pattern, L1-resident); a piece of the layered board (campx/rendering.py:204-215,
+//            layers[ch] = board == ord(ch), canonical channel order) is the static layered image at that phase,
+//            emitted as uint8, float32 or bfloat16 -- the float planes ARE the policy input (actor_critic.py:147,173
+//            `layered_board.view(-1).float()`), so no second pass over HBM converts them;
+//   phase 3  thread = env again: the agent.  One byte of the board and at most two elements of the layered board
+//            (agent plane on, the plane of the character it covers off) are stored over the static streams.
+// No table staging (tables are a few hundred bytes, read through L1), two block barriers, no tensor cores (nothing
 // here is a contraction).  Envs per CTA are chosen by the launcher so that the grid is a few waves deep at any
 // batch size: 32 envs per CTA for a 4,096-env policy loop (128 CTAs), 256 (one thread per env) for 2^20 envs.
 #include "cx_agent_common.cuh"
@@ -151,59 +151,38 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
   }
   __syncthreads();  // the only block barrier
 
-  // ---- phase 2a: boards, 16 bytes of the flat [n, cells] array per thread and iteration ----
+  // ---- phase 2: the output streams.  Every stream is the STATIC image of the game repeated env after env (the
+  // scene without the agent; its layered image), so it is written first, 16 bytes of the flat arrays per thread and
+  // iteration straight from the L1-resident tables -- no per-piece search for the agent -- and the one to three
+  // elements per env that the agent changes are stored over it afterwards, thread = env, behind a block barrier (the
+  // lines are still in L2: the small stores merge there).
   {
     const uint32_t nbytes = (uint32_t)nenv * cells, nfull = nbytes >> 4;
     uint8_t* out = P.board + env0 * cells;
-    #pragma unroll 2
+    uint32_t ph = ((uint32_t)tid << 4) - div_cells((uint32_t)tid << 4) * cells;   // phase of this thread's first piece
+    const uint32_t step = ((uint32_t)nthreads << 4) - div_cells((uint32_t)nthreads << 4) * cells;
+#pragma unroll 4
     for (uint32_t k = tid; k < nfull; k += nthreads) {
-      const uint32_t b0 = k << 4, e_lo = div_cells(b0), ph = b0 - e_lo * cells;
-      const uint4 v = __ldg(g_pat + ph);  // the static scene from phase `ph` on, 16 bytes (wraps)
-      uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      // last env the piece touches (boards of 16 cells or more: at most the next one)
-      const uint32_t e_hi = min(cells >= 16u ? e_lo + (ph + 15u >= cells ? 1u : 0u) : div_cells(b0 + 15u), (uint32_t)nenv - 1u);
-      for (uint32_t e = e_lo; e <= e_hi; ++e) {
-        const uint32_t sh = s_show[e], pos = e * cells + sh - b0;  // unsigned: a cell before the piece wraps high
-        if (sh != none && pos < 16u) put_byte(w, pos, agent_char);
-      }
-      *reinterpret_cast<uint4*>(out + b0) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(out + (k << 4)) = __ldg(g_pat + ph);  // the static scene from phase `ph` on (wraps)
+      ph += step;
+      ph = min(ph, ph - cells);
     }
-    for (uint32_t b = (nfull << 4) + tid; b < nbytes; b += nthreads) {  // ragged tail of the last CTA
-      const uint32_t e = div_cells(b), c = b - e * cells;
-      out[b] = c == s_show[e] ? (uint8_t)agent_char : __ldg(g_basech + c);
-    }
+    for (uint32_t b = (nfull << 4) + tid; b < nbytes; b += nthreads)  // ragged tail of the last CTA
+      out[b] = __ldg(g_basech + (b - div_cells(b) * cells));
   }
-
-  // ---- phase 2b: layered boards, 16 bytes (16 / 4 / 8 elements) of the flat [n, chars, cells] array per piece ----
+  constexpr uint32_t ES = LAY == 1 ? 1u : (LAY == 2 ? 4u : 2u);  // element size of the layered board
+  const uint32_t LC = (uint32_t)H.n_chars * cells;
+  uint8_t* lay_out = LAY != 0 ? static_cast<uint8_t*>(P.layered) + env0 * (int64_t)LC * ES : nullptr;
   if (LAY != 0) {
-    constexpr uint32_t ES = LAY == 1 ? 1u : (LAY == 2 ? 4u : 2u);  // element size
     constexpr uint32_t EPC = 16u / ES;                              // elements per 16-byte piece
-    const uint32_t LC = (uint32_t)H.n_chars * cells, agent_off = (uint32_t)H.agent_k * cells;
-    const bool unocc = H.unoccluded != 0;
     const uint32_t nelem = (uint32_t)nenv * LC, nfull = nelem / EPC;
-    uint8_t* out = static_cast<uint8_t*>(P.layered) + env0 * (int64_t)LC * ES;
-    // byte image of EPC elements starting at flat element i0 (static layered image + the agent's two patches)
-    auto piece = [&](uint32_t i0, uint32_t count, uint32_t (&w)[4]) {
-      const uint32_t e_lo = div_lc(i0), rem = i0 - e_lo * LC;
-#pragma unroll
-      for (uint32_t j = 0; j < EPC / 4; ++j) w[j] = ldg_u32_unaligned(g_lay, rem + 4u * j);
-      const uint32_t e_hi = min(LC >= EPC ? e_lo + (rem + count - 1u >= LC ? 1u : 0u) : div_lc(i0 + count - 1u), (uint32_t)nenv - 1u);
-      for (uint32_t e = e_lo; e <= e_hi; ++e) {
-        // occluded layers follow the board (agent plane on where it is DRAWN, the covered character's plane off);
-        // unoccluded layers follow the curtains (agent plane on where the agent STANDS, nothing else changes)
-        const uint32_t sh = unocc ? s_stood[e] : s_show[e];
-        if (sh == none) continue;
-        const uint32_t at = e * LC + sh - i0;          // + plane offset = position inside the piece (wraps high)
-        const uint32_t kb = unocc ? 0xFFu : __ldg(g_basek + sh);   // plane of the covered character (0xFF: none)
-        const uint32_t off = at + kb * cells, on = at + agent_off;
-        if (kb != 0xFFu && off < EPC) put_byte(w, off, 0u);
-        if (on < EPC) put_byte(w, on, 1u);
-      }
-    };
+    uint32_t rem = (uint32_t)tid * EPC - div_lc((uint32_t)tid * EPC) * LC;        // element phase inside the env
+    const uint32_t step = (uint32_t)nthreads * EPC - div_lc((uint32_t)nthreads * EPC) * LC;
 #pragma unroll 2
     for (uint32_t k = tid; k < nfull; k += nthreads) {
       uint32_t w[4] = {0u, 0u, 0u, 0u};
-      piece(k * EPC, EPC, w);
+#pragma unroll
+      for (uint32_t j = 0; j < EPC / 4; ++j) w[j] = ldg_u32_unaligned(g_lay, rem + 4u * j);
       uint4 v;
       if (LAY == 1) {
         v = make_uint4(w[0], w[1], w[2], w[3]);
@@ -216,18 +195,45 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
                        ((w[1] & 1u) | ((w[1] << 8) & 0x10000u)) * 0x3F80u,
                        (((w[1] >> 16) & 1u) | ((w[1] >> 8) & 0x10000u)) * 0x3F80u);
       }
-      *reinterpret_cast<uint4*>(out + (size_t)k * 16u) = v;
+      *reinterpret_cast<uint4*>(lay_out + (size_t)k * 16u) = v;
+      rem += step;
+      rem = min(rem, rem - LC);
     }
     for (uint32_t i = nfull * EPC + tid; i < nelem; i += nthreads) {  // ragged tail of the last CTA
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-      piece(i, 1u, w);
-      const uint32_t b = w[0] & 1u;
+      const uint32_t b = __ldg(g_lay + (i - div_lc(i) * LC)) & 1u;
       if (LAY == 1)
-        out[i] = (uint8_t)b;
+        lay_out[i] = (uint8_t)b;
       else if (LAY == 2)
-        reinterpret_cast<uint32_t*>(out)[i] = b * 0x3F800000u;
+        reinterpret_cast<uint32_t*>(lay_out)[i] = b * 0x3F800000u;
       else
-        reinterpret_cast<uint16_t*>(out)[i] = (uint16_t)(b * 0x3F80u);
+        reinterpret_cast<uint16_t*>(lay_out)[i] = (uint16_t)(b * 0x3F80u);
+    }
+  }
+  __syncthreads();  // the static streams of this CTA's envs are written: now the agent
+  {
+    const bool unocc = H.unoccluded != 0;
+    const uint32_t agent_off = (uint32_t)H.agent_k * cells;
+    auto put = [&](uint32_t i, uint32_t bit) {  // one element of the layered board
+      if (LAY == 1)
+        lay_out[i] = (uint8_t)bit;
+      else if (LAY == 2)
+        reinterpret_cast<uint32_t*>(lay_out)[i] = bit * 0x3F800000u;
+      else if (LAY == 4)
+        reinterpret_cast<uint16_t*>(lay_out)[i] = (uint16_t)(bit * 0x3F80u);
+    };
+    for (int el = tid; el < nenv; el += nthreads) {
+      const uint32_t show = s_show[el];
+      if (show != none) (P.board + env0 * cells)[(uint32_t)el * cells + show] = (uint8_t)agent_char;
+      if (LAY != 0) {
+        // occluded layers follow the board (agent plane on where it is DRAWN, the covered character's plane off);
+        // unoccluded layers follow the curtains (agent plane on where the agent STANDS, nothing else changes)
+        const uint32_t sh = unocc ? s_stood[el] : show;
+        if (sh != none) {
+          const uint32_t kb = unocc ? 0xFFu : __ldg(g_basek + sh);   // plane of the covered character (0xFF: none)
+          if (kb != 0xFFu) put((uint32_t)el * LC + kb * cells + sh, 0u);
+          put((uint32_t)el * LC + agent_off + sh, 1u);
+        }
+      }
     }
   }
 

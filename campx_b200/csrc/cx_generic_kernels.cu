@@ -876,7 +876,7 @@ __device__ __host__ __forceinline__ size_t warp_state_bytes(const CxGenHeader& H
 __device__ __host__ __forceinline__ size_t warp_mem_bytes(const CxGenHeader& H) {
   const size_t tile = ((size_t)H.tile_envs * H.cells + 15) / 16 * 16;
   const size_t lin = ((size_t)H.tile_envs * H.n_lin * (H.mask_words + 1) * 4 + 15) / 16 * 16;
-  return tile + lin + warp_state_bytes(H);
+  return tile + lin + (warp_state_bytes(H) + 15) / 16 * 16;
 }
 
 __device__ __forceinline__ WarpMem warp_mem(const CxGenHeader& H, uint8_t* smem, int warp, int lane) {

@@ -99,3 +99,4 @@ if __name__ == "__main__":
     if "step" in what: step_probe()
     if "ring" in what: ring_probe()
     if "obs" in what: obs_probe()
+
