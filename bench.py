@@ -666,9 +666,14 @@ def run_ours(args):
         configs = {}
         jobs = [("hello_world_65536", lambda: measure_config("hello", 65536, 32, peak, 40.0, sampler, "k_generic_rollout")),
                 ("demo1_65536", lambda: measure_config("demo1", 65536, 32, peak, 40.0, sampler,
-                                                       "k_agent_rollout_obs (lane-per-env, board only)")),
-                ("demo2_1048576", lambda: measure_config("demo2", 1 << 20, 32, peak, 40.0, sampler, "k_agent_rollout")),
-                ("demo4_1048576", lambda: measure_config("demo4", 1 << 20, 32, peak, 40.0, sampler, "k_agent_rollout")),
+                                                       "k_agent_rollout<NG=1,GW=2> (64 envs per warp)")),
+                ("demo1_65536_episode_per_launch", lambda: measure_config(
+                    "demo1", 65536, EPISODE_LIMIT, peak, 40.0, sampler,
+                    "k_agent_rollout<NG=1,GW=2>, one 100-step episode per launch (examples/actor_critic.py:56)")),
+                ("demo2_1048576", lambda: measure_config("demo2", 1 << 20, 32, peak, 40.0, sampler,
+                                                         "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
+                ("demo4_1048576", lambda: measure_config("demo4", 1 << 20, 32, peak, 40.0, sampler,
+                                                         "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
                 ("actor_critic_rollout_4096", lambda: measure_actor_critic(peak, 40.0, sampler))]
         for name, job in jobs:
             try:

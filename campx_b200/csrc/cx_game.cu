@@ -979,10 +979,11 @@ extern "C" int cx_render(const cx_game* g, const void* d_state, int64_t n, uint8
 }
 
 // CX_AGENT_STEP_FLAT=0 (development knob) sends single steps through the tile kernels again
-static bool step_composer_enabled() {
+static int step_composer_mode() {   // 0: never, 1: where it is faster (default), 2: at any batch size
   const char* e = getenv("CX_AGENT_STEP_FLAT");   // read per call: tests flip it to compare the two routes
-  return !(e && atoi(e) == 0);
+  return e ? atoi(e) : 1;
 }
+static bool step_composer_enabled() { return step_composer_mode() != 0; }
 
 static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                           const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
@@ -1003,7 +1004,8 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
   }
   // one step of a small batch: the stateless composer (cx_agent_step_kernels.cu) -- 2.5 against 3.1 us at 4,096 envs,
   // equal at 65,536; large batches amortise the tile staging over enough envs (2^20: 11 us against 28 us)
-  if (g->path == CX_PATH_AGENT && T == 1 && !synth.on && n < 65536 && step_composer_enabled() &&
+  if (g->path == CX_PATH_AGENT && T == 1 && !synth.on && (n < 65536 || step_composer_mode() == 2) &&
+      step_composer_enabled() &&
       cx_agent_step_applies(g, d_board, nullptr))
     return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, nullptr, CX_DTYPE_U8,
                                 (cudaStream_t)stream);

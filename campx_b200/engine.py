@@ -20,6 +20,8 @@ New keyword arguments (everything else is the reference's):
     track_returns       keep per-env episode return/length and global episode statistics
     verify              after compiling, replay random actions on the GPU and on the compile-time
                         shadow and require identical boards/rewards/discounts (default True)
+    verify_steps        length of that replay (default 24 steps x 4 envs); a world whose behaviour only
+                        shows late (long corridors, rare events) can ask for a longer one
 
 What happens where: set-up is host Python.  `its_showtime()` compiles the game (campx_b200/compiler)
 and uploads it; from then on `play()` is one C-ABI call (`cx_step`) on the current CUDA stream and
@@ -42,7 +44,8 @@ from .runtime import NativeGame
 class Engine(object):
 
     def __init__(self, rows, cols, occlusion_in_layers=True, num_envs=None, device=None, num_actions=5,
-                 action_format=None, max_episode_steps=0, auto_reset=None, track_returns=False, verify=True):
+                 action_format=None, max_episode_steps=0, auto_reset=None, track_returns=False, verify=True,
+                 verify_steps=24):
         # occlusion_in_layers=False (engine.py:31,528): layers follow the intent of the reference's
         # BaseUnoccludedObservationRenderer (rendering.py:227-353) -- a layer is its entity's whole curtain / cell, or
         # the backdrop's own cells, occluded or not; the board is unchanged.  The reference's implementation cannot
@@ -69,6 +72,7 @@ class Engine(object):
         self._auto_reset = self._batched if auto_reset is None else bool(auto_reset)
         self._track_returns = bool(track_returns)
         self._verify = bool(verify)
+        self._verify_steps = max(1, int(verify_steps))
         self._shadow = None
         self._native = None
         self._spec = None
@@ -174,7 +178,7 @@ class Engine(object):
         self.compile()
         self._native = NativeGame(self._spec, self._num_envs, self._device)
         if self._verify:
-            self._verify_against_shadow()
+            self._verify_against_shadow(n_steps=self._verify_steps)
         nat = self._native
         # two sets of output buffers, used alternately: the tensors a play() returns stay valid until the play()
         # AFTER the next one, so a caller can copy step t to the host on a side stream while step t+1 runs

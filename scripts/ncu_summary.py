@@ -80,16 +80,16 @@ if os.path.exists(ll):
             runs.append([k, 1, t])
     total = sum(t for _, t in seq)
     with open(os.path.join(out_dir, "%s_launch_list.md" % tag), "w") as f:
-        f.write("# ncu launch list of `python bench.py --steps 512 --warmup 64 --e2e-steps 8` (%s)\n\n" % tag)
+        f.write("# ncu launch list of `%s` (%s)\n\n" % (os.environ.get("NCU_BENCH_CMD", "python bench.py --steps 512 --warmup 64 --e2e-steps 8"), tag))
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` over the whole command, in launch order "
                 "(run-length encoded) -- cold-cache, serialised: compare shares, not absolutes.\n\n")
         f.write("| # | kernel | consecutive launches | total us | share of command | mean us |\n|---|---|---|---|---|---|\n")
         for i, (k, n, t) in enumerate(runs):
             f.write("| %d | %s | %d | %.1f | %.1f%% | %.1f |\n" % (i, k, n, t / 1e3, 100 * t / total, t / n / 1e3))
-        f.write("\nSections of bench.py: set-up (reset / render / `k_fill_actions`), then the warm-up + TIMED region = the one "
+        f.write("\n" + os.environ.get("NCU_BENCH_NOTE", "Sections of bench.py: set-up (reset / render / `k_fill_actions`), then the warm-up + TIMED region = the one "
                 "long run of `k_agent_rollout<1, 1, 0>` (64 + 512 steps at 32 steps per launch: nothing else launches there, so "
                 "the kernel's share of a timed step is 100 %), then the e2e leg (`cx_step` = `k_agent_rollout` with T = 1, one "
-                "launch per play()), then the secondary board + layered-board measurement (`k_agent_rollout_obs`).\n")
+                "launch per play()), then the secondary board + layered-board measurement (`k_agent_rollout_obs`).") + "\n")
     import shutil
     shutil.copy(ll, os.path.join(out_dir, "%s_launches.csv" % tag))
 json.dump({"k_agent_rollout_track_T32_n1048576": traffic["dram_bytes"], "detail": traffic,

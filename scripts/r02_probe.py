@@ -30,7 +30,7 @@ def graph_of(fn, k):
 
 def step_probe():
     for n in (4096, 65536, 1 << 20):
-        for flat in ("1", "0"):
+        for flat in ("2", "0"):
             os.environ["CX_AGENT_STEP_FLAT"] = flat
             g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
             nb = max(2, int(300e6 // (n * 31)) + 1)

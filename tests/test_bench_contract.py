@@ -25,6 +25,7 @@ def _check(line, n_gpus):
     assert "workload" in line["config"] and "boat_race" in line["config"]["workload"]
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "boat_race" in cb["sample"]
+    assert cb["one_core"]["cores"] == 1 and cb["one_core"]["value"] > 0          # both figures
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
