@@ -85,6 +85,55 @@ def test_play_before_showtime_and_bad_actions():
         game.play(7)
 
 
+def test_batched_actions_that_are_not_actions_are_flagged_not_guessed():
+    """a batched one-hot row with no 1, several 1s or fractional entries used to be argmax-ed silently, and
+    int64 indices >= 256 wrapped into the action set.  Both now leave the env untouched and raise CX_FLAG_BAD_ACTION
+    (the single-env mode, like the reference's `assert sum(act) == 1`, raises)."""
+    from campx_b200 import _native as N
+    n = 64
+    game = make_world("boat_race", num_envs=n)
+    obs, _, _ = game.its_showtime()
+    first = obs.board.clone()
+    onehot = torch.zeros((n, 5), device="cuda")
+    onehot[:, 1] = 1                                           # everybody: right
+    onehot[3] = 0                                              # no action at all
+    onehot[5, 3] = 1                                           # two actions
+    onehot[7] = torch.tensor([0, 0.5, 0.5, 0, 0])              # fractional
+    obs, reward, _ = game.play(onehot)
+    bad = (game.flags & N.CX_FLAG_BAD_ACTION) != 0
+    assert bad.nonzero().flatten().tolist() == [3, 5, 7] and game.bad_action_count() == 3
+    assert torch.equal(obs.board[bad], first[bad]) and bool((reward[bad] == 0).all())
+    assert bool((obs.board[~bad] != first[~bad]).flatten(1).any(dim=1).all())       # the others moved
+    idx = torch.full((n,), 1, dtype=torch.int64, device="cuda")
+    idx[2], idx[4] = 257, -1                                   # 257 must not wrap to action 1, -1 not to 255 & co
+    before = obs.board.clone()
+    obs, reward, _ = game.play(idx)
+    bad = (game.flags & N.CX_FLAG_BAD_ACTION) != 0
+    assert bad.nonzero().flatten().tolist() == [2, 4] and torch.equal(obs.board[bad], before[bad])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_games_on_a_second_device():
+    """the dynamic-shared-memory cap is a per-DEVICE function attribute; a process that had configured it on
+    cuda:0 used to launch unconfigured on cuda:1."""
+    a = make_world("boat_race", num_envs=1 << 16, device="cuda:0")
+    a.its_showtime()
+    acts = a.native.fill_actions(8, seed=1)
+    ref = a.rollout(acts)
+    b = make_world("boat_race", num_envs=1 << 16, device="cuda:1")
+    b.its_showtime()
+    with torch.cuda.device(1):
+        got = b.rollout(acts.to("cuda:1"))
+        lay = b.rollout_observations(acts.to("cuda:1"))[1]
+    assert torch.equal(ref[0], got[0].to("cuda:0")) and torch.equal(ref[1], got[1].to("cuda:0"))
+    assert lay.device.index == 1
+    h = make_world("hello", num_envs=4096, device="cuda:1")
+    h.its_showtime()
+    with torch.cuda.device(1):
+        hb = h.rollout(h.native.fill_actions(4, seed=2))[0]
+    assert hb.device.index == 1 and int((hb == ord("@")).sum()) > 0
+
+
 @pytest.mark.parametrize("world", WORLDS)
 def test_batched_play_matches_oracle(world):
     n, T, limit = 48, 40, 15
