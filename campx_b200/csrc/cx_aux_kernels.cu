@@ -435,6 +435,17 @@ __global__ void k_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, 
   out[i] = (uint8_t)cx_synth_action(seed, env_offset + (uint64_t)e, t0 + (uint64_t)t, (uint32_t)A);
 }
 
+// the same stream, one Philox call per QUAD of envs (its four words serve envs 4q .. 4q+3) and one 4-byte store:
+// env_offset and n multiples of 4, output 4-byte aligned
+__global__ void k_fill_actions_quads(uint64_t seed, uint64_t env_offset, uint64_t t0, int32_t T, int64_t n, int32_t A,
+                                     uint8_t* out) {
+  const int64_t nq = n >> 2, i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= (int64_t)T * nq) return;
+  const int64_t t = i / nq, q = i - t * nq;
+  reinterpret_cast<uint32_t*>(out)[i] =
+      cx_synth_actions_quad(seed, (env_offset >> 2) + (uint64_t)q, t0 + (uint64_t)t, (uint32_t)A);
+}
+
 // examples/actor_critic.py:90-98: `m = Categorical(probs); action = m.sample()`.  Inverse-CDF sampling, one thread
 // per env: u from the counter-based Philox stream (reproducible per (seed, env, step), independent of the launch
 // geometry), the first action whose cumulative weight exceeds u * total.  With logits the weights are
@@ -686,7 +697,11 @@ extern "C" int cx_fill_actions(uint64_t seed, uint64_t env_offset, uint64_t t0, 
     cx_set_error("cx_fill_actions: bad argument");
     return CX_ERR_INVALID_ARG;
   }
-  k_fill_actions<<<blocks_for((int64_t)T * n), TB, 0, (cudaStream_t)stream>>>(seed, env_offset, t0, T, n, A, d_out);
+  if ((env_offset & 3) == 0 && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 3) == 0)
+    k_fill_actions_quads<<<blocks_for((int64_t)T * (n >> 2)), TB, 0, (cudaStream_t)stream>>>(seed, env_offset, t0, T, n,
+                                                                                          A, d_out);
+  else
+    k_fill_actions<<<blocks_for((int64_t)T * n), TB, 0, (cudaStream_t)stream>>>(seed, env_offset, t0, T, n, A, d_out);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -100,3 +100,4 @@ if __name__ == "__main__":
     if "ring" in what: ring_probe()
     if "obs" in what: obs_probe()
 
+
