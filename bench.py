@@ -40,8 +40,9 @@ if ROOT not in sys.path:
 WORLD = "boat_race"
 EPISODE_LIMIT = 100          # examples/actor_critic.py:56
 SEED = 543                   # examples/actor_critic.py:26
-PARITY_ENVS = 64             # first 64 envs of each rank
-PARITY_STEPS = 128           # crosses the auto-reset at step 100
+PARITY_ENVS = 64             # first 64 envs of each rank ...
+PARITY_STEPS = 1000          # ... first 1,000 steps (ten episodes: the auto-reset at step 100 is crossed nine times)
+CONFIG_PARITY_STEPS = 128    # the `configs` entries: a shorter replay per config
 
 
 def parse_args():
@@ -373,7 +374,7 @@ def measure_config(world_name, n, T, peak, min_ms, sampler, kernel):
     state_rw = 2 * nat.info.state_bytes_per_env
     make = (lambda i: hello_actions(nat, T, SEED + i)) if hello else (lambda i: nat.fill_actions(T, seed=SEED, t0=i * T))
     envs = list(range(8)) + [n // 2, n - 1]
-    ok, where = oracle_check(world_name, nat, make, lambda a, o: nat.rollout(a, *o), envs, PARITY_STEPS, T)
+    ok, where = oracle_check(world_name, nat, make, lambda a, o: nat.rollout(a, *o), envs, CONFIG_PARITY_STEPS, T)
     game.reset()
 
     ring = max(2, int(math.ceil(400e6 / (n * T * per_step))))
@@ -408,7 +409,7 @@ def measure_config(world_name, n, T, peak, min_ms, sampler, kernel):
             "alg_bytes_per_env_step": per_step + state_rw / T, "achieved_gbs": gbs, "frac": gbs / peak,
             "kernel": kernel, "l2_policy": "ring of %d output buffers, %.0f MB" % (ring, ring * n * T * per_step / 1e6),
             "issue": "CUDA graph of the ring, replayed",
-            "parity": {"envs": len(envs), "steps": PARITY_STEPS, "ok": bool(ok), "mismatch": where,
+            "parity": {"envs": len(envs), "steps": CONFIG_PARITY_STEPS, "ok": bool(ok), "mismatch": where,
                        "what": "board, every layer, reward, discount, done flags == CPU oracle"}}
 
 

@@ -256,11 +256,8 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
           const uint32_t show = (e >> 8) & 0xFF;   // terminal board on a terminal step
           uint32_t f = e >> 16;
           if (TRACK && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
-#ifdef CX_AB_NOSAT   // development A/B: the unsaturated counter of round 1
-            const uint32_t steps = ts[j][i] + 1u;
-#else
-            const uint32_t steps = min(ts[j][i] + 1u, (uint32_t)CX_STEP_MAX);  // 15-bit counter saturates (bit 15 = OVER)
-#endif
+            // 15-bit counter saturates (bit 15 = OVER); A/B on one box against the unsaturated counter: 0.186 = 0.185 ms
+            const uint32_t steps = min(ts[j][i] + 1u, (uint32_t)CX_STEP_MAX);
             rt[j][i] += r;
             if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;  // time limit
             ts[j][i] = steps;

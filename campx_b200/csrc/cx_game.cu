@@ -1010,11 +1010,10 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, nullptr, CX_DTYPE_U8,
                                 (cudaStream_t)stream);
   if (g->path == CX_PATH_AGENT) {
-    // k_agent_rollout gives every warp 256 envs: below half a wave of its 1,024-env CTAs (7 per SM) the batch is
-    // bound by the per-warp step latency, and the lane-per-env kernel (32 envs per warp, 8x the warps) is faster --
-    // measured on Demo 1: 16,384 envs 0.052 -> 0.020 ms per 32 steps, 65,536 0.052 -> 0.043, 2^18 0.111 -> 0.070,
-    // equal at 2^19, and 0.185 against 0.276 at 2^20 (scripts/small_batch_time.py).  CX_AGENT_SMALL_N overrides the
-    // threshold (0: always k_agent_rollout).
+    // Batches below 32,768 envs: the lane-per-env kernel (32 envs per warp) keeps more warps resident than the 64-env
+    // build of k_agent_rollout and is a little faster there (Demo 1, 32 steps: 4,096 envs 16.6 against 17.9 us,
+    // 16,384 equal, 32,768 20.9 against 19.4 us); from there up k_agent_rollout picks one of its three builds
+    // (profiles/r02_probes.md).  CX_AGENT_SMALL_N overrides the threshold (0: always k_agent_rollout).
     int64_t small_n = 32768;
     if (const char* dbg = getenv("CX_AGENT_SMALL_N")) small_n = atoll(dbg);
     if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS || n < small_n)  // large boards, small batches: lane-per-env kernel, board only
