@@ -91,20 +91,18 @@ class ShadowRenderer(object):
 
     def clear(self):
         self.board.mul_(0)                       # in place, on whatever storage the canvas aliases
+        self._sprites, self._drapes, self._curtain = [], {}, None
 
     def paint_all_of(self, curtain):
         self.board = curtain.as_subclass(torch.Tensor)    # alias of the backdrop storage (set_)
-        if not self.occluded:                             # rendering.py:283-286
-            for ch, layer in self.layers.items():
-                layer.copy_(self.board == ord(ch))
+        self._curtain = self.board                        # the backdrop's own storage (unoccluded layers, render())
 
     def paint_sprite(self, character, position):
         if character not in self.layers:
             raise ValueError('character {} does not seem to be a valid character for '
                              'this game'.format(str(character)))
         self.board[position[0], position[1]] = ord(character)
-        if not self.occluded:                             # rendering.py:309
-            self.layers[character][position[0], position[1]] = 1
+        self._sprites.append((character, (int(position[0]), int(position[1]))))
 
     def paint_drape(self, character, curtain):
         if character not in self.layers:
@@ -112,12 +110,21 @@ class ShadowRenderer(object):
                              'this game'.format(str(character)))
         m = curtain.as_subclass(torch.Tensor).long()
         self.board = self.board - m * self.board + m * ord(character)   # fresh storage
-        if not self.occluded:                             # rendering.py:333
-            self.layers[character].copy_(m != 0)
+        self._drapes[character] = (m != 0)
 
     def render(self):
         if not self.occluded:
-            return                               # layers were filled while painting
+            # read off the finished frame (rendering.py:283-286,309,333; same definition as the oracle's
+            # UnoccludedRenderer): a drape's layer is its curtain; every other character's layer is where the
+            # backdrop curtain holds it once the frame is complete, plus a sprite's own cell
+            for ch, layer in self.layers.items():
+                if ch in self._drapes:
+                    layer.copy_(self._drapes[ch])
+                else:
+                    layer.copy_(self._curtain == ord(ch))
+            for ch, (r, c) in self._sprites:
+                self.layers[ch][r, c] = 1
+            return
         for ch, layer in self.layers.items():
             layer.copy_(self.board == ord(ch))   # identity of layers[ch] is preserved
 

@@ -8,7 +8,6 @@
 #include "cx_internal.cuh"
 #include "cx_philox.cuh"
 
-int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
 
 namespace {
 

@@ -521,6 +521,11 @@ static int build_generic_tables(const cx_game_desc* d, const int* order, CxGenHe
   int n_dyn = 0;
   bool any_stamp = false, needs_prev = false;
   for (int i = 0; i < E; ++i) H->update_order[i] = (uint8_t)order[i];
+  for (int k = 0; k < CX_MAX_CHARS; ++k) H->z_of_char[k] = -1;
+  for (int z = 0; z < E; ++z) {
+    const int k = char_index(d, d->entities[z].character);
+    if (k >= 0) H->z_of_char[k] = (int8_t)z;
+  }
   for (int z = 0; z < E; ++z) {
     const cx_entity_desc& e = d->entities[z];
     CxGenEntity& g = H->ent[z];
@@ -873,12 +878,6 @@ extern "C" int cx_game_create(const cx_game_desc* desc, cx_game** out) {
     build_agent_tables(desc, agent_z, order, &g->ah, &blob);
   } else {
     g->path = CX_PATH_GENERIC;
-    if (desc->unoccluded_layers) {
-      cx_set_error("occlusion_in_layers=False is implemented for single-agent games (one moving one-cell drape over "
-                   "static entities); this game needs the generic kernels");
-      delete g;
-      return CX_ERR_UNSUPPORTED;
-    }
     rc = build_generic_tables(desc, order, &g->gh, &blob);
     if (rc != CX_OK) {
       delete g;
@@ -1070,6 +1069,15 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
                                        d_layered, (cudaStream_t)stream);
   }
   if (g && g->desc.unoccluded_layers) {
+    if (g->path == CX_PATH_GENERIC && d_actions && d_reward && d_flags && d_board && T >= 1) {
+      // generic games: the kernel reads the unoccluded layers off its entity state at every step
+      int rc = check_common(g, d_state, n, "cx_rollout_observations");
+      if (rc) return rc;
+      CxSynth none;
+      memset(&none, 0, sizeof(none));
+      return cx_launch_generic_rollout(g, d_state, n, T, d_actions, none, d_reward, d_discount, d_flags, d_board,
+                                       (cudaStream_t)stream, d_layered);
+    }
     cx_set_error("cx_rollout_observations: unoccluded layers need the fused kernels (16-byte aligned buffers, "
                  "boards that fit the lane-per-env kernel)");
     return CX_ERR_UNSUPPORTED;
@@ -1129,6 +1137,8 @@ extern "C" int cx_render_observations(const cx_game* g, const void* d_state, int
   if (cx_agent_step_applies(g, d_board, d_layered))   // the composer with nothing to step
     return cx_launch_agent_step(g, const_cast<void*>(d_state), n, nullptr, nullptr, nullptr, nullptr, d_board, d_layered,
                                 dtype, (cudaStream_t)stream);
+  if (g->desc.unoccluded_layers && g->path == CX_PATH_GENERIC && dtype == CX_DTYPE_U8)
+    return cx_launch_generic_render(g, d_state, n, d_board, (cudaStream_t)stream, static_cast<uint8_t*>(d_layered));
   if (g->desc.unoccluded_layers || dtype == CX_DTYPE_BF16) {
     cx_set_error("cx_render_observations: this game / element type needs the single-agent composer (16-byte aligned "
                  "buffers)");

@@ -74,6 +74,7 @@ struct GenParams {
   float* discount;
   uint8_t* flags;
   uint8_t* board;
+  uint8_t* layered;               // [T, n, n_chars, cells] unoccluded layers (cx_game_desc::unoccluded_layers) or null
   int64_t n;
   int32_t T;
   int32_t vec;
@@ -826,6 +827,44 @@ __device__ __forceinline__ void store_above(const Ctx& X, const WarpMem& W, int 
   }
 }
 
+// Unoccluded layers of a warp's envs (cx_game_desc::unoccluded_layers, the intent of rendering.py:227-353), read off
+// the entity state the frame was rendered from: layers[ch] = the whole curtain of drape ch (rolled / one cell), or
+// where the BACKDROP holds ch -- the per-env plane, quirk-Q1 stamps included, rendering.py:283-286 -- plus, for a
+// visible sprite, its cell (:309).  One byte per (env, character, cell), written cell by cell: the correctness route of
+// games that need the generic kernels (the single-agent kernels emit these layers as part of their tiles).
+__device__ __forceinline__ void emit_unoccluded_layers(const Ctx& X, const WarpMem& W, int nenv, uint8_t* dst, int lane) {
+  const CxGenHeader& H = *X.H;
+  const uint32_t cells = H.cells, per = (uint32_t)H.n_chars * cells;
+  const uint32_t inv_cells = div_inverse(cells);
+  for (uint32_t e = 0; e < (uint32_t)nenv; ++e) {
+    const uint16_t* st = W.dyn[e];
+    const uint8_t* plane = W.plane + e * cells;
+    for (uint32_t i = lane; i < per; i += 32) {
+      const uint32_t k = fast_div(i, inv_cells), c = i - k * cells;
+      const int z = H.z_of_char[k];
+      bool v;
+      if (z >= 0 && H.ent[z].kind != CX_KIND_SPRITE) {
+        const CxGenEntity& en = H.ent[z];
+        if (en.kind == CX_KIND_STATIC) {
+          v = mask_bit(X, z, (int)c);
+        } else if (en.kind == CX_KIND_ROLL) {
+          const uint32_t off = st[en.dyn_slot], rcv = X.rc[c];
+          int r = (int)(rcv >> 8) - (int)(off >> 8), cc = (int)(rcv & 255) - (int)(off & 255);
+          if (r < 0) r += H.rows;
+          if (cc < 0) cc += H.cols;
+          v = mask_bit(X, z, r * H.cols + cc);
+        } else {
+          v = st[en.dyn_slot] == c;
+        }
+      } else {
+        v = backdrop_at(X, st, plane, (int)c) == H.chars[k];
+        if (z >= 0 && visible_now(H, st, z) && st[H.ent[z].dyn_slot] == c) v = true;
+      }
+      dst[e * per + i] = v ? 1 : 0;
+    }
+  }
+}
+
 // Whole step-end composition of a warp's envs.  `fast`: bitset composer with 16-byte stores; otherwise the
 // per-cell painter's algorithm with byte stores (any geometry, any alignment).
 template <int U>
@@ -1006,6 +1045,10 @@ __global__ void __launch_bounds__(BLK, OCC) k_generic_rollout(const __grid_const
 #if CX_GEN_PROBE != 1  // development probe (1: no composition)
     compose_warp<OCC >= 6 ? 3 : kFlatUnroll>(X, W, nenv, P.board + row * cells, fast, lane);
 #endif
+    if (P.layered) {  // unoccluded layers of this frame, before any auto reset touches the state
+      emit_unoccluded_layers(X, W, nenv, P.layered + row * (int64_t)H.n_chars * cells, lane);
+      __syncwarp();
+    }
 
     // ---- auto reset: back to the its_showtime state (fresh make_game(), actor_critic.py:146) ----
     uint32_t rmask = __ballot_sync(0xffffffffu, reset_me);
@@ -1091,6 +1134,7 @@ __global__ void __launch_bounds__(NT) k_generic_render(const __grid_constant__ G
   }
   __syncwarp();
   compose_warp<kFlatUnroll>(X, W, nenv, P.board + env0 * cells, P.vec && H.fast_compose, lane);
+  if (P.layered) emit_unoccluded_layers(X, W, nenv, P.layered + env0 * (int64_t)H.n_chars * cells, lane);
 }
 
 GenParams make_params(const cx_game* g, void* d_state, int64_t n) {
@@ -1146,7 +1190,7 @@ int configure_once() {
 
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
-                              uint8_t* d_board, cudaStream_t s) {
+                              uint8_t* d_board, cudaStream_t s, uint8_t* d_layered) {
   GenParams P = make_params(g, d_state, n);
   P.actions = d_actions;
   P.synth = synth.on;
@@ -1158,6 +1202,7 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   P.discount = d_discount;
   P.flags = d_flags;
   P.board = d_board;
+  P.layered = d_layered;
   P.T = T;
   const int G = g->gh.tile_envs;
   P.vec = gen_vec_ok(g, n, d_board);
@@ -1198,9 +1243,11 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
   return CX_OK;
 }
 
-int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s) {
+int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s,
+                             uint8_t* d_layered) {
   GenParams P = make_params(g, const_cast<void*>(d_state), n);
   P.board = d_board;
+  P.layered = d_layered;
   P.vec = gen_vec_ok(g, n, d_board);
   const int G = g->gh.tile_envs;
   const int wpc = gen_warps_per_cta(g);

@@ -101,6 +101,8 @@ struct CxGenHeader {
   int32_t zero_backdrop;    // quirk Q1(ii): no drape at all => canvas is zeroed every render
   int32_t needs_prev;       // some entity consults the last render (blockers / entry rewards / conditional terminate)
   int32_t cond_term;        // some entity terminates the episode depending on what its watched entity reached
+  int8_t z_of_char[CX_MAX_CHARS];  // character index -> z index of the sprite / drape that owns it (-1: a backdrop
+                            // character): unoccluded layers are read off the entity state (cx_game_desc::unoccluded_layers)
   int32_t max_steps, auto_reset, track;
   uint8_t update_order[CX_MAX_ENTITIES];  // z-indices in update order
   uint8_t chars[CX_MAX_CHARS];
@@ -233,12 +235,15 @@ bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_
 int cx_launch_agent_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
                          float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* d_layered, int lay_dtype,
                          cudaStream_t s);
+// d_layered (optional, games with cx_game_desc::unoccluded_layers): [T, n, n_chars, cells] / [n, n_chars, cells] uint8
+// unoccluded layers of every frame, read off the entity state inside the kernel
 int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
-                              uint8_t* d_board, cudaStream_t s);
+                              uint8_t* d_board, cudaStream_t s, uint8_t* d_layered = nullptr);
 int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s);
 int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
-int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
+int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s,
+                             uint8_t* d_layered = nullptr);
 int cx_launch_get_entity(const cx_game* g, const void* d_state, int64_t n, int32_t z, int32_t* d_out,
                          cudaStream_t s);
 int cx_launch_set_entity(const cx_game* g, void* d_state, int64_t n, int32_t z, const int32_t* d_in,

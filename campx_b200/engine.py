@@ -50,8 +50,7 @@ class Engine(object):
         # BaseUnoccludedObservationRenderer (rendering.py:227-353) -- a layer is its entity's whole curtain / cell, or
         # the backdrop's own cells, occluded or not; the board is unchanged.  The reference's implementation cannot
         # run (numpy calls on tensors, a 2-field Observation at :348); here the Observation keeps its three fields.
-        # Implemented for single-agent games (the kernels write such layers themselves: they are not a function of
-        # the board); other games raise NotImplementedError at its_showtime().
+        # The step kernels write such layers themselves (they are not a function of the board).
         self._rows = int(rows)
         self._cols = int(cols)
         self._backdrop = None

@@ -169,8 +169,9 @@ typedef struct cx_game_desc {
                               curtain of drape ch / the cell of sprite ch / the backdrop cells holding ch, whether or
                               not something is painted over them; the board is unchanged.  Such layers are not a
                               function of the board: they are written by cx_step_observations /
-                              cx_rollout_observations / cx_render_observations only (single-agent games; others are
-                              CX_ERR_UNSUPPORTED), and cx_layers_from_board refuses the game.  0: occluded (default) */
+                              cx_rollout_observations / cx_render_observations only (single-agent games: any element
+                              type; games on the generic kernels: uint8, read off the entity state inside the step),
+                              and cx_layers_from_board refuses the game.  0: occluded (default) */
 } cx_game_desc;
 
 typedef struct cx_game cx_game; /* opaque */

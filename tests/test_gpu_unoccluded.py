@@ -97,6 +97,51 @@ def test_games_outside_the_definition_are_refused():
     # unoccluded layers its update() pays on every step spent there -- a different game, outside the primitives
     with pytest.raises(CompileError):
         make_world("demo3", num_envs=8, occlusion_in_layers=False).its_showtime()
-    # Hello World needs the generic kernels, which derive layers from the finished board
-    with pytest.raises(NotImplementedError):
-        make_world("hello", num_envs=8, occlusion_in_layers=False).its_showtime()
+    # likewise an agent that can walk underneath a sprite: its wall gate falls back to layers['A'], which the sprite
+    # occludes in one game and does not in the other
+    from examples.generality_worlds import make_generality_world
+    with pytest.raises(CompileError):
+        make_generality_world("goal2", num_envs=8, occlusion_in_layers=False).its_showtime()
+
+
+GENERIC_WORLDS = ["hello", "zswap", "ghost", "scroll"]
+
+
+@pytest.mark.parametrize("world", GENERIC_WORLDS)
+def test_generic_games_read_unoccluded_layers_off_their_entity_state(world):
+    """Games on the generic kernels (rolling drape + sprites + backdrop stamps; z-order directives; hiding sprites; a
+    scrolling backdrop) write their unoccluded layers inside the step kernel, frame by frame
+    -- terminal frames included -- and agree with the oracle's restatement; boards, rewards, discounts and flags are
+    those of the occluded game."""
+    from examples.generality_worlds import make_generality_world
+    mk = make_world if world == "hello" else make_generality_world
+    n, T, limit = 48, 40, 11
+    game = mk(world, num_envs=n, max_episode_steps=limit, occlusion_in_layers=False)
+    twin = mk(world, num_envs=n, max_episode_steps=limit)
+    step = mk(world, num_envs=n, max_episode_steps=limit, occlusion_in_layers=False)
+    obs, _, _ = game.its_showtime()
+    twin.its_showtime()
+    sobs, _, _ = step.its_showtime()
+    chars = game.characters
+    first = O.World(world, occlusion_in_layers=False).first[0]
+    assert np.array_equal(obs.layered_board[0].cpu().numpy(), layered_of(first, chars))
+    rng = np.random.Generator(np.random.PCG64(5))
+    acts = rng.integers(0, 5, size=(T, n)).astype(np.uint8)
+    if world == "hello":
+        acts[(acts == 4) & (rng.random((T, n)) < 0.8)] = 2          # fewer quits: longer episodes
+    dacts = torch.from_numpy(acts).cuda()
+    boards, layered, rewards, discounts, flags = game.rollout_observations(dacts)
+    b2, r2, d2, f2 = twin.rollout(dacts)
+    assert torch.equal(boards, b2) and torch.equal(rewards, r2) and torch.equal(flags, f2)
+    for t in range(T):                                              # play(): one launch per step, same layers
+        sobs, _, _ = step.play(dacts[t])
+        assert torch.equal(sobs.board, boards[t]) and torch.equal(sobs.layered_board, layered[t]), (world, t)
+    lay = layered.cpu().numpy()
+    differs = False
+    for i in (0, 7, n - 1):
+        for t, (o, rew, dsc, term, trunc, eng) in enumerate(
+                O.rollout(world, acts[:, i], rebuild_on_done=True, max_episode_steps=limit, occlusion_in_layers=False)):
+            want = layered_of(o, chars)
+            assert np.array_equal(lay[t, i], want), (world, i, t)
+            differs = differs or int(want.sum()) != game.rows * game.cols    # some cell lies in two layers
+    assert differs or world == "scroll"
