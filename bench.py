@@ -8,7 +8,7 @@ A "step" is one Engine.play() over the whole environment batch (N_envs env-steps
 as fused `cx_rollout` launches of `--chunk` steps each (state stays on chip inside a launch); inputs (uint8
 action indices, generated beforehand with the library's Philox kernel) are resident in HBM when the timed
 region starts, and every env-step writes its full observation contract (board 25 B, reward f32, flags u8)
-to HBM.  One launch writes ~1 GB, far more than the 126 MB L2, and consecutive launches alternate between
+to HBM.  One launch writes ~630 MB, far more than the 126 MB L2, and consecutive launches alternate between
 two output buffers.
 
 How the timed region is built (so that it measures the kernels, not the host's launch path):
@@ -52,13 +52,17 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="environments per GPU")
-    ap.add_argument("--chunk", type=int, default=32, help="env-batch steps fused per kernel launch")
+    ap.add_argument("--chunk", type=int, default=20,
+                    help="env-batch steps fused per kernel launch (20: measured optimum of k_agent_rollout at 2^20 envs, "
+                         "DESIGN.md section 5.1; longer rollouts are split into such launches by the library anyway)")
     ap.add_argument("--min-ms", type=float, default=250.0,
                     help="the K-step block is repeated until the timed region lasts at least this long")
     ap.add_argument("--e2e-steps", type=int, default=64)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of each cpu_baseline leg")
     ap.add_argument("--obs-reps", type=int, default=8,
                     help="launches of the secondary board+layered-board measurement (0: skip it)")
+    ap.add_argument("--parity-steps", type=int, default=PARITY_STEPS,
+                    help="steps every rank replays through the CPU oracle before timing (profiler passes shorten it)")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (other BASELINE configs)")
     ap.add_argument("--reference-root", default=os.environ.get("CAMPX_REFERENCE_ROOT", ""),
                     help="directory holding the unmodified reference (campx/ + examples/): the CPU legs then ALSO "
@@ -381,26 +385,37 @@ def measure_config(world_name, n, T, peak, min_ms, sampler, kernel):
     bufs = [nat.alloc_outputs(T) for _ in range(ring)]
     acts = [make(100 + i) for i in range(ring)]
 
-    def one_ring():
-        for i in range(ring):
-            nat.rollout(acts[i], *bufs[i])
+    per_graph = max(ring, 8)                                   # launches per graph replay (replay gaps amortised)
 
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):                              # warm-up off the capture (lazy kernel configuration)
-        for _ in range(2):
+    def one_ring():
+        for i in range(per_graph):
+            nat.rollout(acts[i % ring], *bufs[i % ring])
+
+    # small launches (tens of microseconds) are replayed from a CUDA graph so that host launch cost cannot show;
+    # large ones are issued directly, back to back, so that programmatic dependent launch overlaps their seams
+    # exactly as in the headline measurement
+    use_graph = n * T * per_step < 3e8
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                          # warm-up off the capture (lazy kernel configuration)
+            for _ in range(2):
+                one_ring()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
             one_ring()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+        issue = lambda i: graph.replay()
+    else:
         one_ring()
-    pilot = device_time_ms(lambda i: graph.replay(), 1, 2) / 2
+        issue = lambda i: one_ring()
+    pilot = device_time_ms(issue, 1, 2) / 2
     reps = max(2, int(math.ceil(min_ms / max(pilot, 1e-3))))
     sampler.active = True
-    ms = device_time_ms(lambda i: graph.replay(), 1, reps)
+    ms = device_time_ms(issue, 1, reps)
     sampler.active = False
-    launches = reps * ring
+    launches = reps * per_graph
     env_steps = float(launches) * n * T
     alg = env_steps * per_step + float(launches) * n * state_rw
     gbs = alg / (ms * 1e-3) / 1e9
@@ -408,7 +423,8 @@ def measure_config(world_name, n, T, peak, min_ms, sampler, kernel):
             "env_steps_per_sec": env_steps / (ms * 1e-3), "avg_launch_ms": ms / launches,
             "alg_bytes_per_env_step": per_step + state_rw / T, "achieved_gbs": gbs, "frac": gbs / peak,
             "kernel": kernel, "l2_policy": "ring of %d output buffers, %.0f MB" % (ring, ring * n * T * per_step / 1e6),
-            "issue": "CUDA graph of the ring, replayed",
+            "issue": ("CUDA graph of %d launches over the ring, replayed" if use_graph else
+                      "%d direct launches over the ring per repetition, back to back (PDL)") % per_graph,
             "parity": {"envs": len(envs), "steps": CONFIG_PARITY_STEPS, "ok": bool(ok), "mismatch": where,
                        "what": "board, every layer, reward, discount, done flags == CPU oracle"}}
 
@@ -504,13 +520,13 @@ def run_ours(args):
     p_envs = list(range(min(PARITY_ENVS, n))) + ([n - 1] if n > PARITY_ENVS else [])
     p_ok, p_where = oracle_check(
         WORLD, nat, lambda i: nat.fill_actions(T, seed=SEED, env_offset=env_offset, t0=i * T),
-        lambda a, o: nat.rollout(a, *o), p_envs, PARITY_STEPS, T)
+        lambda a, o: nat.rollout(a, *o), p_envs, args.parity_steps, T)
     p_all = reduce_max(0.0 if p_ok else 1.0) == 0.0
-    parity = {"ranks": world, "envs": len(p_envs), "steps": PARITY_STEPS, "ok": bool(p_all),
+    parity = {"ranks": world, "envs": len(p_envs), "steps": args.parity_steps, "ok": bool(p_all),
               "mismatch": p_where, "kernel": "cx_rollout on this rank's %d-env batch" % n,
               "what": "per rank: first %d envs + last env, %d steps (auto-reset at %d crossed), actions from the rank's "
                       "own Philox stream (cx_fill_actions, env_offset = rank * envs); board, every layer, reward, "
-                      "done flags == oracle/campx_oracle.py; MIN over ranks" % (PARITY_ENVS, PARITY_STEPS, EPISODE_LIMIT)}
+                      "done flags == oracle/campx_oracle.py; MIN over ranks" % (PARITY_ENVS, args.parity_steps, EPISODE_LIMIT)}
     game.reset()                             # back to the its_showtime state, statistics zeroed
 
     n_act = 4
@@ -671,9 +687,9 @@ def run_ours(args):
                 ("demo1_65536_episode_per_launch", lambda: measure_config(
                     "demo1", 65536, EPISODE_LIMIT, peak, 40.0, sampler,
                     "k_agent_rollout<NG=1,GW=2>, one 100-step episode per launch (examples/actor_critic.py:56)")),
-                ("demo2_1048576", lambda: measure_config("demo2", 1 << 20, 32, peak, 40.0, sampler,
+                ("demo2_1048576", lambda: measure_config("demo2", 1 << 20, 20, peak, 40.0, sampler,
                                                          "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
-                ("demo4_1048576", lambda: measure_config("demo4", 1 << 20, 32, peak, 40.0, sampler,
+                ("demo4_1048576", lambda: measure_config("demo4", 1 << 20, 20, peak, 40.0, sampler,
                                                          "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
                 ("actor_critic_rollout_4096", lambda: measure_actor_critic(peak, 40.0, sampler))]
         for name, job in jobs:

@@ -92,6 +92,5 @@ if os.path.exists(ll):
                 "launch per play()), then the secondary board + layered-board measurement (`k_agent_rollout_obs`).") + "\n")
     import shutil
     shutil.copy(ll, os.path.join(out_dir, "%s_launches.csv" % tag))
-json.dump({"k_agent_rollout_track_T32_n1048576": traffic["dram_bytes"], "detail": traffic,
-           "source": "profiles/%s_ncu_agent_rollout.md" % tag}, open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)
+# (profiles/roofline_traffic.json is maintained by hand since round 2: one key per launch geometry bench.py can time)
 print(open(os.path.join(out_dir, "%s_ncu_agent_rollout.md" % tag)).read())

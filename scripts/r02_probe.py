@@ -101,3 +101,28 @@ if __name__ == "__main__":
     if "obs" in what: obs_probe()
 
 
+
+
+def tsweep_probe():
+    """Steps per launch: Hello World (generic kernel) and mid-size single-agent batches (lockstep / drift effect)."""
+    for world, n, Ts in (("hello", 65536, (8, 12, 16, 24, 32)), ("hello", 1 << 18, (8, 12, 16, 24, 32)),
+                         ("demo1", 1 << 18, (12, 16, 20, 24, 32)), ("demo1", 65536, (16, 32, 64))):
+        for T in Ts:
+            g = NativeGame(expected_spec(world, max_episode_steps=100, track_returns=(world != "hello")), n)
+            per = (478 if world == "hello" else 31)
+            nb = max(2, int(600e6 // (n * T * per)) + 1)
+            bufs = [g.alloc_outputs(T) for _ in range(nb)]
+            acts = [g.fill_actions(T, seed=543 + i) for i in range(nb)]
+            if world == "hello":
+                acts = [torch.where(a == 4, torch.zeros_like(a), a).contiguous() for a in acts]   # no quits: steady state
+            gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), max(nb, 8))
+            ms = timed(lambda i: gr.replay(), 1, 6) / max(nb, 8)
+            state = (942 if world == "hello" else 14)
+            alg = n * (T * per + state)
+            print("%s n=%d T=%d: %.4f ms/launch  %.3e env-steps/s  %.0f GB/s (%.1f%%)" % (
+                world, n, T, ms, n * T / ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 65.341), flush=True)
+            del g, bufs, acts, gr
+
+
+if __name__ == "__main__" and "tsweep" in sys.argv[1:]:
+    tsweep_probe()
