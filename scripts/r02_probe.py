@@ -116,7 +116,9 @@ def tsweep_probe():
             if world == "hello":
                 acts = [torch.where(a == 4, torch.zeros_like(a), a).contiguous() for a in acts]   # no quits: steady state
             gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), max(nb, 8))
-            ms = timed(lambda i: gr.replay(), 1, 6) / max(nb, 8)
+            per_replay = timed(lambda i: gr.replay(), 1, 3)
+            timed(lambda i: gr.replay(), 0, max(3, int(100 / per_replay)))            # back under load
+            ms = timed(lambda i: gr.replay(), 1, max(6, int(60 / per_replay))) / max(nb, 8)
             state = (942 if world == "hello" else 14)
             alg = n * (T * per + state)
             print("%s n=%d T=%d: %.4f ms/launch  %.3e env-steps/s  %.0f GB/s (%.1f%%)" % (
