@@ -585,7 +585,7 @@ def run_ours(args):
                 "traffic": ncu_traffic("k_agent_rollout_track_T%d_n%d" % (t_main, n)),
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one T=%d launch "
                                   "(profiles/roofline_traffic.json; a profiler pass, not this run)" % t_main,
-                "kernel": "k_agent_rollout<TRACK=true>", "fused_steps_per_launch": t_main,
+                "kernel": "k_agent_rollout<TRACK=true,NG=1,GW=2> (64 envs per warp)", "fused_steps_per_launch": t_main,
                 "alg_bytes_per_env_step": alg_bytes_total / (n * total_steps),
                 "alg_bytes_per_launch": n * (t_main * per_step + state_rw), "avg_launch_ms": ms / launches,
                 "launches_timed": launches, "peak_source": peak_src}
@@ -686,14 +686,14 @@ def run_ours(args):
         configs = {}
         jobs = [("hello_world_65536", lambda: measure_config("hello", 65536, 32, peak, 100.0, sampler, "k_generic_rollout")),
                 ("demo1_65536", lambda: measure_config("demo1", 65536, 32, peak, 100.0, sampler,
-                                                       "k_agent_rollout<NG=1,GW=2> (64 envs per warp)")),
+                                                       "k_agent_rollout_lane<TRACK=true> (lane = env, 32 envs per warp)")),
                 ("demo1_65536_episode_per_launch", lambda: measure_config(
                     "demo1", 65536, EPISODE_LIMIT, peak, 100.0, sampler,
-                    "k_agent_rollout<NG=1,GW=2>, one 100-step episode per launch (examples/actor_critic.py:56)")),
+                    "k_agent_rollout_lane<TRACK=true>, one 100-step episode per launch (examples/actor_critic.py:56)")),
                 ("demo2_1048576", lambda: measure_config("demo2", 1 << 20, 20, peak, 100.0, sampler,
-                                                         "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
+                                                         "k_agent_rollout<NG=1,GW=2> (64 envs per warp)")),
                 ("demo4_1048576", lambda: measure_config("demo4", 1 << 20, 20, peak, 100.0, sampler,
-                                                         "k_agent_rollout<NG=2,GW=4> (256 envs per warp)")),
+                                                         "k_agent_rollout<NG=1,GW=2> (64 envs per warp)")),
                 ("actor_critic_rollout_4096", lambda: measure_actor_critic(peak, 100.0, sampler))]
         for name, job in jobs:
             try:

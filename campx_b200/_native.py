@@ -7,7 +7,7 @@ compute entry point is needed, this module raises.  The library is built in-tree
 import ctypes
 import os
 
-CX_ABI_VERSION = 3
+CX_ABI_VERSION = 4
 CX_MAX_ENTITIES = 16
 CX_MAX_ACTIONS = 8
 CX_MAX_CHARS = 32
@@ -138,6 +138,7 @@ PROTOTYPES = {
     "cx_set_entity_state": (ctypes.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "cx_get_render_state": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "cx_get_episode_state": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "cx_stats_fold": (ctypes.c_int, [_P, _P, _P]),
     "cx_stats_read": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_double), _P]),
     "cx_step_perf": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _P]),
     "cx_discounted_returns": (ctypes.c_int, [_P, _P, _P, _P, _I32, _I64, ctypes.c_float, _P, _P]),

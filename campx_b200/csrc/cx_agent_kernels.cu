@@ -39,7 +39,7 @@
 #define CX_OPT_ACT2 1  // action loads run two steps ahead of their use
 #endif
 #ifndef CX_OPT_CTASYNC
-#define CX_OPT_CTASYNC 1   // large-batch build: the CTA's warps meet at a named barrier before every step
+#define CX_OPT_CTASYNC 2   // the CTA's warps meet at a named barrier before every step (2^20 envs, 64-env build: 95.8 % against 94.7 %)
 #endif
 #ifndef CX_OPT_TMA
 #define CX_OPT_TMA 1   // board tiles leave shared memory as one cp.async.bulk (UBLKCP) per warp and step
@@ -220,11 +220,11 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   constexpr bool TMA = VEC && (CX_OPT_TMA != 0);
   const uint64_t l2pol = l2_evict_first_policy();
 
-  // Large-batch build: the warps of a CTA meet at a named barrier before every step.  Nothing they compute depends on
-  // it; it keeps their tiles (4 x 6.4 KB, contiguous in HBM) leaving at the same time, and with them the DRAM rows they
-  // share: +1.3 % at 2^20 envs (91.9 % against 90.6 % of the copy peak at 20 steps per launch; a barrier every fourth
-  // step: +0.5 %).  The same effect is why ~20-step launches beat longer ones (cx_launch_agent_rollout).
-  constexpr bool CTASYNC = CX_OPT_CTASYNC != 0 && NG == 2 && VEC;
+  // The warps of a CTA meet at a named barrier before every step.  Nothing they compute depends on it; it keeps their
+  // tiles (contiguous in HBM) leaving at the same time, and with them the DRAM rows they share: 256-env build +1.3 % at
+  // 2^20 envs (91.9 % against 90.6 % of the copy peak at 20 steps per launch; a barrier every fourth step: +0.5 %),
+  // 64-env build +1 % (95.8 % against 94.7 %).
+  constexpr bool CTASYNC = CX_OPT_CTASYNC != 0 && (NG == 2 || CX_OPT_CTASYNC == 2) && VEC;   // 1: the 256-env build only
   const int64_t warps_total = (n + WT - 1) / WT;
   const int active_threads = 32 * (int)min((int64_t)WARPS, warps_total - (int64_t)blockIdx.x * WARPS);
   for (int t = 0; t < P.T; ++t) {
@@ -397,15 +397,16 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
     const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
     const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
     if (lane == 0) {
+      double* sp = cx_stat_stripe(P.stats, (uint32_t)(blockIdx.x * WARPS + warp));
       if (cnt > 0.0) {
-        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
-        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
-        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
-        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+        atomicAdd(sp + CX_STAT_EPISODES, cnt);
+        atomicAdd(sp + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(sp + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(sp + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
-      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
+      atomicAdd(sp + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
 }
@@ -482,8 +483,10 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   // envs per warp, by envs per SM (measured on 148 SMs, Demo 1, 32-step launches, % of the HBM copy peak for
   // 64 / 128 / 256 envs per warp: 65,536 envs 45 / 36 / 19, 2^17 65 / 62 / 37, 2^18 79 / 87 / 63, 2^19 83 / 82 / 79,
   // 2^20 77 / 84 / 86; scripts/r02_probe.py).  CX_AGENT_WT = 64 | 128 | 256 forces a build.
-  const int64_t per_sm = (n + g->sm_count - 1) / g->sm_count;
-  int WT = per_sm >= 24 * 256 ? 256 : (per_sm >= 12 * 128 ? 128 : 64);
+  // Since the episode statistics are striped (cx_internal.cuh: CX_STAT_STRIPES; the end-of-launch atomics of 4,096 warps
+  // on one line used to cost the 256-env build least) the 64-env build wins at every size that reaches this kernel:
+  // boat_race, % of the copy peak for 64 / 128 / 256 envs per warp: 2^19 envs 91.5 / 84.6 / 73, 2^20 95 / 89-92 / 88-93.
+  int WT = 64;
   if (const char* dbg = getenv("CX_AGENT_WT")) {
     const int w = atoi(dbg);
     if (w == 64 || w == 128 || w == 256) WT = w;

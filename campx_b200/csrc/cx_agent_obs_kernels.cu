@@ -280,15 +280,16 @@ __global__ void __launch_bounds__(OBS_THREADS) k_agent_rollout_obs(const __grid_
     const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
     const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
     if (lane == 0) {
+      double* sp = cx_stat_stripe(P.stats, (uint32_t)(blockIdx.x * OBS_WARPS + warp));
       if (cnt > 0.0) {
-        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
-        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
-        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
-        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+        atomicAdd(sp + CX_STAT_EPISODES, cnt);
+        atomicAdd(sp + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(sp + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(sp + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
-      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
+      atomicAdd(sp + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
 }

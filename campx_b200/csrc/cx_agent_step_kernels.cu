@@ -243,15 +243,16 @@ __global__ void __launch_bounds__(ST_THREADS) k_agent_step_flat(const __grid_con
       const double len = warp_sum((double)st.len), sum = warp_sum(st.sum), sumsq = warp_sum(st.sumsq);
       const float mx = warp_max(st.mx), ngmn = warp_max(st.negmn);
       if ((tid & 31) == 0) {
-        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
-        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
-        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
-        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+        double* sp = cx_stat_stripe(P.stats, (uint32_t)(blockIdx.x * (blockDim.x >> 5) + (tid >> 5)));
+        atomicAdd(sp + CX_STAT_EPISODES, cnt);
+        atomicAdd(sp + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(sp + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(sp + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
     }
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)P.n);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(cx_stat_stripe(P.stats, 0) + CX_STAT_ENV_STEPS, (double)P.n);
   }
 }
 

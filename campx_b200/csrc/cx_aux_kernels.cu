@@ -14,10 +14,36 @@ namespace {
 constexpr int TB = 256;
 inline unsigned blocks_for(int64_t n, int per_block = TB) { return (unsigned)((n + per_block - 1) / per_block); }
 
+__device__ __forceinline__ double stat_identity(int i) {
+  return (i == CX_STAT_RETURN_MAX || i == CX_STAT_NEG_RETURN_MIN) ? -INFINITY : 0.0;
+}
+
+// head block + every stripe (cx_internal.cuh: CX_STAT_STRIPES)
 __global__ void k_stats_init(double* stats) {
-  const int i = threadIdx.x;
-  if (i < CX_STATS_DOUBLES)
-    stats[i] = (i == CX_STAT_RETURN_MAX || i == CX_STAT_NEG_RETURN_MIN) ? -INFINITY : 0.0;
+  const int i = blockIdx.x * TB + threadIdx.x;
+  if (i < (1 + CX_STAT_STRIPES) * CX_STATS_DOUBLES) stats[i] = stat_identity(i % CX_STATS_DOUBLES);
+}
+
+// Add the stripes into the head block and clear them: one block, thread = (stripe group, statistic); sums are taken
+// in a fixed order, so the result does not depend on which warp added to which stripe first.
+__global__ void k_stats_fold(double* stats) {
+  __shared__ double part[TB];
+  const int i = threadIdx.x % CX_STATS_DOUBLES, grp = threadIdx.x / CX_STATS_DOUBLES, ngrp = TB / CX_STATS_DOUBLES;
+  const bool is_max = i == CX_STAT_RETURN_MAX || i == CX_STAT_NEG_RETURN_MIN;
+  double acc = stat_identity(i);
+  for (int s = grp; s < CX_STAT_STRIPES; s += ngrp) {
+    double* p = stats + (1 + s) * CX_STATS_DOUBLES + i;
+    const double v = *p;
+    acc = is_max ? fmax(acc, v) : acc + v;
+    *p = stat_identity(i);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (grp == 0) {
+    double tot = stats[i];
+    for (int g = 0; g < ngrp; ++g) tot = is_max ? fmax(tot, part[g * CX_STATS_DOUBLES + i]) : tot + part[g * CX_STATS_DOUBLES + i];
+    stats[i] = tot;
+  }
 }
 
 __global__ void k_agent_reset(uint8_t* cell, uint16_t* tstep, float* ret, int track, int init_cell,
@@ -516,12 +542,19 @@ __global__ void k_step_perf(const uint8_t* __restrict__ region, int cells, int n
 
 }  // namespace
 
+int cx_launch_stats_fold(void* d_state, cudaStream_t s) {
+  k_stats_fold<<<1, TB, 0, s>>>(static_cast<double*>(d_state));   // off_stats == 0
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
 int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s) {
   const CxStateLayout L = cx_layout(g, n);
   uint8_t* base = static_cast<uint8_t*>(d_state);
   uint16_t* tstep = reinterpret_cast<uint16_t*>(base + L.off_tstep);
   float* ret = reinterpret_cast<float*>(base + L.off_ret);
-  if (!d_mask) k_stats_init<<<1, 32, 0, s>>>(reinterpret_cast<double*>(base + L.off_stats));
+  if (!d_mask)
+    k_stats_init<<<blocks_for((1 + CX_STAT_STRIPES) * CX_STATS_DOUBLES), TB, 0, s>>>(reinterpret_cast<double*>(base + L.off_stats));
   if (g->path == CX_PATH_AGENT) {
     k_agent_reset<<<blocks_for(n), TB, 0, s>>>(base + L.off_dyn, tstep, ret, g->info.tracks, g->ah.init_cell,
                                                d_mask, n);

@@ -44,7 +44,7 @@ CxStateLayout cx_layout(const cx_game* g, int64_t n) {
   L.n = n;
   int64_t off = 0;
   L.off_stats = off;
-  off = align_up(off + CX_STATS_DOUBLES * (int64_t)sizeof(double), 256);
+  off = align_up(off + (1 + CX_STAT_STRIPES) * CX_STATS_DOUBLES * (int64_t)sizeof(double), 256);
   L.off_tstep = off;
   if (g->info.tracks) off = align_up(off + n * 2, 256);
   L.off_ret = off;
@@ -1015,6 +1015,16 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     // (profiles/r02_probes.md).  CX_AGENT_SMALL_N overrides the threshold (0: always k_agent_rollout).
     int64_t small_n = 32768;
     if (const char* dbg = getenv("CX_AGENT_SMALL_N")) small_n = atoll(dbg);
+    // Batches of whole warps up to ~1,800 envs per SM (2^18 on 148 SMs): k_agent_rollout_lane (lane = env, STG.128 tile
+    // copies; cx_agent_lane_kernels.cu).  Demo 1, 32-step launches, % of the copy peak against the best tile build:
+    // 4,096 envs 7.1 / 3.5, 65,536 56.5 / 49.7, 2^17 80.0 / 77.5, 2^18 90.3 / 90.6, 2^19 89.6 / 91.5, 2^20 86 / 95.
+    // CX_AGENT_LANE_N overrides the threshold (0: never).
+    int64_t lane_n = (int64_t)g->sm_count * 1800;
+    if (const char* dbg = getenv("CX_AGENT_LANE_N")) lane_n = atoll(dbg);
+    if (n <= lane_n && T > 1 &&
+        cx_agent_lane_applies(g, n, d_actions, synth.actions_out, d_reward, d_discount, d_flags, d_board))
+      return cx_launch_agent_rollout_lane(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
+                                          (cudaStream_t)stream);
     if (g->ah.cells > CX_AGENT_TILE_MAX_CELLS || n < small_n)  // large boards, small batches: lane-per-env kernel, board only
       return cx_launch_agent_rollout_obs(g, d_state, n, T, d_actions, synth, d_reward, d_discount, d_flags, d_board,
                                          nullptr, (cudaStream_t)stream);
@@ -1195,12 +1205,22 @@ extern "C" int cx_get_render_state(const cx_game* g, const void* d_state, int64_
   return cx_launch_get_render_state(g, d_state, n, d_zorder, d_visible, d_backdrop_off, (cudaStream_t)stream);
 }
 
+extern "C" int cx_stats_fold(const cx_game* g, void* d_state, void* stream) {
+  if (!g || !d_state) {
+    cx_set_error("cx_stats_fold: NULL argument");
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_stats_fold(d_state, (cudaStream_t)stream);
+}
+
 extern "C" int cx_stats_read(const cx_game* g, const void* d_state, double* h_out, void* stream) {
   if (!g || !d_state || !h_out) {
     cx_set_error("cx_stats_read: NULL argument");
     return CX_ERR_INVALID_ARG;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  int rc = cx_launch_stats_fold(const_cast<void*>(d_state), s);   // the partial blocks are part of the statistics
+  if (rc) return rc;
   CX_CUDA_OK(cudaMemcpyAsync(h_out, d_state, CX_STATS_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, s));
   CX_CUDA_OK(cudaStreamSynchronize(s));
   return CX_OK;

@@ -1096,15 +1096,16 @@ __global__ void __launch_bounds__(BLK, OCC) k_generic_rollout(const __grid_const
     const double sum = warp_sum(ep_sum), sumsq = warp_sum(ep_sumsq);
     const float mx = warp_max(ep_max), ngmn = warp_max(ep_negmin);
     if (lane == 0) {
+      double* sp = cx_stat_stripe(P.stats, (uint32_t)(blockIdx.x * wpc + warp));
       if (cnt > 0.0) {
-        atomicAdd(P.stats + CX_STAT_EPISODES, cnt);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUM, sum);
-        atomicAdd(P.stats + CX_STAT_RETURN_SUMSQ, sumsq);
-        atomicAdd(P.stats + CX_STAT_LENGTH_SUM, len);
-        atomic_max_double(P.stats + CX_STAT_RETURN_MAX, (double)mx);
-        atomic_max_double(P.stats + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+        atomicAdd(sp + CX_STAT_EPISODES, cnt);
+        atomicAdd(sp + CX_STAT_RETURN_SUM, sum);
+        atomicAdd(sp + CX_STAT_RETURN_SUMSQ, sumsq);
+        atomicAdd(sp + CX_STAT_LENGTH_SUM, len);
+        atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
+        atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
-      atomicAdd(P.stats + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
+      atomicAdd(sp + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
 }

@@ -162,10 +162,23 @@ struct CxGenHeader {
   uint8_t zdir[CX_MAX_ACTIONS][CX_MAX_ZDIR_GAME];  // move_this << 4 | in_front_of_that (0xF: None), in call order
 };
 
+// Episode statistics.  The float64[CX_STATS_DOUBLES] block at the head of the state blob holds the folded totals; the
+// kernels accumulate into CX_STAT_STRIPES partial blocks behind it (same layout, one 64-byte line each), picked by the
+// global warp index.  With one block, every warp of a launch sent its 5-7 atomics to the same line and the L2 worked
+// them off one per clock: an episode end of all 65,536 envs of BASELINE config 1 (2,048 warps) cost 8 us on top of a
+// 15 us launch, 28,000 atomics at 2^20 envs (measured, scripts/r02_probe.py stgsweep).  cx_stats_read / cx_stats_fold
+// add the stripes into the head block and clear them.
+#define CX_STAT_STRIPES 1024
+#ifdef __CUDACC__
+__device__ __forceinline__ double* cx_stat_stripe(double* stats, uint32_t key) {
+  return stats + CX_STATS_DOUBLES * (1u + (key & (CX_STAT_STRIPES - 1u)));
+}
+#endif
+
 // ---- state blob layout (caller-allocated; see cx_state_bytes) ----
 struct CxStateLayout {
   int64_t n;
-  int64_t off_stats;   // 8 doubles at offset 0
+  int64_t off_stats;   // 8 doubles at offset 0 (folded totals), then CX_STAT_STRIPES partial blocks of 8 doubles
   int64_t off_tstep;   // u16 [n]
   int64_t off_ret;     // f32 [n]
   int64_t off_dyn;     // agent path: u8 [n]; generic: u16 [n_dyn][n]
@@ -229,6 +242,12 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
                                 const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                                 uint8_t* d_board, uint8_t* d_layered /* or null */, cudaStream_t s);
 bool cx_agent_obs_applies(const cx_game* g, bool layers);
+// small batches of single-agent games: lane = env, boards copied out with STG.128 (cx_agent_lane_kernels.cu)
+bool cx_agent_lane_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_actions_out,
+                           const void* d_reward, const void* d_discount, const void* d_flags, const void* d_board);
+int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
+                                 const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
+                                 uint8_t* d_board, cudaStream_t s);
 // one Engine.play() per launch, stateless composer (cx_agent_step_kernels.cu); lay_dtype: CX_DTYPE_* of d_layered
 bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_layered);
 // d_actions == nullptr: render only (nothing is stepped, the state is not written)
@@ -241,6 +260,7 @@ int cx_launch_generic_rollout(const cx_game* g, void* d_state, int64_t n, int32_
                               const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                               uint8_t* d_board, cudaStream_t s, uint8_t* d_layered = nullptr);
 int cx_launch_reset(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_mask, cudaStream_t s);
+int cx_launch_stats_fold(void* d_state, cudaStream_t s);
 int cx_launch_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s);
 int cx_launch_generic_render(const cx_game* g, const void* d_state, int64_t n, uint8_t* d_board, cudaStream_t s,
                              uint8_t* d_layered = nullptr);

@@ -283,9 +283,16 @@ class NativeGame(object):
                                                    _ptr(returns), _stream()))
         return steps, returns
 
+    def fold_stats(self):
+        """Add the kernels' partial statistics blocks into the float64[8] block at the head of the state blob
+        (asynchronous on the current stream)."""
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_stats_fold(self._handle, _ptr(self.state), _stream()))
+
     @property
     def stats_tensor(self):
-        """float64[8] view of the episode statistics inside the state blob (all-reducible in place)."""
+        """float64[8] view of the (folded) episode statistics inside the state blob (all-reducible in place)."""
+        self.fold_stats()
         return self.state[:8 * N.CX_STATS_DOUBLES].view(torch.float64)
 
     def stats(self):

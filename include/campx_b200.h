@@ -58,7 +58,7 @@ extern "C" {
 #define CX_API
 #endif
 
-#define CX_ABI_VERSION 3
+#define CX_ABI_VERSION 4
 
 #define CX_MAX_ENTITIES 16   /* sprites + drapes in one game                         */
 #define CX_MAX_ACTIONS 8     /* discrete actions                                     */
@@ -339,7 +339,13 @@ CX_API int cx_get_render_state(const cx_game* game, const void* d_state, int64_t
 CX_API int cx_get_episode_state(const cx_game* game, const void* d_state, int64_t n_envs, int32_t* d_steps,
                          float* d_returns, void* stream);
 
-/* Synchronously copy the CX_STATS_DOUBLES episode statistics to host memory. */
+/* The kernels accumulate the episode statistics in partial blocks inside the state blob (one per group of warps, so
+ * that their atomics do not serialise on one line).  cx_stats_fold adds them into the float64[CX_STATS_DOUBLES] block at
+ * the head of the blob (asynchronous on `stream`); call it before reading that block on the device, e.g. before the
+ * all-reduce over ranks (campx_b200/dist.py <- the reporting loop of examples/actor_critic.py:176-199). */
+CX_API int cx_stats_fold(const cx_game* game, void* d_state, void* stream);
+
+/* Fold, then synchronously copy the CX_STATS_DOUBLES episode statistics to host memory. */
 CX_API int cx_stats_read(const cx_game* game, const void* d_state, double* h_out, void* stream);
 
 /* Discounted returns over a rollout, on the device (finish_episode, examples/actor_critic.py:115-135:

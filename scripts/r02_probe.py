@@ -55,13 +55,17 @@ def step_probe():
 
 def ring_probe():
     T = 32
-    modes = {"tile256": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="256"), "tile128": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="128"),
-             "tile64": dict(CX_AGENT_SMALL_N="0", CX_AGENT_WT="64"),
-             "lane_ring2": dict(CX_AGENT_SMALL_N=str(1 << 40), CX_OBS_RING="2"), "auto": dict()}
+    modes = {"tile256": dict(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="256"), "tile128": dict(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="128"),
+             "tile64": dict(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="64"),
+             "lane_ring2": dict(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N=str(1 << 40), CX_OBS_RING="2"), "stg": dict(CX_AGENT_LANE_N=str(1 << 40)),
+             "auto": dict()}
+    if os.environ.get("PROBE_MODES"):
+        modes = {k: v for k, v in modes.items() if k in os.environ["PROBE_MODES"].split(",")}
+    sizes = [int(x) for x in os.environ.get("PROBE_SIZES", "4096,16384,32768,65536,131072,262144,524288,1048576").split(",")]
     for world in ("demo1",):
-        for n in (4096, 16384, 32768, 65536, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
+        for n in sizes:
             for mode, env in modes.items():
-                for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING"):
+                for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N"):
                     os.environ.pop(k, None)
                 os.environ.update(env)
                 g = NativeGame(expected_spec(world, max_episode_steps=100, track_returns=True), n)
@@ -73,7 +77,7 @@ def ring_probe():
                 print("%s n=%d T=%d %s: %.4f ms/launch  %.3e env-steps/s  %.0f GB/s (%.1f%%)" % (
                     world, n, T, mode, ms, n * T / ms * 1e3, n * T * 31.44 / ms / 1e6, n * T * 31.44 / ms / 1e6 / 65.341), flush=True)
                 del g, bufs, acts, gr
-    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING"):
+    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N"):
         os.environ.pop(k, None)
 
 
@@ -128,3 +132,63 @@ def tsweep_probe():
 
 if __name__ == "__main__" and "tsweep" in sys.argv[1:]:
     tsweep_probe()
+
+
+def stg_sweep():
+    """Small batches: launch time against steps per launch (slope = per-step time, intercept = fixed cost per launch),
+    with and without episode tracking, for the 64-env tile build and the STG lane kernel."""
+    for mode, env in (("tile64", dict(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="64")), ("stg", dict(CX_AGENT_LANE_N=str(1 << 40)))):
+        for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        for track in (True, False):
+            for n in (4096, 65536):
+                for T in (8, 16, 32, 64, 128):
+                    kw = dict(max_episode_steps=100, track_returns=True) if track else dict()
+                    g = NativeGame(expected_spec("demo1", **kw), n)
+                    nb = max(2, int(400e6 // (n * T * 31)) + 1)
+                    bufs = [g.alloc_outputs(T) for _ in range(nb)]
+                    acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+                    gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), nb)
+                    ms = timed(lambda i: gr.replay(), 2, max(3, int(30 / (nb * 0.03)))) / nb
+                    print("%s track=%d n=%d T=%d: %.2f us/launch  %.3f us/step  %.0f GB/s (%.1f%%)" % (
+                        mode, track, n, T, ms * 1e3, ms * 1e3 / T, n * T * 31.44 / ms / 1e6, n * T * 31.44 / ms / 1e6 / 65.341), flush=True)
+                    del g, bufs, acts, gr
+    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N"):
+        os.environ.pop(k, None)
+
+
+if __name__ == "__main__":
+    if "tsweep" in sys.argv[1:]: tsweep_probe()
+    if "stgsweep" in sys.argv[1:]: stg_sweep()
+
+
+def big_sweep():
+    """Large batches: kernel build x steps per launch (boat_race, the bench workload)."""
+    for n in (1 << 19, 1 << 20):
+        for mode, env in (("tile64", dict(CX_AGENT_WT="64")), ("tile128", dict(CX_AGENT_WT="128")), ("tile256", dict(CX_AGENT_WT="256")), ("stg", dict(CX_AGENT_LANE_N=str(1 << 40)))):
+            if os.environ.get("PROBE_MODES") and mode not in os.environ["PROBE_MODES"].split(","):
+                continue
+            for T in (12, 16, 20, 24, 32, 48):
+                for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N", "CX_AGENT_SUBT"):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                os.environ["CX_AGENT_SUBT"] = "0"
+                g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+                nb = max(2, int(1300e6 // (n * T * 31)) + 1)
+                bufs = [g.alloc_outputs(T) for _ in range(nb)]
+                acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+                fn = lambda i: g.rollout(acts[i % nb], *bufs[i % nb])
+                per = timed(fn, 2, 4)
+                timed(fn, 0, max(4, int(100 / per)))
+                ms = timed(fn, 2, max(8, int(150 / per)))
+                alg = n * (T * 31 + 14)
+                print("boat_race n=%d T=%d %s: %.4f ms/launch  %.3e env-steps/s  %.0f GB/s (%.1f%%)" % (
+                    n, T, mode, ms, n * T / ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 65.341), flush=True)
+                del g, bufs, acts
+    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_OBS_RING", "CX_AGENT_LANE_N", "CX_AGENT_SUBT"):
+        os.environ.pop(k, None)
+
+
+if __name__ == "__main__":
+    if "bigsweep" in sys.argv[1:]: big_sweep()

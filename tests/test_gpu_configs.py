@@ -153,6 +153,7 @@ def test_register_state_kernel_builds_agree(monkeypatch):
         game.its_showtime()
         acts = game.native.fill_actions(T, seed=5)
         boards, rewards, discounts, flags = game.rollout(acts)
+        game.native.fold_stats()   # partial statistics blocks follow the launch geometry
         results.append((boards.clone(), rewards.clone(), flags.clone(), game.native.state.clone(), game.episode_stats()))
     monkeypatch.delenv("CX_GEN_BUILD")
     for other in results[1:]:

@@ -282,6 +282,7 @@ def test_in_kernel_random_rollout_equals_fill_actions_plus_rollout(world, n):
     assert torch.equal(played, acts)
     for x, y in zip(ra, rb):
         assert (x is None and y is None) or torch.equal(x, y)
+    a.native.fold_stats(), b.native.fold_stats()
     assert torch.equal(a.native.state, b.native.state)
     rc = b.rollout_random(3, seed, env_offset=off, t0=t0 + T)           # without writing the actions out
     rd = a.rollout(a.native.fill_actions(3, seed=seed, env_offset=off, t0=t0 + T))
@@ -360,5 +361,6 @@ def test_play_emits_the_whole_observation_from_one_kernel_once_layers_are_read(w
             assert torch.equal(lay, b.native.layers_from_board(ob.board)), t
             for k, ch in enumerate(oa.characters):
                 assert torch.equal(oa.layers[ch], (ob.board == ord(ch)).to(torch.uint8)), (t, ch)
+    a.native.fold_stats(), b.native.fold_stats()
     assert torch.equal(a.native.state, b.native.state)
     assert a.episode_stats() == b.episode_stats()

@@ -221,6 +221,7 @@ def test_random_wall_and_treasure_worlds(rows, cols, seed, n):
     boards2, layered2, rewards2, _, flags2 = b.rollout_observations(acts)
     assert torch.equal(boards, boards2) and torch.equal(rewards, rewards2) and torch.equal(flags, flags2)
     assert torch.equal(layered2, b.native.layers_from_board(boards2))
+    a.native.fold_stats(), b.native.fold_stats()
     assert torch.equal(a.native.state, b.native.state)
     assert int((flags == 2).sum()) == 2 * n                               # two time limits (17, 34) per env
 

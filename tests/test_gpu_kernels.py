@@ -15,13 +15,17 @@ pytestmark = pytest.mark.gpu
 WORLDS = ["boat_race", "demo1", "demo2", "demo3", "demo4", "hello"]
 
 
-@pytest.fixture(autouse=True, params=["auto", "wt64", "wt128", "wt256"])
+@pytest.fixture(autouse=True, params=["auto", "wt64", "wt128", "wt256", "stg"])
 def agent_kernel(request, monkeypatch):
     """Single-agent worlds run on several kernels: tiny batches take the lane-per-env kernel (cx_rollout's default),
     larger ones k_agent_rollout in one of three builds (64 / 128 / 256 envs per warp; 256 is the bench kernel), single
     steps the stateless composer.  Every test of this module runs on all of them: CX_AGENT_SMALL_N=0 sends small
-    batches to k_agent_rollout as well and CX_AGENT_WT picks its build."""
-    if request.param != "auto":
+    batches to k_agent_rollout as well and CX_AGENT_WT picks its build; "stg" sends every batch of whole warps to the
+    small-batch kernel (k_agent_rollout_lane: lane = env, STG.128 tile copies)."""
+    if request.param == "stg":
+        monkeypatch.setenv("CX_AGENT_LANE_N", str(1 << 40))
+    elif request.param != "auto":
+        monkeypatch.setenv("CX_AGENT_LANE_N", "0")
         monkeypatch.setenv("CX_AGENT_SMALL_N", "0")
         monkeypatch.setenv("CX_AGENT_WT", request.param[2:])
     return request.param
@@ -109,6 +113,7 @@ def test_random_rollout_vs_oracle(world, n):
         g2.step(dacts[t].contiguous(), b1, r1, f1, d1)
         assert torch.equal(b1, board[t]) and torch.equal(r1, reward[t]) and torch.equal(f1, flags[t])
         assert torch.equal(d1, disc[t])
+    g.fold_stats(), g2.fold_stats()   # the partial statistics blocks depend on the launch geometry
     if not torch.equal(g.state, g2.state):
         bad = (g.state != g2.state).nonzero().flatten().cpu().tolist()
         raise AssertionError("state blobs differ at byte offsets %s: %s vs %s; stats %s vs %s" % (
