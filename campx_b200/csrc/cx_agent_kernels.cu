@@ -427,7 +427,9 @@ int launch(const AgentParams& P, unsigned grid, unsigned block, size_t smem, cud
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const char* pdl_env = getenv("CX_AGENT_PDL");   // development knob, read per launch
+  const bool pdl = pdl_env == nullptr || atoi(pdl_env) != 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout<TRACK, VEC, SYNTH, NG, GW>, P));
@@ -507,19 +509,23 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
     return CX_ERR_INVALID_ARG;
   }
   const bool track = g->ah.track != 0, sy = synth.on != 0;
-  if (WT == 64) return launch_s<1, 2>(sy, track, vec, P, (unsigned)grid, block, smem, s);
-  if (WT == 128) return launch_s<1, 4>(sy, track, vec, P, (unsigned)grid, block, smem, s);
-  // Large batches: a long rollout goes out as back-to-back launches of about 20 steps (PDL overlaps each prologue with
-  // the previous tail; the env state makes the round trip through HBM, 14 bytes per env and launch).  The warps of a
-  // launch never synchronise, so over a long launch they drift apart and the write stream loses its DRAM row
-  // locality: measured at 2^20 envs, % of the copy peak by steps per launch -- 8: 86.8, 12: 88.3, 16: 90.0,
-  // 20: 91.0, 24: 90.2, 28: 89.2, 32: 87.4, 48: 81.7, 64: 81.1, 100: 79.8.  CX_AGENT_SUBT overrides (0: never split).
-  int sub = 20;
+  // Large batches: a long rollout goes out as back-to-back launches of about 25-32 steps (PDL overlaps each prologue
+  // with the previous tail; the env state makes the round trip through HBM, 14 bytes per env and launch).  The warps
+  // of a launch synchronise only inside their CTA, so over a long launch the CTAs drift apart and the write stream
+  // loses its DRAM row locality: measured at 2^20 envs with the 64-env build, % of the copy peak by steps per launch
+  // -- 12: 95.2, 16: 96.1, 24: 96.0, 32: 96.1, 48: 95.5, 100: 92.3 (256-env build before the statistics were striped:
+  // 20: 91.0, 32: 87.4, 100: 79.8).  CX_AGENT_SUBT overrides the piece length (0: never split).
+  int sub = 32;
   if (const char* dbg = getenv("CX_AGENT_SUBT")) sub = atoi(dbg);
-  if (sub <= 0 || T <= sub + sub / 2) return launch_s<2, 4>(sy, track, vec, P, (unsigned)grid, block, smem, s);
+  auto launch_wt = [&](const AgentParams& Q) {
+    if (WT == 64) return launch_s<1, 2>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+    if (WT == 128) return launch_s<1, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+    return launch_s<2, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+  };
+  if (sub <= 0 || T <= sub + sub / 2 || n < (int64_t)g->sm_count * 3000) return launch_wt(P);   // small batches: one launch
   const int pieces = (T + sub - 1) / sub;
   for (int i = 0, t = 0; i < pieces; ++i) {
-    const int steps = (T - t + (pieces - i) - 1) / (pieces - i);   // balanced: 32 -> 16 + 16, 100 -> 5 x 20
+    const int steps = (T - t + (pieces - i) - 1) / (pieces - i);   // balanced: 100 -> 4 x 25
     AgentParams Q = P;
     Q.T = steps;
     Q.t0 = P.t0 + (uint64_t)t;
@@ -529,7 +535,7 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
     if (P.discount) Q.discount = P.discount + (int64_t)t * n;
     Q.flags = P.flags + (int64_t)t * n;
     Q.board = P.board + (int64_t)t * n * g->ah.cells;
-    const int rc = launch_s<2, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+    const int rc = launch_wt(Q);
     if (rc != CX_OK) return rc;
     t += steps;
   }

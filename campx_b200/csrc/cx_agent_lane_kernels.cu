@@ -47,7 +47,35 @@ struct LaneParams {
 constexpr int LANE_MAX_WARPS = 4;
 constexpr int LANE_UNR = 4;   // steps per unrolled group (tile parity and action registers are indexed statically)
 
-template <bool TRACK, bool SYNTH>
+// shared-memory accesses by 32-bit shared-window address: the table reads carry no ordering (read-only data, free to
+// schedule), the tile accesses are ordered against __syncwarp by their memory clobber
+__device__ __forceinline__ uint32_t lds_tab_u32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_tab_f32(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_tab_u8(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_tile_u8(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_tile_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+// DISC: the game can change the discount (a [T, n] discount stream is written); SMALL: boards of up to 32 cells (at
+// most two 16-byte chunks of the warp's tile per lane)
+template <bool TRACK, bool SYNTH, bool DISC, bool SMALL>
 __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(const __grid_constant__ LaneParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CxAgentHeader& H = P.h;
@@ -67,18 +95,15 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
   if (env0 >= n) return;
   const int64_t env = env0 + lane;
 
-  const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
-  const float* __restrict__ s_tr = reinterpret_cast<const float*>(smem + H.off_tr);
-  const float* __restrict__ s_td = reinterpret_cast<const float*>(smem + H.off_td);
-  const uint8_t* __restrict__ s_basech = smem + H.off_basech;
-  const uint8_t* __restrict__ s_shown = smem + H.off_shown;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const uint32_t a_tt = sbase + H.off_tt, a_tr = sbase + H.off_tr, a_td = sbase + H.off_td;
+  const uint32_t a_basech = sbase + H.off_basech;
   const uint32_t stride = H.stride, n_actions = H.n_actions;
-  const uint8_t agent_char = (uint8_t)H.agent_char;
+  const uint32_t agent_char = (uint32_t)H.agent_char & 0xFF;
   const uint32_t none = cells;
   // the step counter's common case ends one short of the time limit / of saturation
-  const uint32_t limit = min(H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu, (uint32_t)CX_STEP_MAX);
   const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
-  const bool want_discount = P.discount != nullptr;
+  const uint32_t limit = min(max_steps, (uint32_t)CX_STEP_MAX);
 
   // two tiles per warp, back to back: 2 * 32 boards of the static scene, written as 16-byte pattern chunks
   const int tile_bytes = 32 * cells, nch = tile_bytes / 16;   // 32 * cells is a multiple of 32
@@ -98,50 +123,59 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
     ts = P.tstep[env];
     rt = P.ret[env];
   }
-  const int mine0 = tile0 + lane * cells;                 // this env's board in tile 0; tile 1 is tile_bytes further
+  const uint32_t a_mine = sbase + tile0 + lane * cells;   // this env's board in tile 0; tile 1 is tile_bytes further
+  const uint32_t a_copy = sbase + tile0 + lane * 16;      // this lane's first chunk of tile 0
   uint32_t drawn[2];
-  drawn[0] = drawn[1] = s_shown[cell];
+  drawn[0] = drawn[1] = smem[H.off_shown + cell];
   if (drawn[0] != none) {
-    smem[mine0 + drawn[0]] = agent_char;
-    smem[mine0 + tile_bytes + drawn[0]] = agent_char;
+    sts_tile_u8(a_mine + drawn[0], agent_char);
+    sts_tile_u8(a_mine + tile_bytes + drawn[0], agent_char);
   }
   LaneStats& stats = reinterpret_cast<LaneStats*>(smem + H.blob_bytes + (size_t)WARPS * 2 * tile_bytes)[tid];
   if (TRACK) stats.clear();
 
-  auto fetch_action = [&](int t) -> uint32_t {
-    if (t >= P.T) return 0u;
-    if (SYNTH) {
-      const uint32_t a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t, n_actions);
-      if (P.actions_out) P.actions_out[(int64_t)t * n + env] = (uint8_t)a;
-      return a;
+  // actions: one group of LANE_UNR steps is in flight while the previous one is consumed; running row pointer
+  const uint8_t* p_act = SYNTH ? nullptr : P.actions + env;
+  int t_fetch = 0;
+  auto fetch_action = [&]() -> uint32_t {
+    uint32_t a = 0u;
+    if (t_fetch < P.T) {
+      if (SYNTH) {
+        a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t_fetch, n_actions);
+        if (P.actions_out) P.actions_out[(int64_t)t_fetch * n + env] = (uint8_t)a;
+      } else {
+        a = __ldcs(p_act);
+        p_act += n;
+      }
     }
-    return __ldcs(P.actions + (int64_t)t * n + env);
+    ++t_fetch;
+    return a;
   };
   uint32_t act[LANE_UNR], act_next[LANE_UNR];
 #pragma unroll
-  for (int u = 0; u < LANE_UNR; ++u) act[u] = fetch_action(u);
+  for (int u = 0; u < LANE_UNR; ++u) act[u] = fetch_action();
 
   // running pointers: one 64-bit add per stream and step
   float* p_rw = P.reward + env;
-  float* p_dc = want_discount ? P.discount + env : nullptr;
+  float* p_dc = DISC ? P.discount + env : nullptr;
   uint8_t* p_fl = P.flags + env;
   uint4* p_bd = reinterpret_cast<uint4*>(P.board + env0 * cells) + lane;
   const int64_t bd_step = n * cells / 16;   // uint4 per [n, cells] row: n % 32 == 0
-  const bool small_tile = nch <= 64;
+  const bool two = lane + 32 < nch;         // SMALL: this lane copies a second chunk
 
   for (int t0 = 0; t0 < P.T; t0 += LANE_UNR) {
 #pragma unroll
-    for (int u = 0; u < LANE_UNR; ++u) act_next[u] = fetch_action(t0 + LANE_UNR + u);
+    for (int u = 0; u < LANE_UNR; ++u) act_next[u] = fetch_action();
 #pragma unroll
     for (int u = 0; u < LANE_UNR; ++u) {
       if (t0 + u >= P.T) break;
       // ---- the env's step: one table look-up ----
       const uint32_t a = min(act[u], n_actions);
-      const uint32_t idx = a * stride + cell;
-      uint32_t e = s_tt[idx];
-      float rw = s_tr[idx];
+      const uint32_t idx4 = (a * stride + cell) * 4u;
+      const uint32_t e = lds_tab_u32(a_tt + idx4);
+      float rw = lds_tab_f32(a_tr + idx4);
       float dc = 1.0f;
-      if (want_discount) dc = s_td[H.td_per_cell ? idx : a];
+      if (DISC) dc = lds_tab_f32(a_td + (H.td_per_cell ? idx4 : a * 4u));
       uint32_t f = e >> 16;
       uint32_t p = e & 0xFF, show = (e >> 8) & 0xFF;
       if (TRACK) {
@@ -180,7 +214,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
       cell = p;
       __stcs(p_rw, rw);
       p_rw += n;
-      if (want_discount) {
+      if (DISC) {
         __stcs(p_dc, dc);
         p_dc += n;
       }
@@ -188,20 +222,19 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
       p_fl += n;
 
       // ---- the boards: poke tile (t & 1), then the warp copies it out, 512 contiguous bytes per instruction ----
-      const int mine = mine0 + (u & 1) * tile_bytes;
+      const uint32_t toff = (u & 1) * tile_bytes;
       const uint32_t was = drawn[u & 1];
       if (was != show) {
-        if (was != none) smem[mine + was] = s_basech[was];
-        if (show != none) smem[mine + show] = agent_char;
+        if (was != none) sts_tile_u8(a_mine + toff + was, lds_tab_u8(a_basech + was));
+        if (show != none) sts_tile_u8(a_mine + toff + show, agent_char);
         drawn[u & 1] = show;
       }
       __syncwarp();
-      const uint4* t16 = reinterpret_cast<const uint4*>(smem + tile0 + (u & 1) * tile_bytes) + lane;
-      if (small_tile) {   // boards of up to 32 cells: at most two chunks per lane
-        if (lane < nch) __stcs(p_bd, t16[0]);
-        if (lane + 32 < nch) __stcs(p_bd + 32, t16[32]);
+      if (SMALL) {
+        __stcs(p_bd, lds_tile_v4(a_copy + toff));   // 32 <= nch <= 64: every lane has a first chunk
+        if (two) __stcs(p_bd + 32, lds_tile_v4(a_copy + toff + 512));
       } else {
-        for (int k = 0; k + lane < nch; k += 32) __stcs(p_bd + k, t16[k]);
+        for (int k = 0; k + lane < nch; k += 32) __stcs(p_bd + k, lds_tile_v4(a_copy + toff + k * 16));
       }
       p_bd += bd_step;
     }
@@ -236,11 +269,11 @@ size_t lane_smem_bytes(const cx_game* g, int warps) {
          (g->ah.track ? (size_t)warps * 32 * sizeof(LaneStats) : 0);
 }
 
-template <bool TRACK, bool SYNTH>
-int launch_lane(const LaneParams& P, unsigned grid, unsigned block, size_t smem, cudaStream_t s) {
+template <bool TRACK, bool SYNTH, bool DISC, bool SMALL>
+int launch_lane(const LaneParams& P, unsigned grid, unsigned block, size_t smem, bool pdl, cudaStream_t s) {
   static CxPerDevice configured;
   if (configured.need()) {
-    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_lane<TRACK, SYNTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_rollout_lane<TRACK, SYNTH, DISC, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     227 * 1024));
     configured.mark();
   }
@@ -251,10 +284,10 @@ int launch_lane(const LaneParams& P, unsigned grid, unsigned block, size_t smem,
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout_lane<TRACK, SYNTH>, P));
+  CX_CUDA_OK(cudaLaunchKernelEx(&cfg, k_agent_rollout_lane<TRACK, SYNTH, DISC, SMALL>, P));
   return CX_OK;
 }
 
@@ -306,9 +339,29 @@ int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int
   }
   const size_t smem = lane_smem_bytes(g, wpc);
   const bool track = g->ah.track != 0;
-  if (synth.on)
-    return track ? launch_lane<true, true>(P, (unsigned)grid, 32u * wpc, smem, s)
-                 : launch_lane<false, true>(P, (unsigned)grid, 32u * wpc, smem, s);
-  return track ? launch_lane<true, false>(P, (unsigned)grid, 32u * wpc, smem, s)
-               : launch_lane<false, false>(P, (unsigned)grid, 32u * wpc, smem, s);
+  // Programmatic dependent launch lets the next launch's CTAs become resident (and stage their tables) while this one
+  // runs.  For grids of 12-30 one-warp CTAs per SM that costs more than it hides -- the early CTAs take their slots
+  // wherever room is, and the launch then runs unevenly spread over the SMs: Demo 1, 32 / 100 steps per launch, us per
+  // launch with / without: 8,192 envs 9.1 / 10.8, 32,768 12.3 / 12.2, 65,536 18.9 / 16.1 (100 steps: 51.8 / 40.7),
+  // 98,304 23.6 / 21.8, 2^17 29.3 / 28.5, 2^18 50.0 / 50.4.  CX_AGENT_PDL = 0 | 1 forces it.
+  const int64_t warps_per_sm = warps / g->sm_count;
+  bool pdl = !(warps_per_sm >= 12 && warps_per_sm <= 30);
+  if (const char* dbg = getenv("CX_AGENT_PDL")) pdl = atoi(dbg) != 0;
+  const unsigned blk = 32u * wpc;
+  // SMALL needs a first chunk for every lane: 32 <= chunks per tile <= 64, i.e. boards of 16..32 cells
+  const int sel = (track ? 8 : 0) | (synth.on ? 4 : 0) | (d_discount ? 2 : 0) | ((g->ah.cells >= 16 && g->ah.cells <= 32) ? 1 : 0);
+  switch (sel) {
+#define CX_LANE_CASE(i, a, b, c, d) \
+  case i: return launch_lane<a, b, c, d>(P, (unsigned)grid, blk, smem, pdl, s);
+    CX_LANE_CASE(0, false, false, false, false) CX_LANE_CASE(1, false, false, false, true)
+    CX_LANE_CASE(2, false, false, true, false) CX_LANE_CASE(3, false, false, true, true)
+    CX_LANE_CASE(4, false, true, false, false) CX_LANE_CASE(5, false, true, false, true)
+    CX_LANE_CASE(6, false, true, true, false) CX_LANE_CASE(7, false, true, true, true)
+    CX_LANE_CASE(8, true, false, false, false) CX_LANE_CASE(9, true, false, false, true)
+    CX_LANE_CASE(10, true, false, true, false) CX_LANE_CASE(11, true, false, true, true)
+    CX_LANE_CASE(12, true, true, false, false) CX_LANE_CASE(13, true, true, false, true)
+    CX_LANE_CASE(14, true, true, true, false) CX_LANE_CASE(15, true, true, true, true)
+#undef CX_LANE_CASE
+  }
+  return CX_ERR_INVALID_ARG;
 }

@@ -50,6 +50,12 @@ namespace {
 #define CX_GEN_MIN_CTAS 5  // resident CTAs per SM the register allocation aims for (5 x 128 threads x 96 registers); the
                            // register-state kernel is also built for one CTA more, see cx_launch_generic_rollout
 #endif
+#ifndef CX_GEN_STHINT
+#define CX_GEN_STHINT 0    // board chunk stores of the flat composer: 0 default policy, 1 L2 evict-first hint, 2 evict-last... (probe)
+#endif
+#ifndef CX_GEN_CTASYNC
+#define CX_GEN_CTASYNC 0   // register-state kernel: the CTA's warps meet at a named barrier before every step (probe)
+#endif
 #ifndef CX_GEN_PROBE
 #define CX_GEN_PROBE 0
 #endif
@@ -702,6 +708,16 @@ __device__ __forceinline__ void compose_direct_flat(const Ctx& X, const WarpMem&
   }
   const uint32_t nchunks = (uint32_t)nenv * cells >> 4;     // the tile holds whole chunks (gen_vec_ok)
   const uint32_t inv_cells = div_inverse(cells);
+#if CX_GEN_STHINT
+  uint64_t l2pol;
+#if CX_GEN_STHINT == 1
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2pol));
+#elif CX_GEN_STHINT == 2
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2pol));
+#else
+  asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(l2pol));
+#endif
+#endif
 #pragma unroll U
   for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
     const uint32_t c = c0 + lane;
@@ -717,7 +733,14 @@ __device__ __forceinline__ void compose_direct_flat(const Ctx& X, const WarpMem&
       m.rot = q & 0xFFFu;
       overlay16(v, direct_slice(m, o, cells), ch4[i]);
     }
+#if CX_GEN_STHINT
+    if (valid && o + 16u <= cells)
+      asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(d16 + c), "r"(v.x), "r"(v.y),
+                   "r"(v.z), "r"(v.w), "l"(l2pol)
+                   : "memory");
+#else
     if (valid && o + 16u <= cells) d16[c] = v;  // default policy: measured 3 % faster than st.global.cs here
+#endif
   }
   // the chunk across the boundary between env i-1 and env i (lane i), if there is one
   if ((cells & 15u) != 0) {
@@ -879,7 +902,7 @@ __device__ __forceinline__ void compose_warp(const Ctx& X, const WarpMem& W, int
       __syncwarp();
     }
     compose_direct<U>(X, W, nenv, dst, lane);
-    if (H.n_above > 0) {
+    if (H.n_above > 0 && CX_GEN_PROBE != 4) {   // development probe (4: no stores over the finished board)
       __syncwarp();  // orders the chunk stores before the byte stores of other lanes to the same addresses
       if (lane < nenv) store_above(X, W, lane, dst);
     }
@@ -984,7 +1007,14 @@ __global__ void __launch_bounds__(BLK, OCC) k_generic_rollout(const __grid_const
 
   uint32_t a_next = 0;  // this lane's action for the coming step, loaded one step ahead of its use
   if (mine && !P.synth) a_next = P.actions[env0 + lane];
+#if CX_GEN_CTASYNC
+  const int64_t warps_total = (P.n + G - 1) / G;
+  const int active_threads = 32 * (int)min((int64_t)wpc, warps_total - (int64_t)blockIdx.x * wpc);
+#endif
   for (int t = 0; t < P.T; ++t) {
+#if CX_GEN_CTASYNC
+    if (FAST && active_threads > 32) asm volatile("bar.sync 1, %0;" ::"r"(active_threads) : "memory");
+#endif
     const int64_t row = (int64_t)t * P.n + env0;
     bool reset_me = false;
     if (mine && CX_GEN_PROBE != 3) {  // development probe (3: composition only)

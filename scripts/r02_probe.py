@@ -192,3 +192,29 @@ def big_sweep():
 
 if __name__ == "__main__":
     if "bigsweep" in sys.argv[1:]: big_sweep()
+
+
+def lane_knobs():
+    """k_agent_rollout_lane at BASELINE config 1 (Demo 1, 65,536 envs): warps per CTA, steps per launch."""
+    for wpc in ("1",):
+        os.environ.pop("CX_AGENT_PDL", None); os.environ.pop("CX_AGENT_LANE_N", None); os.environ.pop("CX_AGENT_SMALL_N", None)
+        if wpc.endswith("pdl0"): os.environ["CX_AGENT_PDL"] = "0"
+        if wpc.startswith("tile64"): os.environ.update(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="64")
+        for n in (4096, 16384, 32768, 65536, 131072, 262144):
+            for T in (32, 100):
+                g = NativeGame(expected_spec("demo1", max_episode_steps=100, track_returns=True), n)
+                nb = max(2, int(400e6 // (n * T * 31)) + 1)
+                bufs = [g.alloc_outputs(T) for _ in range(nb)]
+                acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+                gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), max(nb, 8))
+                per = timed(lambda i: gr.replay(), 1, 3)
+                timed(lambda i: gr.replay(), 0, max(3, int(100 / per)))
+                ms = timed(lambda i: gr.replay(), 1, max(6, int(60 / per))) / max(nb, 8)
+                alg = n * (T * 31 + 14)
+                print("lane wpc=%s n=%d T=%d: %.2f us/launch  %.0f GB/s (%.1f%%)" % (wpc, n, T, ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 65.341), flush=True)
+                del g, bufs, acts, gr
+    for k in ("CX_AGENT_PDL", "CX_AGENT_LANE_N", "CX_AGENT_SMALL_N", "CX_AGENT_WT"): os.environ.pop(k, None)
+
+
+if __name__ == "__main__":
+    if "laneknobs" in sys.argv[1:]: lane_knobs()
