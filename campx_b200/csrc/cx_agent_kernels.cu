@@ -489,6 +489,12 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   // on one line used to cost the 256-env build least) the 64-env build wins at every size that reaches this kernel:
   // boat_race, % of the copy peak for 64 / 128 / 256 envs per warp: 2^19 envs 91.5 / 84.6 / 73, 2^20 95 / 89-92 / 88-93.
   int WT = 64;
+  // ... except for launches of very few steps (cx_step, T = 1): there the one-time staging per warp dominates and fewer,
+  // larger tiles win.  us per launch for 64 / 128 / 256 envs per warp: 2^20 envs T = 1: 16.6 / 11.4 / 10.0, T = 2:
+  // 20.4 / 15.7 / 15.3, T = 4: 28.5 / 25.3 / 26.1, T = 8: 45.3 / 46.5 / 47.7; 2^19 envs T = 1: 9.2 / 5.9 / 8.2, T = 4:
+  // 15.3 / 13.8 / 18.3 (scripts/r02_probe.py tsmall).
+  const int64_t per_sm = (n + g->sm_count - 1) / g->sm_count;
+  if (T <= 4 && per_sm >= 1800) WT = (T == 1 && per_sm >= 6000) ? 256 : 128;
   if (const char* dbg = getenv("CX_AGENT_WT")) {
     const int w = atoi(dbg);
     if (w == 64 || w == 128 || w == 256) WT = w;

@@ -218,3 +218,30 @@ def lane_knobs():
 
 if __name__ == "__main__":
     if "laneknobs" in sys.argv[1:]: lane_knobs()
+
+
+def t_small():
+    """Large batches, few steps per launch: which tile build?"""
+    for n in (1 << 19, 1 << 20):
+        for mode, env in (("tile64", dict(CX_AGENT_WT="64")), ("tile128", dict(CX_AGENT_WT="128")), ("tile256", dict(CX_AGENT_WT="256"))):
+            for T in (1, 2, 4, 8):
+                for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_AGENT_LANE_N", "CX_AGENT_STEP_FLAT"):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
+                os.environ["CX_AGENT_STEP_FLAT"] = "0"
+                g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+                nb = max(2, int(400e6 // (n * T * 31)) + 1)
+                bufs = [g.alloc_outputs(T) for _ in range(nb)]
+                acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+                gr = graph_of(lambda i: g.rollout(acts[i % nb], *bufs[i % nb]), nb)
+                per = timed(lambda i: gr.replay(), 1, 3)
+                ms = timed(lambda i: gr.replay(), 1, max(6, int(40 / per))) / nb
+                alg = n * (T * 31 + 14)
+                print("boat_race n=%d T=%d %s: %.2f us/launch  %.0f GB/s (%.1f%%)" % (n, T, mode, ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 65.341), flush=True)
+                del g, bufs, acts, gr
+    for k in ("CX_AGENT_SMALL_N", "CX_AGENT_WT", "CX_AGENT_LANE_N", "CX_AGENT_STEP_FLAT"):
+        os.environ.pop(k, None)
+
+
+if __name__ == "__main__":
+    if "tsmall" in sys.argv[1:]: t_small()

@@ -193,9 +193,10 @@ def _random_art(rng, rows, cols, p_wall, p_star):
                                               (13, 21, 10, 64), (16, 17, 11, 40)])
 def test_random_wall_and_treasure_worlds(rows, cols, seed, n):
     """Randomly generated boards (walls, first-entry treasures, open toroidal edges) of several sizes and batch
-    sizes: <= 96 cells run on k_agent_rollout, 97..254 cells on the lane-per-env single-agent kernel (bulk
-    stores when n * cells is a multiple of 16, byte stores and ragged warps otherwise), larger boards on the
-    generic kernels.  User-level Walker class vs the oracle's restatement of the Demo 3 agent, frame by frame."""
+    sizes: batches of whole warps (n = 64) run their fused rollouts on k_agent_rollout_lane (boards of 9 .. 240
+    cells: its two-chunk fast path and its general copy loop, in-kernel Philox actions included), the others on
+    the lane-per-env TMA kernel (bulk stores when n * cells is a multiple of 16, byte stores and ragged warps
+    otherwise), boards above 254 cells on the generic kernels; single steps take the stateless composer.  User-level Walker class vs the oracle's restatement of the Demo 3 agent, frame by frame."""
     rng = np.random.Generator(np.random.PCG64(seed))
     art = _random_art(rng, rows, cols, 0.25, 0.2)
     game = ascii_art_to_game(art, ' ', drapes={'A': Partial(Walker, walls='#', treasures='*'),
