@@ -1019,7 +1019,9 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     // copies; cx_agent_lane_kernels.cu).  Demo 1, 32-step launches, % of the copy peak against the best tile build:
     // 4,096 envs 7.1 / 3.5, 65,536 56.5 / 49.7, 2^17 80.0 / 77.5, 2^18 90.3 / 90.6, 2^19 89.6 / 91.5, 2^20 86 / 95.
     // CX_AGENT_LANE_N overrides the threshold (0: never).
-    int64_t lane_n = (int64_t)g->sm_count * 1800;
+    // Boards above 96 cells: only tiny batches (its tile copy is 2 * cells / 32 LDS.128 + STG.128 pairs per lane and
+    // step, one bulk store in the TMA kernels: random 15x16 maze, 65,536 envs 64 against 88 %, 16,384 envs 18 against 36 us).
+    int64_t lane_n = (int64_t)g->sm_count * (g->ah.cells <= CX_AGENT_TILE_MAX_CELLS ? 1800 : 200);
     if (const char* dbg = getenv("CX_AGENT_LANE_N")) lane_n = atoll(dbg);
     if (n <= lane_n && T > 1 &&
         cx_agent_lane_applies(g, n, d_actions, synth.actions_out, d_reward, d_discount, d_flags, d_board))
