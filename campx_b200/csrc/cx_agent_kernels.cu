@@ -59,7 +59,9 @@ struct AgentParams {
   float* discount;         // [T, n] or null
   uint8_t* flags;          // [T, n]
   uint8_t* board;          // [T, n, cells]
-  int64_t n;
+  int64_t n;               // envs of the batch = row stride of the [T, n] arrays
+  int64_t env_base, n_end; // this launch covers envs [env_base, n_end): the whole batch, or its aligned part (VEC), or
+                           // the ragged rest behind it (!VEC, n_end == n)
   int32_t T;
   uint64_t seed, env_offset, t0;  // SYNTH: actions come from cx_philox.cuh instead of `actions`
   uint8_t* actions_out;           // SYNTH: [T, n] or null
@@ -97,9 +99,9 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   }
   __syncthreads();  // the only block barrier; warps are independent from here on
 
-  const int64_t env0 = ((int64_t)blockIdx.x * WARPS + warp) * WT;
-  if (env0 >= P.n) return;
-  const int nenv = VEC ? WT : (int)min((int64_t)WT, P.n - env0);
+  const int64_t env0 = P.env_base + ((int64_t)blockIdx.x * WARPS + warp) * WT;
+  if (env0 >= P.n_end) return;
+  const int nenv = VEC ? WT : (int)min((int64_t)WT, P.n_end - env0);
   const int64_t n = P.n;
 
   const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
@@ -200,7 +202,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
     const int el = j * (32 * GW) + lane * GW;
     if (!(VEC || el < nenv)) return 0u;
     if (SYNTH) {
-      const uint64_t genv = P.env_offset + (uint64_t)(env0 + el);   // a multiple of GW
+      const uint64_t genv = P.env_offset + (uint64_t)(env0 + el);   // a multiple of GW (env_base is one of 64)
       uint32_t a4 = cx_synth_actions_quad(P.seed, genv >> 2, P.t0 + (uint64_t)t, n_actions);
       if (GW == 2) a4 = (a4 >> (8 * (uint32_t)(genv & 2))) & GMASK;   // the half quad this group is
       if (P.actions_out) st_u8xg<VEC, GW>(P.actions_out, (int64_t)t * n + env0 + el, (int64_t)(t + 1) * n, a4);
@@ -225,7 +227,7 @@ k_agent_rollout(const __grid_constant__ AgentParams P) {
   // 2^20 envs (91.9 % against 90.6 % of the copy peak at 20 steps per launch; a barrier every fourth step: +0.5 %),
   // 64-env build +1 % (95.8 % against 94.7 %).
   constexpr bool CTASYNC = CX_OPT_CTASYNC != 0 && (NG == 2 || CX_OPT_CTASYNC == 2) && VEC;   // 1: the 256-env build only
-  const int64_t warps_total = (n + WT - 1) / WT;
+  const int64_t warps_total = (P.n_end - P.env_base + WT - 1) / WT;
   const int active_threads = 32 * (int)min((int64_t)WARPS, warps_total - (int64_t)blockIdx.x * WARPS);
   for (int t = 0; t < P.T; ++t) {
     if (CTASYNC && active_threads > 32) asm volatile("bar.sync 1, %0;" ::"r"(active_threads) : "memory");
@@ -476,6 +478,8 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   P.flags = d_flags;
   P.board = d_board;
   P.n = n;
+  P.env_base = 0;
+  P.n_end = n;
   P.T = T;
   P.seed = synth.seed;
   P.env_offset = synth.env_offset;
@@ -499,22 +503,45 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
     const int w = atoi(dbg);
     if (w == 64 || w == 128 || w == 256) WT = w;
   }
-  // vector path: every warp owns a full tile of WT envs and every [T, n] row starts 16-byte aligned
-  const bool vec = (n % WT == 0) && al16(d_actions) && al16(synth.actions_out) && al16(d_reward) && al16(d_discount) && al16(d_flags) &&
-                   al16(d_board);
-  const int64_t warps = (n + WT - 1) / WT;
-  // warps per CTA: 4, fewer while that leaves the grid under ~4 CTAs per SM (small grids spread more evenly)
-  int wpc = CX_AGENT_CTA_THREADS / 32;
-  while (wpc > 1 && (warps + wpc - 1) / wpc < (int64_t)g->sm_count * 4) wpc >>= 1;
-  const unsigned block = 32u * wpc;
-  const size_t smem = (size_t)g->ah.blob_bytes + (size_t)wpc * WT * g->ah.cells +
-                      (g->ah.track ? (size_t)block * sizeof(LaneStats) : 0);
-  const int64_t grid = (warps + wpc - 1) / wpc;
-  if (grid > 0x7fffffff) {
-    cx_set_error("cx_rollout: too many environments for one launch");
-    return CX_ERR_INVALID_ARG;
-  }
+  // Vector path: every warp owns a full tile of WT envs and every [T, n] row starts 16-byte aligned.  A batch of a
+  // multiple of 16 envs that is not a whole number of tiles runs its whole tiles here and the rest (16..WT-16 envs) as
+  // one or two warps of k_agent_rollout_lane, not on the scalar path: boat_race, 20 steps, 500,000 envs ran entirely
+  // on the scalar path at 47 % of the copy peak (2^19 envs: 95 %).
+  const bool aligned = (n % 16 == 0) && al16(d_actions) && al16(synth.actions_out) && al16(d_reward) && al16(d_discount) &&
+                       al16(d_flags) && al16(d_board);
+  const bool rest_on_lanes = aligned && cx_agent_lane_applies(g, n, d_actions, synth.actions_out, d_reward, d_discount,
+                                                             d_flags, d_board);
+  const int64_t n_vec = aligned && (rest_on_lanes || n % WT == 0) ? n / WT * WT : 0;   // envs [0, n_vec): vector path
   const bool track = g->ah.track != 0, sy = synth.on != 0;
+  // one launch over envs [lo, hi) of the batch
+  auto launch_range = [&](AgentParams Q, int64_t lo, int64_t hi, bool vec) -> int {
+    Q.env_base = lo;
+    Q.n_end = hi;
+    const int64_t warps = (hi - lo + WT - 1) / WT;
+    // warps per CTA: 4, fewer while that leaves the grid under ~4 CTAs per SM (small grids spread more evenly)
+    int wpc = CX_AGENT_CTA_THREADS / 32;
+    while (wpc > 1 && (warps + wpc - 1) / wpc < (int64_t)g->sm_count * 4) wpc >>= 1;
+    const unsigned block = 32u * wpc;
+    const size_t smem = (size_t)g->ah.blob_bytes + (size_t)wpc * WT * g->ah.cells +
+                        (g->ah.track ? (size_t)block * sizeof(LaneStats) : 0);
+    const int64_t grid = (warps + wpc - 1) / wpc;
+    if (grid > 0x7fffffff) {
+      cx_set_error("cx_rollout: too many environments for one launch");
+      return CX_ERR_INVALID_ARG;
+    }
+    if (WT == 64) return launch_s<1, 2>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+    if (WT == 128) return launch_s<1, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+    return launch_s<2, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
+  };
+  auto launch_wt = [&](const AgentParams& Q) -> int {   // the whole tiles, then the rest
+    if (n_vec == 0) return launch_range(Q, 0, n, false);
+    const int rc = launch_range(Q, 0, n_vec, true);
+    if (rc != CX_OK || n_vec == n) return rc;
+    CxSynth sy2 = synth;
+    sy2.t0 = Q.t0;
+    sy2.actions_out = Q.actions_out;
+    return cx_launch_agent_rollout_lane(g, d_state, n, Q.T, Q.actions, sy2, Q.reward, Q.discount, Q.flags, Q.board, s, n_vec);
+  };
   // Large batches: a long rollout goes out as back-to-back launches of about 25-32 steps (PDL overlaps each prologue
   // with the previous tail; the env state makes the round trip through HBM, 14 bytes per env and launch).  The warps
   // of a launch synchronise only inside their CTA, so over a long launch the CTAs drift apart and the write stream
@@ -523,11 +550,6 @@ int cx_launch_agent_rollout(const cx_game* g, void* d_state, int64_t n, int32_t 
   // 20: 91.0, 32: 87.4, 100: 79.8).  CX_AGENT_SUBT overrides the piece length (0: never split).
   int sub = 32;
   if (const char* dbg = getenv("CX_AGENT_SUBT")) sub = atoi(dbg);
-  auto launch_wt = [&](const AgentParams& Q) {
-    if (WT == 64) return launch_s<1, 2>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
-    if (WT == 128) return launch_s<1, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
-    return launch_s<2, 4>(sy, track, vec, Q, (unsigned)grid, block, smem, s);
-  };
   if (sub <= 0 || T <= sub + sub / 2 || n < (int64_t)g->sm_count * 3000) return launch_wt(P);   // small batches: one launch
   const int pieces = (T + sub - 1) / sub;
   for (int i = 0, t = 0; i < pieces; ++i) {

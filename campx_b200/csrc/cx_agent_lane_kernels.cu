@@ -38,7 +38,9 @@ struct LaneParams {
   float* discount;         // [T, n] or null
   uint8_t* flags;          // [T, n]
   uint8_t* board;          // [T, n, cells]
-  int64_t n;               // a multiple of 32
+  int64_t n;               // envs of the batch = row stride of the [T, n] arrays (n * cells a multiple of 16)
+  int64_t env_base;        // this launch covers envs [env_base, n): the whole batch, or the rest behind the whole tiles
+                           // of k_agent_rollout; env_base is a multiple of 32 and the last warp may hold 16 envs only
   int32_t T;
   uint64_t seed, env_offset, t0;
   uint8_t* actions_out;    // SYNTH: [T, n] or null
@@ -91,9 +93,11 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
   __syncthreads();  // the only block barrier
 
   const int64_t n = P.n;
-  const int64_t env0 = ((int64_t)blockIdx.x * WARPS + warp) * 32;
+  const int64_t env0 = P.env_base + ((int64_t)blockIdx.x * WARPS + warp) * 32;
   if (env0 >= n) return;
   const int64_t env = env0 + lane;
+  const int nenv = (int)min((int64_t)32, n - env0);   // 32, or 16 in the last warp of a batch with n % 32 == 16
+  const bool mine = lane < nenv;
 
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
   const uint32_t a_tt = sbase + H.off_tt, a_tr = sbase + H.off_tr, a_td = sbase + H.off_td;
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
 
   // two tiles per warp, back to back: 2 * 32 boards of the static scene, written as 16-byte pattern chunks
   const int tile_bytes = 32 * cells, nch = tile_bytes / 16;   // 32 * cells is a multiple of 32
+  const int nch_here = nenv * cells / 16;                     // chunks of this warp's boards (nenv is a multiple of 16)
   const int tile0 = H.blob_bytes + warp * 2 * tile_bytes;     // byte offset of this warp's tile 0 in smem[]
   {
     const uint4* pat = reinterpret_cast<const uint4*>(smem + H.off_pat);
@@ -116,10 +121,10 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
   __syncwarp();
 
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  uint32_t cell = min((uint32_t)P.cell[env], none);
+  uint32_t cell = mine ? min((uint32_t)P.cell[env], none) : none;
   uint32_t ts = 0;
   float rt = 0.0f;
-  if (TRACK) {
+  if (TRACK && mine) {
     ts = P.tstep[env];
     rt = P.ret[env];
   }
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
   int t_fetch = 0;
   auto fetch_action = [&]() -> uint32_t {
     uint32_t a = 0u;
-    if (t_fetch < P.T) {
+    if (t_fetch < P.T && mine) {
       if (SYNTH) {
         a = cx_synth_action(P.seed, P.env_offset + (uint64_t)env, P.t0 + (uint64_t)t_fetch, n_actions);
         if (P.actions_out) P.actions_out[(int64_t)t_fetch * n + env] = (uint8_t)a;
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
   uint8_t* p_fl = P.flags + env;
   uint4* p_bd = reinterpret_cast<uint4*>(P.board + env0 * cells) + lane;
   const int64_t bd_step = n * cells / 16;   // uint4 per [n, cells] row: n % 32 == 0
-  const bool two = lane + 32 < nch;         // SMALL: this lane copies a second chunk
+  const bool one = lane < nch_here, two = lane + 32 < nch_here;   // SMALL: this lane copies a first / a second chunk
 
   for (int t0 = 0; t0 < P.T; t0 += LANE_UNR) {
 #pragma unroll
@@ -169,7 +174,8 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
 #pragma unroll
     for (int u = 0; u < LANE_UNR; ++u) {
       if (t0 + u >= P.T) break;
-      // ---- the env's step: one table look-up ----
+      // ---- the env's step: one table look-up.  Lanes without an env (last warp of a batch with n % 32 == 16) step an
+      // empty mask alongside -- branch-free; their stores are predicated off and their statistics dropped at the end ----
       const uint32_t a = min(act[u], n_actions);
       const uint32_t idx4 = (a * stride + cell) * 4u;
       const uint32_t e = lds_tab_u32(a_tt + idx4);
@@ -212,13 +218,13 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
         }
       }
       cell = p;
-      __stcs(p_rw, rw);
+      if (mine) __stcs(p_rw, rw);
       p_rw += n;
       if (DISC) {
-        __stcs(p_dc, dc);
+        if (mine) __stcs(p_dc, dc);
         p_dc += n;
       }
-      *p_fl = (uint8_t)f;
+      if (mine) *p_fl = (uint8_t)f;
       p_fl += n;
 
       // ---- the boards: poke tile (t & 1), then the warp copies it out, 512 contiguous bytes per instruction ----
@@ -231,10 +237,10 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
       }
       __syncwarp();
       if (SMALL) {
-        __stcs(p_bd, lds_tile_v4(a_copy + toff));   // 32 <= nch <= 64: every lane has a first chunk
+        if (one) __stcs(p_bd, lds_tile_v4(a_copy + toff));
         if (two) __stcs(p_bd + 32, lds_tile_v4(a_copy + toff + 512));
       } else {
-        for (int k = 0; k + lane < nch; k += 32) __stcs(p_bd + k, lds_tile_v4(a_copy + toff + k * 16));
+        for (int k = 0; k + lane < nch_here; k += 32) __stcs(p_bd + k, lds_tile_v4(a_copy + toff + k * 16));
       }
       p_bd += bd_step;
     }
@@ -242,10 +248,14 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
     for (int u = 0; u < LANE_UNR; ++u) act[u] = act_next[u];
   }
 
-  P.cell[env] = (uint8_t)cell;
+  if (mine) P.cell[env] = (uint8_t)cell;
   if (TRACK) {
-    P.tstep[env] = (uint16_t)ts;
-    P.ret[env] = rt;
+    if (mine) {
+      P.tstep[env] = (uint16_t)ts;
+      P.ret[env] = rt;
+    } else {
+      stats.clear();   // whatever the empty mask of a lane without an env "played"
+    }
     const double cnt = warp_sum((double)stats.cnt), len = warp_sum((double)stats.len);
     const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
     const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(LANE_MAX_WARPS * 32) k_agent_rollout_lane(cons
         atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
         atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
       }
-      atomicAdd(sp + CX_STAT_ENV_STEPS, 32.0 * (double)P.T);
+      atomicAdd(sp + CX_STAT_ENV_STEPS, (double)nenv * (double)P.T);
     }
   }
 }
@@ -293,17 +303,18 @@ int launch_lane(const LaneParams& P, unsigned grid, unsigned block, size_t smem,
 
 }  // namespace
 
-// whole warps of 32 envs, every [T, n] / [T, n, cells] row 16-byte aligned, tiles that fit shared memory
+// batches of a multiple of 16 envs (the last warp may hold 16), every [T, n] / [T, n, cells] row 16-byte aligned,
+// tiles that fit shared memory
 bool cx_agent_lane_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_actions_out,
                            const void* d_reward, const void* d_discount, const void* d_flags, const void* d_board) {
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return g->path == CX_PATH_AGENT && n % 32 == 0 && n > 0 && lane_smem_bytes(g, 1) <= 64 * 1024 && al16(d_actions) &&
+  return g->path == CX_PATH_AGENT && n > 0 && n % 16 == 0 && lane_smem_bytes(g, 1) <= 64 * 1024 && al16(d_actions) &&
          al16(d_actions_out) && al16(d_reward) && al16(d_discount) && al16(d_flags) && al16(d_board);
 }
 
 int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                                  const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
-                                 uint8_t* d_board, cudaStream_t s) {
+                                 uint8_t* d_board, cudaStream_t s, int64_t env_base) {
   const CxStateLayout L = cx_layout(g, n);
   uint8_t* base = static_cast<uint8_t*>(d_state);
   LaneParams P;
@@ -319,12 +330,13 @@ int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int
   P.flags = d_flags;
   P.board = d_board;
   P.n = n;
+  P.env_base = env_base;
   P.T = T;
   P.seed = synth.seed;
   P.env_offset = synth.env_offset;
   P.t0 = synth.t0;
   P.actions_out = synth.actions_out;
-  const int64_t warps = n / 32;
+  const int64_t warps = (n - env_base + 31) / 32;
   // warps per CTA: 4, fewer while that leaves the grid under ~8 CTAs per SM (small grids spread more evenly)
   int wpc = LANE_MAX_WARPS;
   while (wpc > 1 && (warps + wpc - 1) / wpc < (int64_t)g->sm_count * 8) wpc >>= 1;
@@ -350,9 +362,10 @@ int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int
   const unsigned blk = 32u * wpc;
   // SMALL needs a first chunk for every lane: 32 <= chunks per tile <= 64, i.e. boards of 16..32 cells
   const int sel = (track ? 8 : 0) | (synth.on ? 4 : 0) | (d_discount ? 2 : 0) | ((g->ah.cells >= 16 && g->ah.cells <= 32) ? 1 : 0);
+  int rc = CX_ERR_INVALID_ARG;
   switch (sel) {
 #define CX_LANE_CASE(i, a, b, c, d) \
-  case i: return launch_lane<a, b, c, d>(P, (unsigned)grid, blk, smem, pdl, s);
+  case i: rc = launch_lane<a, b, c, d>(P, (unsigned)grid, blk, smem, pdl, s); break;
     CX_LANE_CASE(0, false, false, false, false) CX_LANE_CASE(1, false, false, false, true)
     CX_LANE_CASE(2, false, false, true, false) CX_LANE_CASE(3, false, false, true, true)
     CX_LANE_CASE(4, false, true, false, false) CX_LANE_CASE(5, false, true, false, true)
@@ -363,5 +376,5 @@ int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int
     CX_LANE_CASE(14, true, true, true, false) CX_LANE_CASE(15, true, true, true, true)
 #undef CX_LANE_CASE
   }
-  return CX_ERR_INVALID_ARG;
+  return rc;
 }

@@ -245,9 +245,10 @@ bool cx_agent_obs_applies(const cx_game* g, bool layers);
 // small batches of single-agent games: lane = env, boards copied out with STG.128 (cx_agent_lane_kernels.cu)
 bool cx_agent_lane_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_actions_out,
                            const void* d_reward, const void* d_discount, const void* d_flags, const void* d_board);
+// env_base > 0 (a multiple of 32): only envs [env_base, n), the rest behind the whole tiles of k_agent_rollout
 int cx_launch_agent_rollout_lane(const cx_game* g, void* d_state, int64_t n, int32_t T, const uint8_t* d_actions,
                                  const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
-                                 uint8_t* d_board, cudaStream_t s);
+                                 uint8_t* d_board, cudaStream_t s, int64_t env_base = 0);
 // one Engine.play() per launch, stateless composer (cx_agent_step_kernels.cu); lay_dtype: CX_DTYPE_* of d_layered
 bool cx_agent_step_applies(const cx_game* g, const void* d_board, const void* d_layered);
 // d_actions == nullptr: render only (nothing is stepped, the state is not written)

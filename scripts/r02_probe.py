@@ -245,3 +245,24 @@ def t_small():
 
 if __name__ == "__main__":
     if "tsmall" in sys.argv[1:]: t_small()
+
+
+def ragged():
+    """Batches that are not a whole number of warp tiles: how far off the aligned path are they?"""
+    for n in (1 << 19, 500000, 500016, 500001, 65536, 65552, 65521):
+        T = 20
+        g = NativeGame(expected_spec("boat_race", max_episode_steps=100, track_returns=True), n)
+        nb = max(2, int(700e6 // (n * T * 31)) + 1)
+        bufs = [g.alloc_outputs(T) for _ in range(nb)]
+        acts = [g.fill_actions(T, seed=1, t0=i * T) for i in range(nb)]
+        fn = lambda i: g.rollout(acts[i % nb], *bufs[i % nb])
+        gr = graph_of(fn, max(nb, 8))
+        per = timed(lambda i: gr.replay(), 1, 3)
+        ms = timed(lambda i: gr.replay(), 1, max(6, int(60 / per))) / max(nb, 8)
+        alg = n * (T * 31 + 14)
+        print("ragged n=%d T=%d: %.2f us/launch  %.0f GB/s (%.1f%%)" % (n, T, ms * 1e3, alg / ms / 1e6, alg / ms / 1e6 / 65.341), flush=True)
+        del g, bufs, acts, gr
+
+
+if __name__ == "__main__":
+    if "ragged" in sys.argv[1:]: ragged()

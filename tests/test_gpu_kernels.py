@@ -130,3 +130,33 @@ def test_random_rollout_vs_oracle(world, n):
         total += ret[done[t]].sum()
         ret[done[t]] = 0
     assert abs(st["return_sum"] - total) < 1e-6
+
+
+@pytest.mark.parametrize("world", ["boat_race", "demo3"])
+@pytest.mark.parametrize("n", [48, 1040, 1000])
+def test_ragged_batches_run_their_aligned_part_on_the_vector_path(world, n):
+    """A batch that is not a whole number of warp tiles: its aligned part takes the vector kernels (whole warps of
+    k_agent_rollout_lane / whole tiles of k_agent_rollout), the rest one warp of the scalar path -- two launches that
+    must give what one would (n % 16 == 0; n = 1000 has unaligned rows and runs on the scalar path altogether)."""
+    from campx_b200 import _native as N
+    T, limit = 40, 13
+    g = _game(world, n, max_episode_steps=limit, auto_reset=True, track_returns=True)
+    acts = g.fill_actions(T, seed=99)
+    board, reward, flags, disc = g.alloc_outputs(T, discount=True)
+    g.rollout(acts, board, reward, flags, disc)
+    a, b, r, f = acts.cpu().numpy(), board.cpu().numpy(), reward.cpu().numpy(), flags.cpu().numpy()
+    for i in sorted({0, 31, 32, n // 2, n - 17, n - 16, n - 1}):
+        for t, (obs, rew, dsc, term, trunc, eng) in enumerate(
+                O.rollout(world, a[:, i], rebuild_on_done=True, max_episode_steps=limit)):
+            ctx = "%s env %d t %d" % (world, i, t)
+            assert np.array_equal(b[t, i].reshape(-1), np.asarray(obs.board).reshape(-1).astype(np.uint8)), ctx
+            assert (0.0 if rew is None else float(rew)) == float(r[t, i]), ctx
+            assert term == bool(f[t, i] & N.CX_FLAG_TERMINATED) and trunc == bool(f[t, i] & N.CX_FLAG_TRUNCATED), ctx
+    g2 = _game(world, n, max_episode_steps=limit, auto_reset=True, track_returns=True)
+    b1, r1, f1, d1 = g2.alloc_outputs(discount=True)
+    for t in range(T):
+        g2.step(acts[t].contiguous(), b1, r1, f1, d1)
+        assert torch.equal(b1, board[t]) and torch.equal(r1, reward[t]) and torch.equal(f1, flags[t])
+    g.fold_stats(), g2.fold_stats()
+    assert torch.equal(g.state, g2.state)
+    assert g.stats()["env_steps"] == T * n
