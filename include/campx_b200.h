@@ -341,7 +341,9 @@ CX_API int cx_get_episode_state(const cx_game* game, const void* d_state, int64_
 
 /* The kernels accumulate the episode statistics in partial blocks inside the state blob (one per group of warps, so
  * that their atomics do not serialise on one line).  cx_stats_fold adds them into the float64[CX_STATS_DOUBLES] block at
- * the head of the blob (asynchronous on `stream`); call it before reading that block on the device, e.g. before the
+ * the head of the blob (asynchronous on `stream`, which must be the stream the steps were issued on, or be ordered
+ * after them: the fold is not atomic against a step kernel that is still running); call it before reading that block on
+ * the device, e.g. before the
  * all-reduce over ranks (campx_b200/dist.py <- the reporting loop of examples/actor_critic.py:176-199). */
 CX_API int cx_stats_fold(const cx_game* game, void* d_state, void* stream);
 
