@@ -475,24 +475,18 @@ __global__ void k_fill_actions_quads(uint64_t seed, uint64_t env_offset, uint64_
 // per env: u from the counter-based Philox stream (reproducible per (seed, env, step), independent of the launch
 // geometry), the first action whose cumulative weight exceeds u * total.  With logits the weights are
 // exp(l - max l) -- the softmax the policy head would otherwise run as its own kernel.
-__global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, int A, int is_logits, uint64_t seed,
-                                 uint64_t env_offset, const uint64_t* __restrict__ d_step, uint64_t step_offset,
-                                 uint8_t* __restrict__ actions, float* __restrict__ logp) {
-  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
-  if (i >= n) return;
-  float w[CX_MAX_ACTIONS];
+// Categorical(w).sample() for env i (w: probabilities, or logits when is_logits): shared by cx_sample_actions and
+// cx_policy_sample, so that the two agree on equal scores.  Returns the action; *logp_out = log p(action).
+__device__ __forceinline__ int sample_categorical(float (&w)[CX_MAX_ACTIONS], int A, int is_logits, uint64_t seed,
+                                                  uint64_t g, uint64_t step, float* logp_out) {
   float mx = -INFINITY;
-  for (int a = 0; a < A; ++a) {
-    w[a] = scores[i * A + a];
-    mx = fmaxf(mx, w[a]);
-  }
+  for (int a = 0; a < A; ++a) mx = fmaxf(mx, w[a]);
   float total = 0.0f;
   for (int a = 0; a < A; ++a) {
     if (is_logits) w[a] = __expf(w[a] - mx);
     w[a] = w[a] > 0.0f ? w[a] : 0.0f;   // negative / NaN weights count as zero
     total += w[a];
   }
-  const uint64_t g = env_offset + (uint64_t)i, step = (d_step ? *d_step : 0ull) + step_offset;
   const CxPhilox4 p = cx_philox4(seed ^ 0x5A4D504C45ull, g >> 2, step);   // a stream apart from cx_fill_actions
   const float u = (float)(p.w[g & 3] >> 8) * (1.0f / 16777216.0f) * total;   // [0, total)
   int pick = A - 1;
@@ -505,8 +499,162 @@ __global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, in
     }
   }
   while (pick > 0 && !(w[pick] > 0.0f)) --pick;   // rounding at the top end must not select a zero-weight action
+  *logp_out = __logf(w[pick] / total);
+  return pick;
+}
+
+__global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, int A, int is_logits, uint64_t seed,
+                                 uint64_t env_offset, const uint64_t* __restrict__ d_step, uint64_t step_offset,
+                                 uint8_t* __restrict__ actions, float* __restrict__ logp) {
+  const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (i >= n) return;
+  float w[CX_MAX_ACTIONS];
+  for (int a = 0; a < A; ++a) w[a] = scores[i * A + a];
+  float lp;
+  const int pick = sample_categorical(w, A, is_logits, seed, env_offset + (uint64_t)i,
+                                      (d_step ? *d_step : 0ull) + step_offset, &lp);
   actions[i] = (uint8_t)pick;
-  if (logp) logp[i] = __logf(w[pick] / total);
+  if (logp) logp[i] = lp;
+}
+
+// The reference's policy head evaluated and sampled in ONE launch (examples/actor_critic.py:64-98: affine1 -> relu ->
+// action_head -> softmax -> Categorical.sample()).  At the 4,096 envs of BASELINE config 5 an env-batch step is
+// launch-bound; this kernel replaces four launches (two GEMMs, ReLU, sampling) of the rollout loop.
+// A CTA of eight warps owns 32 envs, lane = env.  Both operands are staged once with 16-byte loads that are all in
+// flight together: the CTA's input rows (one contiguous [32, n_in] block) transposed into xs[d][env] (row pitch 33:
+// conflict-free both ways) and W1^T [n_in, 32] as it lies in memory.  Warp w then accumulates hidden units 4w..4w+3
+// for its 32 envs: per input one LDS.32 of x and one broadcast LDS.128 of weights feed 4 FFMA (a first version with
+// lane = hidden unit re-read the whole 22 KB weight tile per env and staged it transposed inside the kernel: 11.3 us
+// per launch at 4,096 envs), multiplies relu(h) into its share of every action logit and leaves the shares in shared
+// memory; warp 0 adds them up in warp order and samples, one lane per env, from the same Philox stream and with the
+// same arithmetic as cx_sample_actions.  The small operands (b1, W2, b2, the step counter) are requested before the
+// tiles so that no load waits behind another.
+constexpr int POLICY_THREADS = 256;   // 8 warps: warp w accumulates hidden units 4w .. 4w+3
+constexpr int POLICY_PITCH = 33;
+__global__ void __launch_bounds__(POLICY_THREADS)
+    k_policy_sample(const float* __restrict__ x, int64_t n, int n_in, const float* __restrict__ w1t,
+                    const float* __restrict__ b1, int n_hidden, const float* __restrict__ w2, const float* __restrict__ b2,
+                    int A, uint64_t seed, uint64_t env_offset, const uint64_t* __restrict__ d_step, uint64_t step_offset,
+                    uint8_t* __restrict__ actions, float* __restrict__ logp, float* __restrict__ logits_out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_w = reinterpret_cast<float*>(smem_raw);             // [n_in][32]  W1^T, hidden units padded to 32 with zeros
+  float* s_x = s_w + (size_t)n_in * 32;                        // [n_in][33]  inputs of the CTA's envs, transposed
+  float* s_h = s_x + (size_t)n_in * POLICY_PITCH;              // [8 warps][CX_MAX_ACTIONS][33]  the warps' shares of the logits
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int n_here = (int)min((int64_t)32, n - e0);
+  // the small operands first, so that their latency hides behind the tiles': this warp's four b1 entries and its
+  // 4 x A slice of W2 (lane a < A holds row a), b2, the Philox step counter
+  const int j0 = warp * 4;
+  float b1r = 0.0f, b2r = 0.0f;
+  float4 w2r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (lane < 4 && j0 + lane < n_hidden) b1r = __ldg(b1 + j0 + lane);
+  if (lane < A) {
+    b2r = __ldg(b2 + lane);
+    const float* r = w2 + lane * n_hidden + j0;
+    w2r.x = j0 + 0 < n_hidden ? __ldg(r + 0) : 0.0f;
+    w2r.y = j0 + 1 < n_hidden ? __ldg(r + 1) : 0.0f;
+    w2r.z = j0 + 2 < n_hidden ? __ldg(r + 2) : 0.0f;
+    w2r.w = j0 + 3 < n_hidden ? __ldg(r + 3) : 0.0f;
+  }
+  const uint64_t step = (d_step ? *d_step : 0ull) + step_offset;
+  // ---- staging: every thread requests up to 8 + 8 float4 (weights, inputs) before it stores any of them, so one
+  // round of memory latency covers both operands for n_in <= 256 (a loop of load -> store pays it per iteration) ----
+  const float* blk = x + e0 * n_in;                            // [n_here][n_in], contiguous
+  const int total = n_here * n_in;
+  const uint32_t inv = 0xFFFFFFFFu / (uint32_t)n_in + 1u;      // k / n_in by multiplication (k * n_in < 2^32)
+  const bool w_vec = n_hidden == 32 && (reinterpret_cast<uintptr_t>(w1t) & 15) == 0;
+  const bool x_vec = (reinterpret_cast<uintptr_t>(blk) & 15) == 0;
+  const int w_q = w_vec ? n_in * 8 : 0, x_q = x_vec ? total / 4 : 0;   // float4 counts on the vector paths
+  constexpr int DEPTH = 8;
+  for (int base = tid; base < max(w_q, x_q); base += DEPTH * POLICY_THREADS) {
+    float4 vw[DEPTH], vx[DEPTH];
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) {
+      const int q = base + u * POLICY_THREADS;
+      if (q < w_q) vw[u] = __ldg(reinterpret_cast<const float4*>(w1t) + q);
+      if (q < x_q) vx[u] = __ldcs(reinterpret_cast<const float4*>(blk) + q);
+    }
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) {
+      const int q = base + u * POLICY_THREADS;
+      if (q < w_q) reinterpret_cast<float4*>(s_w)[q] = vw[u];
+      if (q < x_q) {
+        const float vv[4] = {vx[u].x, vx[u].y, vx[u].z, vx[u].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t k = 4u * q + c, e = __umulhi(k, inv), d = k - e * (uint32_t)n_in;
+          s_x[d * POLICY_PITCH + e] = vv[c];
+        }
+      }
+    }
+  }
+  if (!w_vec)
+    for (int k = tid; k < n_in * 32; k += POLICY_THREADS) {
+      const int d = k >> 5, j = k & 31;
+      s_w[k] = j < n_hidden ? __ldg(w1t + (size_t)d * n_hidden + j) : 0.0f;
+    }
+  for (int k = (x_vec ? (total & ~3) : 0) + tid; k < total; k += POLICY_THREADS) {
+    const uint32_t e = __umulhi((uint32_t)k, inv), d = (uint32_t)k - e * (uint32_t)n_in;
+    s_x[d * POLICY_PITCH + e] = __ldcs(blk + k);
+  }
+  if (n_here < 32)                                             // lanes without an env compute on zeros
+    for (int k = tid; k < n_in * (32 - n_here); k += POLICY_THREADS) {
+      const int d = k / (32 - n_here), e = n_here + k - d * (32 - n_here);
+      s_x[d * POLICY_PITCH + e] = 0.0f;
+    }
+  __syncthreads();
+  // ---- hidden layer: warp w, hidden units 4w .. 4w+3, lane = env; then this warp's share of every action logit ----
+  {
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = __shfl_sync(0xffffffffu, b1r, u);
+    const float* xp = s_x + lane;
+    const float4* wp = reinterpret_cast<const float4*>(s_w + j0);
+#pragma unroll 8
+    for (int d = 0; d < n_in; ++d) {
+      const float xv = xp[d * POLICY_PITCH];
+      const float4 wa = wp[d * 8];
+      acc[0] = fmaf(wa.x, xv, acc[0]);
+      acc[1] = fmaf(wa.y, xv, acc[1]);
+      acc[2] = fmaf(wa.z, xv, acc[2]);
+      acc[3] = fmaf(wa.w, xv, acc[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = fmaxf(acc[u], 0.0f);                               // relu(affine1(x))
+#pragma unroll
+    for (int a = 0; a < CX_MAX_ACTIONS; ++a) {
+      if (a < A) {                                                                          // warp-uniform
+        const float c0 = __shfl_sync(0xffffffffu, w2r.x, a), c1 = __shfl_sync(0xffffffffu, w2r.y, a);
+        const float c2 = __shfl_sync(0xffffffffu, w2r.z, a), c3 = __shfl_sync(0xffffffffu, w2r.w, a);
+        s_h[(warp * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane] = fmaf(c3, acc[3], fmaf(c2, acc[2], fmaf(c1, acc[1], c0 * acc[0])));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- sum the eight shares in warp order, add b2, sample: warp 0, lane = env ----
+  if (warp == 0) {
+    float w[CX_MAX_ACTIONS];
+#pragma unroll
+    for (int a = 0; a < CX_MAX_ACTIONS; ++a) {
+      w[a] = 0.0f;
+      if (a < A) {
+        float sum = __shfl_sync(0xffffffffu, b2r, a);
+#pragma unroll
+        for (int q = 0; q < POLICY_THREADS / 32; ++q) sum += s_h[(q * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane];
+        w[a] = sum;
+      }
+    }
+    if (lane < n_here) {
+      const int64_t i = e0 + lane;
+      if (logits_out)
+        for (int a = 0; a < A; ++a) logits_out[i * A + a] = w[a];
+      float lp;
+      const int pick = sample_categorical(w, A, 1, seed, env_offset + (uint64_t)i, step, &lp);
+      actions[i] = (uint8_t)pick;
+      if (logp) logp[i] = lp;
+    }
+  }
 }
 
 // examples/actor_critic.py:119-122: `R = r + gamma * R` backwards; one thread per env, coalesced over envs
@@ -719,6 +867,37 @@ extern "C" int cx_sample_actions(const float* d_scores, int64_t n, int32_t A, in
   }
   k_sample_actions<<<blocks_for(n), TB, 0, (cudaStream_t)stream>>>(d_scores, n, A, is_logits, seed, env_offset, d_step,
                                                                    step_offset, d_actions, d_logp);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" int cx_policy_sample(const float* d_x, int64_t n, int32_t n_in, const float* d_w1t, const float* d_b1,
+                                int32_t n_hidden, const float* d_w2, const float* d_b2, int32_t A, uint64_t seed,
+                                uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, uint8_t* d_actions,
+                                float* d_logp, float* d_logits, void* stream) {
+  if (!d_x || !d_w1t || !d_b1 || !d_w2 || !d_b2 || !d_actions || n < 1 || n_in < 1 || A < 1 || A > CX_MAX_ACTIONS ||
+      n_hidden < 1 || n_hidden > 32) {
+    cx_set_error("cx_policy_sample: bad argument (n_hidden must be in 1..32, n_actions in 1..%d)", CX_MAX_ACTIONS);
+    return CX_ERR_INVALID_ARG;
+  }
+  const size_t smem = ((size_t)n_in * (32 + POLICY_PITCH) + (POLICY_THREADS / 32) * CX_MAX_ACTIONS * POLICY_PITCH) * sizeof(float);
+  if (smem > 200 * 1024 || (int64_t)n_in * 32 >= (1ll << 31) / n_in) {
+    cx_set_error("cx_policy_sample: n_inputs %d too large for the shared-memory tiles", n_in);
+    return CX_ERR_UNSUPPORTED;
+  }
+  static CxPerDevice configured;
+  if (configured.need()) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_policy_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured.mark();
+  }
+  const int64_t grid = (n + 31) / 32;
+  if (grid > 0x7fffffff) {
+    cx_set_error("cx_policy_sample: too many environments for one launch");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_policy_sample<<<(unsigned)grid, POLICY_THREADS, smem, (cudaStream_t)stream>>>(d_x, n, n_in, d_w1t, d_b1, n_hidden, d_w2,
+                                                                                  d_b2, A, seed, env_offset, d_step,
+                                                                                  step_offset, d_actions, d_logp, d_logits);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -196,6 +196,37 @@ class NativeGame(object):
                                                 _stream()))
         return out
 
+    def policy_sample(self, x, w1t, b1, w2, b2, seed, step=None, step_offset=0, env_offset=0, out=None, logp=None,
+                      logits_out=None):
+        """relu(x @ w1t + b1) @ w2.T + b2 -> softmax -> Categorical.sample() in ONE launch: the acting half of the
+        reference's Policy (examples/actor_critic.py:64-98) -> uint8 [n] action indices.  x float32 [n, n_inputs]
+        (e.g. the planes step_observations wrote); w1t [n_inputs, n_hidden] is affine1.weight TRANSPOSED
+        (`weight.t().contiguous()`), w2 / b1 / b2 in torch.nn.Linear layout; n_hidden <= 32.  Sampling as in
+        sample_actions(logits=True): equal logits give equal actions."""
+        n = self.num_envs
+        if x.dim() != 2 or x.shape[0] != n or w1t.dim() != 2:
+            raise ValueError("x must be [num_envs, n_inputs], w1t [n_inputs, n_hidden]")
+        n_in, n_hidden = int(x.shape[1]), int(w1t.shape[1])
+        self._check(x, torch.float32, (n, n_in), "x")
+        self._check(w1t, torch.float32, (n_in, n_hidden), "w1t")
+        self._check(b1, torch.float32, (n_hidden,), "b1")
+        self._check(w2, torch.float32, (self.n_actions, n_hidden), "w2")
+        self._check(b2, torch.float32, (self.n_actions,), "b2")
+        if out is None:
+            out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(out, torch.uint8, (n,), "actions")
+        if step is not None:
+            self._check(step, torch.int64, (1,), "step")
+        if logp is not None:
+            self._check(logp, torch.float32, (n,), "logp")
+        if logits_out is not None:
+            self._check(logits_out, torch.float32, (n, self.n_actions), "logits_out")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_policy_sample(_ptr(x), n, n_in, _ptr(w1t), _ptr(b1), n_hidden, _ptr(w2), _ptr(b2),
+                                               self.n_actions, int(seed), int(env_offset), _ptr(step), int(step_offset),
+                                               _ptr(out), _ptr(logp), _ptr(logits_out), _stream()))
+        return out
+
     def rollout_synth(self, n_steps, seed, board, reward, flags, discount=None, env_offset=0, t0=0, actions_out=None):
         """Fused rollout with uniform random actions generated inside the kernel (no action bytes read);
         identical to fill_actions(seed, env_offset, t0) + rollout."""

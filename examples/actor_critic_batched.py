@@ -87,20 +87,26 @@ def run(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, l
 class GraphedRollout(object):
     """One T-step rollout (policy -> sample -> Engine.play, T times) captured ONCE as a CUDA graph and replayed
     per iteration.  A 4,096-env step is launch-bound on a B200 (it moves 3 MB), so the loop is built from as few
-    launches as the reference's data flow allows -- five per env-batch step:
+    launches as the reference's data flow allows -- two per env-batch step:
 
-        Linear(175,32)  ReLU  Linear(32,5)        the policy's action logits (ordinary torch)
-        cx_sample_actions                         softmax + Categorical.sample() in one kernel (actor_critic.py:90-98)
+        cx_policy_sample                          the acting half of the policy in one kernel: Linear(175,32), ReLU,
+                                                  Linear(32,5), softmax and Categorical.sample()
+                                                  (actor_critic.py:64-98); weights are read from the torch module
         cx_step_observations                      Engine.play() that writes the NEXT policy input -- the layered
                                                   board as float32 planes (actor_critic.py:147,173) -- together with
                                                   board, reward and flags, straight into the rollout buffers
+
+    (fused_policy=False keeps the policy in torch: Linear, ReLU, Linear, then cx_sample_actions -- five launches.)
 
     The rollout runs under no_grad into static buffers (states, actions, rewards, flags); the learner then
     re-evaluates the policy on all T*N states in one batched forward pass (the usual A2C/PPO split).
     """
 
-    def __init__(self, game, policy, steps, seed=543):
+    def __init__(self, game, policy, steps, seed=543, fused_policy=None):
         self.game, self.policy, self.T, self.seed = game, policy, int(steps), int(seed)
+        if fused_policy is None:
+            fused_policy = policy.affine1.out_features <= 32
+        self.fused_policy = bool(fused_policy)
         nat = game.native
         n, dev = game.num_envs, nat.device
         self.feat = nat.n_chars * nat.cells
@@ -115,8 +121,10 @@ class GraphedRollout(object):
         first = game.reset(self.all_envs)
         self._states[0].copy_(first.layered_board_as(torch.float32).view(n, -1))
         self.graph = None
-        self.step_kernel = "cx_step_observations (k_agent_step_flat: board + float32 planes + reward + flags)"
-        self.kernels_per_step = 5
+        self.step_kernel = ("cx_policy_sample (k_policy_sample: policy MLP + softmax + sample) + " if self.fused_policy else "") + \
+            "cx_step_observations (k_agent_step_flat: board + float32 planes + reward + flags)"
+        self.kernels_per_step = 2 if self.fused_policy else 5
+        self.w1t = torch.empty((self.feat, policy.affine1.out_features), dtype=torch.float32, device=dev)
 
     @property
     def states(self):
@@ -126,9 +134,16 @@ class GraphedRollout(object):
     def _body(self):
         nat, game, n = self.game.native, self.game, self.game.num_envs
         with torch.no_grad():
+            p = self.policy
+            if self.fused_policy:                               # affine1.weight transposed, once per rollout
+                self.w1t.copy_(p.affine1.weight.t())
             for t in range(self.T):
-                logits = self.policy.action_logits(self._states[t])
-                nat.sample_actions(logits, self.seed, step=self.step, step_offset=t, logits=True, out=self.actions[t])
+                if self.fused_policy:
+                    nat.policy_sample(self._states[t], self.w1t, p.affine1.bias, p.action_head.weight,
+                                      p.action_head.bias, self.seed, step=self.step, step_offset=t, out=self.actions[t])
+                else:
+                    logits = p.action_logits(self._states[t])
+                    nat.sample_actions(logits, self.seed, step=self.step, step_offset=t, logits=True, out=self.actions[t])
                 nat.step_observations(self.actions[t], self.board, self._states[t + 1], self.rewards[t], self.flags[t])
             self.step.add_(self.T)
             # a fresh episode for every env, like the reference's make_game() per episode (actor_critic.py:146):

@@ -25,6 +25,7 @@
  *                                          bfloat16 planes straight from the step kernel
  *                                          examples/actor_critic.py:147,173 (`layered_board.view(-1).float()`)
  *   cx_sample_actions                  <-  Categorical(probs).sample()      examples/actor_critic.py:90-98
+ *   cx_policy_sample                   <-  Policy.forward + select_action    examples/actor_critic.py:64-98
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
  *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
@@ -313,6 +314,19 @@ CX_API int cx_onehot_to_index(const float* d_onehot, int64_t n_envs, int32_t n_a
 CX_API int cx_sample_actions(const float* d_scores, int64_t n_envs, int32_t n_actions, int32_t is_logits, uint64_t seed,
                       uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, uint8_t* d_actions,
                       float* d_logp, void* stream);
+
+/* The reference's policy head evaluated and sampled in one launch (examples/actor_critic.py:64-98: Policy.forward's
+ * affine1 -> relu -> action_head -> softmax, then select_action's Categorical(probs).sample()):
+ *   d_x [n, n_inputs] float32 policy input (the planes cx_step_observations writes); d_w1t [n_inputs, n_hidden] =
+ *   affine1.weight TRANSPOSED (torch: `weight.t().contiguous()`, refreshed by the caller when the weights change --
+ *   once per training iteration, not per step), d_b1 [n_hidden]; d_w2 [n_actions, n_hidden], d_b2 [n_actions] in
+ *   torch.nn.Linear layout; n_hidden <= 32.
+ *   Sampling, d_step / step_offset and d_logp as in cx_sample_actions (same Philox stream: equal logits give equal
+ *   actions); d_logits [n, n_actions] (may be NULL) receives the action logits. */
+CX_API int cx_policy_sample(const float* d_x, int64_t n_envs, int32_t n_inputs, const float* d_w1t, const float* d_b1,
+                     int32_t n_hidden, const float* d_w2, const float* d_b2, int32_t n_actions, uint64_t seed,
+                     uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, uint8_t* d_actions, float* d_logp,
+                     float* d_logits, void* stream);
 
 /* Synthetic uniform actions from counter-based Philox4x32-10: with g = env_offset + i (global env id),
  *   out[t, i] = mulhi(philox(key = seed, counter = (g >> 2, t0 + t))[g & 3], n_actions). */

@@ -169,3 +169,40 @@ def test_cuda_graph_rollout_is_bit_exact_and_learns_on_device():
     first = fresh.reset().layered_board.view(n, -1).float()
     assert torch.equal(roll.states[0], first)
     assert game.episode_stats()["env_steps"] >= 3 * n * T
+
+
+@pytest.mark.parametrize("n,n_hidden", [(4096, 32), (333, 17)])
+def test_policy_sample_is_the_torch_policy_plus_sample_actions(n, n_hidden):
+    """cx_policy_sample = relu(x W1^T + b1) W2^T + b2 -> softmax -> Categorical.sample() in one launch
+    (examples/actor_critic.py:64-98): its logits equal the torch module's to rounding, and its actions / log-probs are
+    exactly what cx_sample_actions draws from those logits (same Philox stream); a CUDA graph with a device-side step
+    counter draws fresh numbers per replay."""
+    from examples.actor_critic_batched import Policy
+    torch.manual_seed(3)
+    game = make_world("boat_race", num_envs=n, max_episode_steps=10)
+    obs, _, _ = game.its_showtime()
+    nat = game.native
+    game.play(nat.fill_actions(1, seed=5)[0])
+    x = game.play(nat.fill_actions(1, seed=6)[0])[0].layered_board_as(torch.float32).reshape(n, -1).contiguous()
+    x = x + 0.25 * torch.randn_like(x)                       # not only 0/1 inputs
+    pol = Policy(x.shape[1], n_hidden=n_hidden).cuda()
+    logits = torch.empty((n, nat.n_actions), dtype=torch.float32, device="cuda")
+    logp = torch.empty(n, dtype=torch.float32, device="cuda")
+    step = torch.full((1,), 7, dtype=torch.int64, device="cuda")
+    with torch.no_grad():
+        acts = nat.policy_sample(x, pol.affine1.weight.t().contiguous(), pol.affine1.bias, pol.action_head.weight, pol.action_head.bias,
+                                 seed=11, step=step, step_offset=3, logp=logp, logits_out=logits)
+        want = pol.action_logits(x)
+    assert torch.allclose(logits, want, rtol=1e-4, atol=1e-5), float((logits - want).abs().max())
+    logp2 = torch.empty_like(logp)
+    acts2 = nat.sample_actions(logits, 11, step=step, step_offset=3, logits=True, logp=logp2)
+    assert torch.equal(acts, acts2) and torch.equal(logp, logp2)
+    assert int(acts.max()) < nat.n_actions and len(torch.unique(acts)) > 1
+    step += 1
+    with torch.no_grad():
+        acts3 = nat.policy_sample(x, pol.affine1.weight.t().contiguous(), pol.affine1.bias, pol.action_head.weight, pol.action_head.bias,
+                                  seed=11, step=step, step_offset=3)
+    assert not torch.equal(acts, acts3)
+    with pytest.raises(Exception):
+        big = Policy(x.shape[1], n_hidden=64).cuda()
+        nat.policy_sample(x, big.affine1.weight.t().contiguous(), big.affine1.bias, big.action_head.weight, big.action_head.bias, seed=1)
