@@ -12,7 +12,8 @@
 // B200 mapping.  The kernel is an HBM write stream (31 of the 33 algorithmic bytes per env-step are
 // stores), so the design goal is: every global access is a full 16-byte-per-lane, 512-byte-per-warp
 // coalesced transaction, and nothing ever waits on a block barrier.
-//   * one WARP owns 256 consecutive envs for all T steps; its env state lives in registers;
+//   * one WARP owns 64, 128 or 256 consecutive envs (template NG, GW; 64 is what the launcher picks since the episode
+//     statistics are striped, the figures below are for 256) for all T steps; its env state lives in registers;
 //   * the static scene (backdrop + fixed drapes composed in z-order) is staged once in shared memory as
 //     a pre-tiled byte image of the warp's 256 boards (256*cells bytes);  a step only un-pokes the
 //     agent's old cell and pokes its new one (2 byte stores per env), then the warp streams the tile to

@@ -1009,13 +1009,13 @@ static int rollout_common(const cx_game* g, void* d_state, int64_t n, int32_t T,
     return cx_launch_agent_step(g, d_state, n, d_actions, d_reward, d_discount, d_flags, d_board, nullptr, CX_DTYPE_U8,
                                 (cudaStream_t)stream);
   if (g->path == CX_PATH_AGENT) {
-    // Batches below 32,768 envs: the lane-per-env kernel (32 envs per warp) keeps more warps resident than the 64-env
-    // build of k_agent_rollout and is a little faster there (Demo 1, 32 steps: 4,096 envs 16.6 against 17.9 us,
-    // 16,384 equal, 32,768 20.9 against 19.4 us); from there up k_agent_rollout picks one of its three builds
-    // (profiles/r02_probes.md).  CX_AGENT_SMALL_N overrides the threshold (0: always k_agent_rollout).
+    // Batches below 32,768 envs that k_agent_rollout_lane (next) does not take -- rows that are not 16-byte aligned, i.e.
+    // n not a multiple of 16 -- run on the lane-per-env TMA kernel, which handles ragged warps and unaligned buffers and
+    // is a little faster there than the scalar path of k_agent_rollout (Demo 1, 32 steps: 4,096 envs 16.6 against 17.9 us).
+    // CX_AGENT_SMALL_N overrides the threshold (0: always k_agent_rollout).
     int64_t small_n = 32768;
     if (const char* dbg = getenv("CX_AGENT_SMALL_N")) small_n = atoll(dbg);
-    // Batches of whole warps up to ~1,800 envs per SM (2^18 on 148 SMs): k_agent_rollout_lane (lane = env, STG.128 tile
+    // Batches of a multiple of 16 envs up to ~1,800 envs per SM (2^18 on 148 SMs): k_agent_rollout_lane (lane = env, STG.128 tile
     // copies; cx_agent_lane_kernels.cu).  Demo 1, 32-step launches, % of the copy peak against the best tile build:
     // 4,096 envs 7.1 / 3.5, 65,536 56.5 / 49.7, 2^17 80.0 / 77.5, 2^18 90.3 / 90.6, 2^19 89.6 / 91.5, 2^20 86 / 95.
     // CX_AGENT_LANE_N overrides the threshold (0: never).
