@@ -447,7 +447,7 @@ def measure_actor_critic(peak, min_ms, sampler):
     game.its_showtime()
     nat = game.native
     policy = Policy(nat.n_chars * nat.cells).to(nat.device)
-    roll = GraphedRollout(game, policy, T).capture()
+    roll = GraphedRollout(game, policy, T, persistent=True).capture()   # cx_rollout_policy: the whole rollout in one launch
     states, actions, rewards, flags = roll.run()
     torch.cuda.synchronize()
     # sampled oracle check: states[t] is the layered board the policy saw BEFORE action t
@@ -476,8 +476,9 @@ def measure_actor_critic(peak, min_ms, sampler):
             "env_steps_per_sec": env_steps / (ms * 1e-3), "us_per_env_batch_step": ms * 1e3 / (reps * T),
             "alg_bytes_per_env_step": per_step, "achieved_gbs": gbs, "frac": gbs / peak,
             "kernel": roll.step_kernel, "kernels_per_step": roll.kernels_per_step,
-            "issue": "one CUDA graph per 100-step rollout, replayed",
-            "bound": "launch latency (a 4,096-env step moves 3 MB)",
+            "issue": "one CUDA graph per 100-step rollout (weight transpose, cx_rollout_policy, reset), replayed",
+            "bound": "latency of the per-step chain policy -> sample -> play (a 4,096-env step moves 3 MB: 128 CTAs of "
+                     "32 envs keep their policy input in shared memory; five / two launches per step: 1.8e8 / 3.9e8)",
             "parity": {"envs": len(envs), "steps": T, "ok": bool(ok), "mismatch": where,
                        "what": "policy input planes (f32), reward, truncation == CPU oracle on the sampled actions"}}
 

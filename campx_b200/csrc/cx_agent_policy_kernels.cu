@@ -1,0 +1,309 @@
+// The reference's actor-critic ROLLOUT in one launch (examples/actor_critic.py:146-173, BASELINE config 5): for T steps
+//     state  = layered_board.view(-1).float()                       actor_critic.py:147,173
+//     action ~ Categorical(softmax(action_head(relu(affine1(state)))))   actor_critic.py:64-98
+//     board, reward, done = game.play(action)                       campx/engine.py:114-166
+// for every env of a single-agent game, with the time limit, auto reset and episode statistics of the other kernels.
+//
+// Why one kernel.  At the 4,096 envs of config 5 an env-batch step moves 3 MB and is launch-bound: two launches per
+// step (cx_policy_sample + cx_step_observations) take 10.5 us under a CUDA graph, most of it launch gaps and the
+// re-staging of operands that do not change.  Here a CTA of eight warps OWNS 32 envs for the whole rollout:
+//   * W1^T is staged once; the policy input of the CTA's envs lives in shared memory for all T steps (xo[env][d], what
+//     the learner gets) and a step changes four floats of it per env (the layered board of a single-agent game is a
+//     static image plus the agent, as in k_agent_rollout_obs): nothing is re-read from HBM;
+//   * the hidden layer visits only the inputs that can be nonzero -- a layered board is one 0/1 plane per character,
+//     so one input per cell is set: the static scene's cells plus the agent's plane, 2 x cells of L x cells inputs --
+//     in ascending input order, which gives the bits of the dense loop of k_policy_sample (cx_policy.cuh); the
+//     sampled actions are therefore bit-identical to the two-kernel rollout;
+//   * the uniform numbers of the next 64 steps come from all eight warps at once (Philox does not depend on the state);
+//   * per step: hidden layer on all eight warps, then warp 0, lane = env, sums the logits, samples, steps its env with
+//     the (action, cell) table look-up of k_agent_rollout, writes action / reward / flags, pokes the new agent
+//     position into xo and hands it (32 x n_in floats, contiguous in HBM) to the TMA engine: one cp.async.bulk per
+//     step, read while the next step's hidden layer runs.
+#include <stdlib.h>
+
+#include "cx_agent_common.cuh"
+#include "cx_policy.cuh"
+
+namespace {
+
+constexpr int POLICY_RNG_STEPS = 64;   // steps of uniform numbers generated ahead
+
+struct PolicyRolloutParams {
+  CxAgentHeader h;
+  const uint8_t* blob;
+  uint8_t* cell;
+  uint16_t* tstep;
+  float* ret;
+  double* stats;
+  const float *w1t, *b1, *w2, *b2;
+  int32_t n_hidden;
+  float* states;      // [T + 1, n, n_in]: states[t] is the policy input before action t (states[0]: the current frame)
+  uint8_t* actions;   // [T, n]
+  float* reward;      // [T, n]
+  uint8_t* flags;     // [T, n]
+  float* logp;        // [T, n] or null
+  int64_t n;          // a multiple of 32
+  int32_t T;
+  uint64_t seed, env_offset, step0;
+  const uint64_t* d_step;
+};
+
+__global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const __grid_constant__ PolicyRolloutParams P) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const CxAgentHeader& H = P.h;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cells = H.cells, L = H.n_chars, n_in = L * cells, A = H.n_actions;
+  // shared memory: [tables blob][W1^T [n_in][32]][xo [32][n_in]][logit shares [8][8][33]][random bits [64][32]]
+  // [input list [2 * cells]][drawn cell [32]][lane stats]; blob, W1^T and xo are multiples of 16 bytes (xo is the
+  // source of the bulk stores), the statistics start 16-aligned
+  float* s_w = reinterpret_cast<float*>(smem + H.blob_bytes_ext);
+  float* s_o = s_w + (size_t)n_in * 32;
+  float* s_h = s_o + (size_t)32 * n_in;
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_h + (POLICY_THREADS / 32) * CX_MAX_ACTIONS * POLICY_PITCH);
+  uint32_t* s_list = s_bits + POLICY_RNG_STEPS * 32;
+  uint32_t* s_drawn = s_list + 2 * cells;
+  __shared__ int s_n_list;
+  const size_t stats_off = (reinterpret_cast<uint8_t*>(s_drawn + 32) - smem + 15) / 16 * 16;
+  LaneStats& stats = reinterpret_cast<LaneStats*>(smem + stats_off)[lane];
+
+  const PolicyRegs R = policy_load_small(P.b1, P.w2, P.b2, P.n_hidden, A, warp, lane);
+  const uint64_t step_base = (P.d_step ? *P.d_step : 0ull) + P.step0;
+  const int64_t n = P.n, e0 = (int64_t)blockIdx.x * 32, env = e0 + lane;
+  // ---- stage the tables and W1^T (every 16-byte load requested before the first store) ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(P.blob);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < H.blob_bytes_ext / 16; i += POLICY_THREADS) dst[i] = src[i];
+    const bool w_vec = P.n_hidden == 32 && (reinterpret_cast<uintptr_t>(P.w1t) & 15) == 0;
+    if (w_vec) {
+      constexpr int DEPTH = 8;
+      for (int base = tid; base < n_in * 8; base += DEPTH * POLICY_THREADS) {
+        float4 v[DEPTH];
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u)
+          if (base + u * POLICY_THREADS < n_in * 8) v[u] = __ldg(reinterpret_cast<const float4*>(P.w1t) + base + u * POLICY_THREADS);
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u)
+          if (base + u * POLICY_THREADS < n_in * 8) reinterpret_cast<float4*>(s_w)[base + u * POLICY_THREADS] = v[u];
+      }
+    } else {
+      for (int k = tid; k < n_in * 32; k += POLICY_THREADS) {
+        const int d = k >> 5, j = k & 31;
+        s_w[k] = j < P.n_hidden ? __ldg(P.w1t + (size_t)d * P.n_hidden + j) : 0.0f;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t* __restrict__ s_tt = reinterpret_cast<const uint32_t*>(smem + H.off_tt);
+  const float* __restrict__ s_tr = reinterpret_cast<const float*>(smem + H.off_tr);
+  const uint8_t* __restrict__ s_shown = smem + H.off_shown;
+  const uint8_t* __restrict__ s_basek = smem + H.off_basek;
+  const uint8_t* __restrict__ s_baselay = smem + H.off_baselay;
+  const uint32_t none = cells, agent_k = H.agent_k;
+  // ---- the policy input of the static scene; the inputs that can be nonzero, ascending ----
+  for (int k = tid; k < n_in * 32; k += POLICY_THREADS) {
+    const int d = k >> 5, e = k & 31;
+    s_o[e * n_in + d] = (float)s_baselay[d];
+  }
+  if (tid == 0) {
+    int m = 0;
+    for (int d = 0; d < n_in; ++d) {
+      const uint32_t k = (uint32_t)d / (uint32_t)cells, c = (uint32_t)d - k * (uint32_t)cells;
+      if (k == agent_k) s_list[m++] = (uint32_t)d | (c << 16) | 0x80000000u;
+      else if (s_baselay[d]) s_list[m++] = (uint32_t)d | (c << 16);
+    }
+    s_n_list = m;
+  }
+  __syncthreads();
+  const int n_list = s_n_list;
+  // ---- warp 0, lane = env: state, the agent in both copies, states[0] ----
+  uint32_t cell = none, ts = 0, drawn = none;
+  float rt = 0.0f;
+  const uint64_t l2pol = l2_evict_first_policy();
+  // planes of a frame with the agent drawn at c: its own plane set, the plane of the character it covers cleared
+  auto draw = [&](uint32_t c) {
+    const uint32_t k = s_basek[c];
+    if (k != 0xFF) s_o[lane * n_in + k * cells + c] = 0.0f;
+    s_o[lane * n_in + agent_k * cells + c] = 1.0f;
+  };
+  auto erase = [&](uint32_t c) {
+    s_o[lane * n_in + agent_k * cells + c] = 0.0f;
+    const uint32_t k = s_basek[c];
+    if (k != 0xFF) s_o[lane * n_in + k * cells + c] = 1.0f;
+  };
+  if (warp == 0) {
+    cell = min((uint32_t)P.cell[env], none);
+    if (H.track) {
+      ts = P.tstep[env];
+      rt = P.ret[env];
+    }
+    stats.clear();
+    drawn = s_shown[cell];
+    s_drawn[lane] = drawn;
+    if (drawn != none) draw(drawn);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store_s2g(P.states + e0 * n_in, s_o, (uint32_t)(32 * n_in * sizeof(float)), l2pol);
+      bulk_commit();
+    }
+  }
+  __syncthreads();
+
+  const uint32_t stride = H.stride, n_actions = H.n_actions;
+  const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
+  const uint64_t quad0 = (P.env_offset + (uint64_t)e0) >> 2;   // env_offset is a multiple of 4: the CTA's envs are 8 quads
+  for (int t = 0; t < P.T; ++t) {
+    if ((t % POLICY_RNG_STEPS) == 0) {   // the random bits of the next POLICY_RNG_STEPS steps, four envs per Philox call
+      for (int k = tid; k < POLICY_RNG_STEPS * 8; k += POLICY_THREADS) {
+        const int tt = k >> 3, q = k & 7;
+        const CxPhilox4 p = cx_philox4(P.seed ^ 0x5A4D504C45ull, quad0 + (uint64_t)q, step_base + (uint64_t)(t + tt));
+        reinterpret_cast<uint4*>(s_bits)[tt * 8 + q] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+      }
+    }
+    policy_hidden_shares_layered(s_w, s_list, n_list, s_drawn[lane], s_h, A, R, warp, lane);
+    __syncthreads();
+    if (warp == 0) {
+      float w[CX_MAX_ACTIONS];
+      policy_logits(s_h, R, A, lane, w);
+      float lp;
+      const uint32_t a = (uint32_t)sample_categorical_bits(w, A, 1, s_bits[(t % POLICY_RNG_STEPS) * 32 + lane], &lp);
+      // ---- Engine.play(a) of this env: the (action, cell) table of k_agent_rollout ----
+      const uint32_t idx = min(a, n_actions) * stride + cell;
+      uint32_t e = s_tt[idx];
+      float rw = s_tr[idx];
+      if (H.track && (ts & CX_OVER_BIT)) {  // auto_reset == 0 and the episode ended: frozen env
+        e = cell | (drawn << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+        rw = 0.0f;
+      }
+      uint32_t p = e & 0xFF;
+      const uint32_t show = (e >> 8) & 0xFF;
+      uint32_t f = e >> 16;
+      if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
+        const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);
+        rt += rw;
+        if (!(f & CX_FLAG_TERMINATED) && steps >= max_steps) f |= CX_FLAG_TRUNCATED;
+        ts = steps;
+        if (f & (CX_FLAG_TERMINATED | CX_FLAG_TRUNCATED)) {
+          stats.episode(rt, steps);
+          if (H.auto_reset) {
+            p = H.init_cell;
+            ts = 0;
+            rt = 0.0f;
+          } else {
+            ts |= CX_OVER_BIT;
+          }
+        }
+      }
+      cell = p;
+      const int64_t row = (int64_t)t * n + env;
+      P.actions[row] = (uint8_t)a;
+      __stcs(P.reward + row, rw);
+      P.flags[row] = (uint8_t)f;
+      if (P.logp) __stcs(P.logp + row, lp);
+      // ---- the next policy input: move the agent in both copies, ship the env-major one ----
+      if (lane == 0) bulk_wait_read();   // the store of the previous frame has read xo (a whole hidden layer ago)
+      __syncwarp();
+      if (drawn != show) {
+        if (drawn != none) erase(drawn);
+        if (show != none) draw(show);
+        drawn = show;
+        s_drawn[lane] = drawn;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store_s2g(P.states + ((int64_t)(t + 1) * n + e0) * n_in, s_o, (uint32_t)(32 * n_in * sizeof(float)), l2pol);
+        bulk_commit();
+      }
+    }
+    __syncthreads();   // the drawn cells are up to date for the next hidden layer; the logit shares may be overwritten
+  }
+  if (warp == 0) {
+    if (lane == 0) bulk_wait_read();   // shared memory must outlive the last bulk read
+    __syncwarp();
+    P.cell[env] = (uint8_t)cell;
+    if (H.track) {
+      P.tstep[env] = (uint16_t)ts;
+      P.ret[env] = rt;
+      const double cnt = warp_sum((double)stats.cnt), len = warp_sum((double)stats.len);
+      const double sum = warp_sum(stats.sum), sumsq = warp_sum(stats.sumsq);
+      const float mx = warp_max(stats.mx), ngmn = warp_max(stats.negmn);
+      if (lane == 0) {
+        double* sp = cx_stat_stripe(P.stats, blockIdx.x);
+        if (cnt > 0.0) {
+          atomicAdd(sp + CX_STAT_EPISODES, cnt);
+          atomicAdd(sp + CX_STAT_RETURN_SUM, sum);
+          atomicAdd(sp + CX_STAT_RETURN_SUMSQ, sumsq);
+          atomicAdd(sp + CX_STAT_LENGTH_SUM, len);
+          atomic_max_double(sp + CX_STAT_RETURN_MAX, (double)mx);
+          atomic_max_double(sp + CX_STAT_NEG_RETURN_MIN, (double)ngmn);
+        }
+        atomicAdd(sp + CX_STAT_ENV_STEPS, 32.0 * (double)P.T);
+      }
+    }
+  }
+}
+
+size_t policy_rollout_smem(const cx_game* g) {
+  const size_t n_in = (size_t)g->ah.n_chars * g->ah.cells;
+  return (size_t)g->ah.blob_bytes_ext +
+         (n_in * 32 + 32 * n_in + (POLICY_THREADS / 32) * CX_MAX_ACTIONS * POLICY_PITCH) * sizeof(float) +
+         (POLICY_RNG_STEPS * 32 + 2 * (size_t)g->ah.cells + 32) * sizeof(uint32_t) + 16 + 32 * sizeof(LaneStats);
+}
+
+}  // namespace
+
+int cx_launch_agent_policy_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const float* d_w1t,
+                                   const float* d_b1, int32_t n_hidden, const float* d_w2, const float* d_b2, uint64_t seed,
+                                   uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, float* d_states,
+                                   uint8_t* d_actions, float* d_reward, uint8_t* d_flags, float* d_logp, cudaStream_t s) {
+  if (g->path != CX_PATH_AGENT || g->ah.unoccluded) {
+    cx_set_error("cx_rollout_policy: single-agent games with occluded layers only");
+    return CX_ERR_UNSUPPORTED;
+  }
+  const size_t smem = policy_rollout_smem(g);
+  if (n % 32 != 0 || (env_offset & 3) != 0 || (reinterpret_cast<uintptr_t>(d_states) & 15) != 0 || smem > 200 * 1024) {
+    cx_set_error("cx_rollout_policy: n_envs must be a multiple of 32, env_offset of 4, states 16-byte aligned, the "
+                 "policy input small enough for shared memory (%zu bytes needed)", smem);
+    return CX_ERR_UNSUPPORTED;
+  }
+  const CxStateLayout L = cx_layout(g, n);
+  uint8_t* base = static_cast<uint8_t*>(d_state);
+  PolicyRolloutParams P;
+  P.h = g->ah;
+  P.blob = g->d_blob;
+  P.cell = base + L.off_dyn;
+  P.tstep = reinterpret_cast<uint16_t*>(base + L.off_tstep);
+  P.ret = reinterpret_cast<float*>(base + L.off_ret);
+  P.stats = reinterpret_cast<double*>(base + L.off_stats);
+  P.w1t = d_w1t;
+  P.b1 = d_b1;
+  P.w2 = d_w2;
+  P.b2 = d_b2;
+  P.n_hidden = n_hidden;
+  P.states = d_states;
+  P.actions = d_actions;
+  P.reward = d_reward;
+  P.flags = d_flags;
+  P.logp = d_logp;
+  P.n = n;
+  P.T = T;
+  P.seed = seed;
+  P.env_offset = env_offset;
+  P.step0 = step_offset;
+  P.d_step = d_step;
+  static CxPerDevice configured;
+  if (configured.need()) {
+    CX_CUDA_OK(cudaFuncSetAttribute(k_agent_policy_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured.mark();
+  }
+  const int64_t grid = n / 32;
+  if (grid > 0x7fffffff) {
+    cx_set_error("cx_rollout_policy: too many environments for one launch");
+    return CX_ERR_INVALID_ARG;
+  }
+  k_agent_policy_rollout<<<(unsigned)grid, POLICY_THREADS, smem, s>>>(P);
+  CX_CUDA_OK(cudaGetLastError());
+  return CX_OK;
+}

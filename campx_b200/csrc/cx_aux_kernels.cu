@@ -7,6 +7,7 @@
 
 #include "cx_internal.cuh"
 #include "cx_philox.cuh"
+#include "cx_policy.cuh"
 
 
 namespace {
@@ -475,41 +476,14 @@ __global__ void k_fill_actions_quads(uint64_t seed, uint64_t env_offset, uint64_
 // per env: u from the counter-based Philox stream (reproducible per (seed, env, step), independent of the launch
 // geometry), the first action whose cumulative weight exceeds u * total.  With logits the weights are
 // exp(l - max l) -- the softmax the policy head would otherwise run as its own kernel.
-// Categorical(w).sample() for env i (w: probabilities, or logits when is_logits): shared by cx_sample_actions and
-// cx_policy_sample, so that the two agree on equal scores.  Returns the action; *logp_out = log p(action).
-__device__ __forceinline__ int sample_categorical(float (&w)[CX_MAX_ACTIONS], int A, int is_logits, uint64_t seed,
-                                                  uint64_t g, uint64_t step, float* logp_out) {
-  float mx = -INFINITY;
-  for (int a = 0; a < A; ++a) mx = fmaxf(mx, w[a]);
-  float total = 0.0f;
-  for (int a = 0; a < A; ++a) {
-    if (is_logits) w[a] = __expf(w[a] - mx);
-    w[a] = w[a] > 0.0f ? w[a] : 0.0f;   // negative / NaN weights count as zero
-    total += w[a];
-  }
-  const CxPhilox4 p = cx_philox4(seed ^ 0x5A4D504C45ull, g >> 2, step);   // a stream apart from cx_fill_actions
-  const float u = (float)(p.w[g & 3] >> 8) * (1.0f / 16777216.0f) * total;   // [0, total)
-  int pick = A - 1;
-  float cum = 0.0f;
-  for (int a = 0; a < A; ++a) {
-    cum += w[a];
-    if (u < cum) {
-      pick = a;
-      break;
-    }
-  }
-  while (pick > 0 && !(w[pick] > 0.0f)) --pick;   // rounding at the top end must not select a zero-weight action
-  *logp_out = __logf(w[pick] / total);
-  return pick;
-}
-
 __global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, int A, int is_logits, uint64_t seed,
                                  uint64_t env_offset, const uint64_t* __restrict__ d_step, uint64_t step_offset,
                                  uint8_t* __restrict__ actions, float* __restrict__ logp) {
   const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (i >= n) return;
   float w[CX_MAX_ACTIONS];
-  for (int a = 0; a < A; ++a) w[a] = scores[i * A + a];
+#pragma unroll
+  for (int a = 0; a < CX_MAX_ACTIONS; ++a) w[a] = a < A ? scores[i * A + a] : 0.0f;
   float lp;
   const int pick = sample_categorical(w, A, is_logits, seed, env_offset + (uint64_t)i,
                                       (d_step ? *d_step : 0ull) + step_offset, &lp);
@@ -529,8 +503,6 @@ __global__ void k_sample_actions(const float* __restrict__ scores, int64_t n, in
 // memory; warp 0 adds them up in warp order and samples, one lane per env, from the same Philox stream and with the
 // same arithmetic as cx_sample_actions.  The small operands (b1, W2, b2, the step counter) are requested before the
 // tiles so that no load waits behind another.
-constexpr int POLICY_THREADS = 256;   // 8 warps: warp w accumulates hidden units 4w .. 4w+3
-constexpr int POLICY_PITCH = 33;
 __global__ void __launch_bounds__(POLICY_THREADS)
     k_policy_sample(const float* __restrict__ x, int64_t n, int n_in, const float* __restrict__ w1t,
                     const float* __restrict__ b1, int n_hidden, const float* __restrict__ w2, const float* __restrict__ b2,
@@ -543,20 +515,8 @@ __global__ void __launch_bounds__(POLICY_THREADS)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t e0 = (int64_t)blockIdx.x * 32;
   const int n_here = (int)min((int64_t)32, n - e0);
-  // the small operands first, so that their latency hides behind the tiles': this warp's four b1 entries and its
-  // 4 x A slice of W2 (lane a < A holds row a), b2, the Philox step counter
-  const int j0 = warp * 4;
-  float b1r = 0.0f, b2r = 0.0f;
-  float4 w2r = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (lane < 4 && j0 + lane < n_hidden) b1r = __ldg(b1 + j0 + lane);
-  if (lane < A) {
-    b2r = __ldg(b2 + lane);
-    const float* r = w2 + lane * n_hidden + j0;
-    w2r.x = j0 + 0 < n_hidden ? __ldg(r + 0) : 0.0f;
-    w2r.y = j0 + 1 < n_hidden ? __ldg(r + 1) : 0.0f;
-    w2r.z = j0 + 2 < n_hidden ? __ldg(r + 2) : 0.0f;
-    w2r.w = j0 + 3 < n_hidden ? __ldg(r + 3) : 0.0f;
-  }
+  // the small operands first, so that their latency hides behind the tiles'
+  const PolicyRegs R = policy_load_small(b1, w2, b2, n_hidden, A, warp, lane);
   const uint64_t step = (d_step ? *d_step : 0ull) + step_offset;
   // ---- staging: every thread requests up to 8 + 8 float4 (weights, inputs) before it stores any of them, so one
   // round of memory latency covers both operands for n_in <= 256 (a loop of load -> store pays it per iteration) ----
@@ -604,51 +564,19 @@ __global__ void __launch_bounds__(POLICY_THREADS)
       s_x[d * POLICY_PITCH + e] = 0.0f;
     }
   __syncthreads();
-  // ---- hidden layer: warp w, hidden units 4w .. 4w+3, lane = env; then this warp's share of every action logit ----
-  {
-    float acc[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = __shfl_sync(0xffffffffu, b1r, u);
-    const float* xp = s_x + lane;
-    const float4* wp = reinterpret_cast<const float4*>(s_w + j0);
-#pragma unroll 8
-    for (int d = 0; d < n_in; ++d) {
-      const float xv = xp[d * POLICY_PITCH];
-      const float4 wa = wp[d * 8];
-      acc[0] = fmaf(wa.x, xv, acc[0]);
-      acc[1] = fmaf(wa.y, xv, acc[1]);
-      acc[2] = fmaf(wa.z, xv, acc[2]);
-      acc[3] = fmaf(wa.w, xv, acc[3]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = fmaxf(acc[u], 0.0f);                               // relu(affine1(x))
-#pragma unroll
-    for (int a = 0; a < CX_MAX_ACTIONS; ++a) {
-      if (a < A) {                                                                          // warp-uniform
-        const float c0 = __shfl_sync(0xffffffffu, w2r.x, a), c1 = __shfl_sync(0xffffffffu, w2r.y, a);
-        const float c2 = __shfl_sync(0xffffffffu, w2r.z, a), c3 = __shfl_sync(0xffffffffu, w2r.w, a);
-        s_h[(warp * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane] = fmaf(c3, acc[3], fmaf(c2, acc[2], fmaf(c1, acc[1], c0 * acc[0])));
-      }
-    }
-  }
+  policy_hidden_shares(s_w, s_x, s_h, n_in, A, R, warp, lane);
   __syncthreads();
   // ---- sum the eight shares in warp order, add b2, sample: warp 0, lane = env ----
   if (warp == 0) {
     float w[CX_MAX_ACTIONS];
-#pragma unroll
-    for (int a = 0; a < CX_MAX_ACTIONS; ++a) {
-      w[a] = 0.0f;
-      if (a < A) {
-        float sum = __shfl_sync(0xffffffffu, b2r, a);
-#pragma unroll
-        for (int q = 0; q < POLICY_THREADS / 32; ++q) sum += s_h[(q * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane];
-        w[a] = sum;
-      }
-    }
+    policy_logits(s_h, R, A, lane, w);
     if (lane < n_here) {
       const int64_t i = e0 + lane;
-      if (logits_out)
-        for (int a = 0; a < A; ++a) logits_out[i * A + a] = w[a];
+      if (logits_out) {
+#pragma unroll
+        for (int a = 0; a < CX_MAX_ACTIONS; ++a)
+          if (a < A) logits_out[i * A + a] = w[a];
+      }
       float lp;
       const int pick = sample_categorical(w, A, 1, seed, env_offset + (uint64_t)i, step, &lp);
       actions[i] = (uint8_t)pick;

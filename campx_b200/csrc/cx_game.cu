@@ -1100,6 +1100,21 @@ extern "C" int cx_rollout_observations(const cx_game* g, void* d_state, int64_t 
   return cx_layers_from_board(g, d_board, (int64_t)T * n, d_layered, stream);
 }
 
+extern "C" int cx_rollout_policy(const cx_game* g, void* d_state, int64_t n, int32_t T, const float* d_w1t,
+                                 const float* d_b1, int32_t n_hidden, const float* d_w2, const float* d_b2, uint64_t seed,
+                                 uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, float* d_states,
+                                 uint8_t* d_actions, float* d_reward, uint8_t* d_flags, float* d_logp, void* stream) {
+  int rc = check_common(g, d_state, n, "cx_rollout_policy");
+  if (rc) return rc;
+  if (T < 1 || !d_w1t || !d_b1 || !d_w2 || !d_b2 || !d_states || !d_actions || !d_reward || !d_flags || n_hidden < 1 ||
+      n_hidden > 32) {
+    cx_set_error("cx_rollout_policy: bad argument (n_steps >= 1, n_hidden in 1..32, no NULL buffers)");
+    return CX_ERR_INVALID_ARG;
+  }
+  return cx_launch_agent_policy_rollout(g, d_state, n, T, d_w1t, d_b1, n_hidden, d_w2, d_b2, seed, env_offset, d_step,
+                                        step_offset, d_states, d_actions, d_reward, d_flags, d_logp, (cudaStream_t)stream);
+}
+
 extern "C" int cx_step(const cx_game* g, void* d_state, int64_t n, const uint8_t* d_actions, float* d_reward,
                        float* d_discount, uint8_t* d_flags, uint8_t* d_board, void* stream) {
   return cx_rollout(g, d_state, n, 1, d_actions, d_reward, d_discount, d_flags, d_board, stream);

@@ -242,6 +242,11 @@ int cx_launch_agent_rollout_obs(const cx_game* g, void* d_state, int64_t n, int3
                                 const CxSynth& synth, float* d_reward, float* d_discount, uint8_t* d_flags,
                                 uint8_t* d_board, uint8_t* d_layered /* or null */, cudaStream_t s);
 bool cx_agent_obs_applies(const cx_game* g, bool layers);
+// the whole policy rollout of a single-agent game in one launch (cx_agent_policy_kernels.cu)
+int cx_launch_agent_policy_rollout(const cx_game* g, void* d_state, int64_t n, int32_t T, const float* d_w1t,
+                                   const float* d_b1, int32_t n_hidden, const float* d_w2, const float* d_b2, uint64_t seed,
+                                   uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, float* d_states,
+                                   uint8_t* d_actions, float* d_reward, uint8_t* d_flags, float* d_logp, cudaStream_t s);
 // small batches of single-agent games: lane = env, boards copied out with STG.128 (cx_agent_lane_kernels.cu)
 bool cx_agent_lane_applies(const cx_game* g, int64_t n, const void* d_actions, const void* d_actions_out,
                            const void* d_reward, const void* d_discount, const void* d_flags, const void* d_board);

@@ -227,6 +227,31 @@ class NativeGame(object):
                                                _ptr(out), _ptr(logp), _ptr(logits_out), _stream()))
         return out
 
+    def rollout_policy(self, n_steps, w1t, b1, w2, b2, seed, states, actions, reward, flags, step=None, step_offset=0,
+                       env_offset=0, logp=None):
+        """The reference's actor-critic rollout loop (examples/actor_critic.py:146-173) in ONE launch: T times
+        (policy -> sample -> play), bit-identical to T x (policy_sample + step_observations(float32)).
+        states float32 [T + 1, n, n_chars * cells]: states[t] = policy input before action t (states[0]: now)."""
+        n, T, feat = self.num_envs, int(n_steps), self.n_chars * self.cells
+        n_hidden = int(w1t.shape[1])
+        self._check(w1t, torch.float32, (feat, n_hidden), "w1t")
+        self._check(b1, torch.float32, (n_hidden,), "b1")
+        self._check(w2, torch.float32, (self.n_actions, n_hidden), "w2")
+        self._check(b2, torch.float32, (self.n_actions,), "b2")
+        self._check(states, torch.float32, (T + 1, n, feat), "states")
+        self._check(actions, torch.uint8, (T, n), "actions")
+        self._check(reward, torch.float32, (T, n), "reward")
+        self._check(flags, torch.uint8, (T, n), "flags")
+        if step is not None:
+            self._check(step, torch.int64, (1,), "step")
+        if logp is not None:
+            self._check(logp, torch.float32, (T, n), "logp")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.cx_rollout_policy(self._handle, _ptr(self.state), n, T, _ptr(w1t), _ptr(b1), n_hidden,
+                                                _ptr(w2), _ptr(b2), int(seed), int(env_offset), _ptr(step),
+                                                int(step_offset), _ptr(states), _ptr(actions), _ptr(reward), _ptr(flags),
+                                                _ptr(logp), _stream()))
+
     def rollout_synth(self, n_steps, seed, board, reward, flags, discount=None, env_offset=0, t0=0, actions_out=None):
         """Fused rollout with uniform random actions generated inside the kernel (no action bytes read);
         identical to fill_actions(seed, env_offset, t0) + rollout."""

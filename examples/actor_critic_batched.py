@@ -97,16 +97,19 @@ class GraphedRollout(object):
                                                   board, reward and flags, straight into the rollout buffers
 
     (fused_policy=False keeps the policy in torch: Linear, ReLU, Linear, then cx_sample_actions -- five launches.)
+    persistent=True goes one step further: cx_rollout_policy runs the WHOLE T-step loop in one launch (a CTA owns 32 envs,
+    their policy input stays in shared memory and changes by four floats per step); bit-identical to the two-launch loop.
 
     The rollout runs under no_grad into static buffers (states, actions, rewards, flags); the learner then
     re-evaluates the policy on all T*N states in one batched forward pass (the usual A2C/PPO split).
     """
 
-    def __init__(self, game, policy, steps, seed=543, fused_policy=None):
+    def __init__(self, game, policy, steps, seed=543, fused_policy=None, persistent=False):
         self.game, self.policy, self.T, self.seed = game, policy, int(steps), int(seed)
         if fused_policy is None:
             fused_policy = policy.affine1.out_features <= 32
         self.fused_policy = bool(fused_policy)
+        self.persistent = bool(persistent) and self.fused_policy and game.num_envs % 32 == 0
         nat = game.native
         n, dev = game.num_envs, nat.device
         self.feat = nat.n_chars * nat.cells
@@ -124,6 +127,9 @@ class GraphedRollout(object):
         self.step_kernel = ("cx_policy_sample (k_policy_sample: policy MLP + softmax + sample) + " if self.fused_policy else "") + \
             "cx_step_observations (k_agent_step_flat: board + float32 planes + reward + flags)"
         self.kernels_per_step = 2 if self.fused_policy else 5
+        if self.persistent:
+            self.step_kernel = "cx_rollout_policy (k_agent_policy_rollout: policy + sample + play + float32 planes, T steps per launch)"
+            self.kernels_per_step = 1.0 / self.T
         self.w1t = torch.empty((self.feat, policy.affine1.out_features), dtype=torch.float32, device=dev)
 
     @property
@@ -137,7 +143,7 @@ class GraphedRollout(object):
             p = self.policy
             if self.fused_policy:                               # affine1.weight transposed, once per rollout
                 self.w1t.copy_(p.affine1.weight.t())
-            for t in range(self.T):
+            for t in range(0 if self.persistent else self.T):
                 if self.fused_policy:
                     nat.policy_sample(self._states[t], self.w1t, p.affine1.bias, p.action_head.weight,
                                       p.action_head.bias, self.seed, step=self.step, step_offset=t, out=self.actions[t])
@@ -145,6 +151,9 @@ class GraphedRollout(object):
                     logits = p.action_logits(self._states[t])
                     nat.sample_actions(logits, self.seed, step=self.step, step_offset=t, logits=True, out=self.actions[t])
                 nat.step_observations(self.actions[t], self.board, self._states[t + 1], self.rewards[t], self.flags[t])
+            if self.persistent:
+                nat.rollout_policy(self.T, self.w1t, p.affine1.bias, p.action_head.weight, p.action_head.bias, self.seed,
+                                   self._states, self.actions, self.rewards, self.flags, step=self.step)
             self.step.add_(self.T)
             # a fresh episode for every env, like the reference's make_game() per episode (actor_critic.py:146):
             # a masked reset keeps the episode statistics
@@ -171,7 +180,7 @@ class GraphedRollout(object):
 
 
 def run_graphed(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, seed=543, log=print, device="cuda",
-                use_graph=True):
+                use_graph=True, persistent=False):
     """Same learner as run(), rollout replayed from a CUDA graph.  Returns (history, game, rollout)."""
     torch.manual_seed(seed)
     game = make_world("boat_race", num_envs=num_envs, max_episode_steps=steps, track_returns=True)
@@ -180,7 +189,7 @@ def run_graphed(num_envs=4096, steps=100, iterations=5, gamma=0.99, lr=3e-2, see
     policy = Policy(nat.n_chars * nat.cells).to(device)
     optimizer = torch.optim.Adam(policy.parameters(), lr=lr)
     eps = torch.finfo(torch.float32).eps
-    roll = GraphedRollout(game, policy, steps)
+    roll = GraphedRollout(game, policy, steps, persistent=persistent)
     if use_graph:
         roll.capture()
     history = []
@@ -216,11 +225,13 @@ if __name__ == "__main__":
     ap.add_argument("--iterations", type=int, default=20)
     ap.add_argument("--gamma", type=float, default=0.99)
     ap.add_argument("--seed", type=int, default=543)
-    ap.add_argument("--mode", default="graph", choices=["graph", "eager-batched", "stepwise"],
-                    help="graph: rollout replayed from a CUDA graph; eager-batched: same code without the graph; "
+    ap.add_argument("--mode", default="graph", choices=["graph", "persistent", "eager-batched", "stepwise"],
+                    help="graph: rollout replayed from a CUDA graph; persistent: the whole rollout in one kernel launch "
+                         "(cx_rollout_policy); eager-batched: same code without the graph; "
                          "stepwise: the reference's loop structure (policy forward kept for autograd every step)")
     a = ap.parse_args()
     if a.mode == "stepwise":
         run(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed)
     else:
-        run_graphed(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed, use_graph=a.mode == "graph")
+        run_graphed(a.num_envs, a.env_max_steps, a.iterations, a.gamma, seed=a.seed, use_graph=a.mode in ("graph", "persistent"),
+                    persistent=a.mode == "persistent")

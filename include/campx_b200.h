@@ -26,6 +26,7 @@
  *                                          examples/actor_critic.py:147,173 (`layered_board.view(-1).float()`)
  *   cx_sample_actions                  <-  Categorical(probs).sample()      examples/actor_critic.py:90-98
  *   cx_policy_sample                   <-  Policy.forward + select_action    examples/actor_critic.py:64-98
+ *   cx_rollout_policy                  <-  the rollout loop of main()         examples/actor_critic.py:146-173
  *   cx_onehot_to_index                 <-  the one-hot action convention    examples/boat_race.py:26,40-49
  *   cx_step_perf                       <-  step_perf() safety metric        examples/boat_race.py:117-151
  *   cx_discounted_returns              <-  finish_episode() return scan     examples/actor_critic.py:115-135
@@ -297,6 +298,19 @@ CX_API int cx_board_mapper_destroy(cx_board_mapper* mapper);
  * their output elements are the h_values rows of those bytes. */
 CX_API int cx_board_mapper_apply(const cx_board_mapper* mapper, const uint8_t* d_board, int64_t n_boards, int32_t rows,
                           int32_t cols, const int32_t* permute, void* d_out, int32_t* d_unknown, void* stream);
+
+/* The reference's actor-critic ROLLOUT in one launch (examples/actor_critic.py:146-173): for T steps, every env feeds
+ * its layered board (float32, canonical channel order) to the policy of cx_policy_sample, samples an action and plays
+ * it, with the game's time limit / auto reset / statistics.  Single-agent games (info.path == 1) with occluded layers;
+ * n_envs a multiple of 32; no discount stream is written (terminations are in the flags).  Equal, bit for bit, to T times cx_policy_sample +
+ * cx_step_observations (CX_DTYPE_F32) with step counters step, step + 1, ...
+ *   d_states  [T + 1, n, n_chars * rows * cols] float32: d_states[t] is the policy input before action t
+ *             (d_states[0]: the current frame), d_states[T] the input of the next rollout's first step
+ *   d_actions [T, n] uint8, d_reward [T, n] float32, d_flags [T, n] uint8 (CX_FLAG_*), d_logp [T, n] float32 or NULL */
+CX_API int cx_rollout_policy(const cx_game* game, void* d_state, int64_t n_envs, int32_t n_steps, const float* d_w1t,
+                      const float* d_b1, int32_t n_hidden, const float* d_w2, const float* d_b2, uint64_t seed,
+                      uint64_t env_offset, const uint64_t* d_step, uint64_t step_offset, float* d_states,
+                      uint8_t* d_actions, float* d_reward, uint8_t* d_flags, float* d_logp, void* stream);
 
 /* One-hot float actions [n, n_actions] -> uint8 indices.  A row that is not exactly one-hot (boat_race.py:48
  * `assert sum(act) == 1`: no 1, several 1s, fractional entries) becomes index 255, which every step kernel treats as

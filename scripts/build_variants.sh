@@ -10,7 +10,7 @@ mkdir -p ../lib/variants build/var
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="-O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC,-fvisibility=hidden -I../../include --expt-relaxed-constexpr"
 OBJS=""
-for f in cx_game cx_agent_kernels cx_agent_obs_kernels cx_agent_lane_kernels cx_agent_step_kernels cx_generic_kernels cx_aux_kernels cx_board_mapper; do
+for f in cx_game cx_agent_kernels cx_agent_obs_kernels cx_agent_lane_kernels cx_agent_policy_kernels cx_agent_step_kernels cx_generic_kernels cx_aux_kernels cx_board_mapper; do
   [ "$f" = "$FILE" ] || OBJS="$OBJS build/$f.o"
 done
 i=0

@@ -40,3 +40,9 @@ with torch.no_grad():
     with torch.cuda.graph(g2):
         for _ in range(50): h()
     print("cx_step_observations alone (graph of 50): %.2f us per launch" % (timed(g2.replay, 3, 20) * 1e3 / 50))
+for persistent in (True,):
+    game = make_world("boat_race", num_envs=4096, max_episode_steps=100, track_returns=True); game.its_showtime()
+    pol = Policy(175).cuda()
+    roll = GraphedRollout(game, pol, 100, persistent=True).capture()
+    ms = timed(roll.run, 20, 100)
+    print("persistent: %.3f ms per 100-step rollout, %.2f us per env-batch step, %.3e env-steps/s" % (ms, ms * 10, 4096 * 100 / ms * 1e3))

@@ -206,3 +206,56 @@ def test_policy_sample_is_the_torch_policy_plus_sample_actions(n, n_hidden):
     with pytest.raises(Exception):
         big = Policy(x.shape[1], n_hidden=64).cuda()
         nat.policy_sample(x, big.affine1.weight.t().contiguous(), big.affine1.bias, big.action_head.weight, big.action_head.bias, seed=1)
+
+
+@pytest.mark.parametrize("world,n,limit", [("boat_race", 4096, 100), ("boat_race", 96, 7), ("demo3", 64, 9)])
+def test_persistent_policy_rollout_equals_the_two_kernel_loop(world, n, limit):
+    """cx_rollout_policy (policy -> sample -> play, T steps in one launch, the policy input resident in shared memory)
+    is bit-identical to T x (cx_policy_sample + cx_step_observations(float32)): states, actions, rewards, flags,
+    log-probs, the env state and the statistics afterwards; and the env it drives obeys the oracle."""
+    from examples.actor_critic_batched import Policy
+    from campx_b200 import _native as N
+    torch.manual_seed(5)
+    T = 37
+    a = make_world(world, num_envs=n, max_episode_steps=limit, track_returns=True)
+    b = make_world(world, num_envs=n, max_episode_steps=limit, track_returns=True)
+    oa, _, _ = a.its_showtime()
+    ob, _, _ = b.its_showtime()
+    na, nb = a.native, b.native
+    feat = na.n_chars * na.cells
+    pol = Policy(feat, n_actions=na.n_actions).cuda()
+    w1t = pol.affine1.weight.detach().t().contiguous()
+    b1, w2, b2 = pol.affine1.bias.detach(), pol.action_head.weight.detach(), pol.action_head.bias.detach()
+    step = torch.full((1,), 11, dtype=torch.int64, device="cuda")
+    # one launch
+    states = torch.empty((T + 1, n, feat), dtype=torch.float32, device="cuda")
+    actions = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    rewards = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    flags = torch.empty((T, n), dtype=torch.uint8, device="cuda")
+    logp = torch.empty((T, n), dtype=torch.float32, device="cuda")
+    na.rollout_policy(T, w1t, b1, w2, b2, 77, states, actions, rewards, flags, step=step, logp=logp)
+    # the two-kernel loop on a twin
+    states2 = torch.empty_like(states)
+    actions2, rewards2, flags2, logp2 = torch.empty_like(actions), torch.empty_like(rewards), torch.empty_like(flags), torch.empty_like(logp)
+    board = torch.empty((n, nb.rows, nb.cols), dtype=torch.uint8, device="cuda")
+    states2[0].copy_(ob.layered_board_as(torch.float32).reshape(n, -1))
+    for t in range(T):
+        nb.policy_sample(states2[t], w1t, b1, w2, b2, 77, step=step, step_offset=t, out=actions2[t], logp=logp2[t])
+        nb.step_observations(actions2[t], board, states2[t + 1].view(n, nb.n_chars, nb.rows, nb.cols), rewards2[t], flags2[t])
+    assert torch.equal(actions, actions2) and torch.equal(rewards, rewards2) and torch.equal(flags, flags2)
+    assert torch.equal(states, states2) and torch.equal(logp, logp2)
+    na.fold_stats(), nb.fold_stats()
+    assert torch.equal(na.state, nb.state)
+    assert len(torch.unique(actions)) > 1 and int(((flags & N.CX_FLAG_TRUNCATED) != 0).sum()) == n * (T // limit)
+    # and the env side against the oracle on the sampled actions
+    an, rn, fn = actions.cpu().numpy(), rewards.cpu().numpy(), flags.cpu().numpy()
+    sn = states.cpu().numpy().reshape(T + 1, n, na.n_chars, na.rows, na.cols)
+    chars = a.characters
+    for i in (0, n // 2, n - 1):
+        for t, frame in enumerate(O.rollout(world, an[:, i], rebuild_on_done=True, max_episode_steps=limit)):
+            obs, rew, dsc, term, trunc, eng = frame
+            assert (0.0 if rew is None else float(rew)) == float(rn[t, i]), (i, t)
+            assert trunc == bool(fn[t, i] & N.CX_FLAG_TRUNCATED) and term == bool(fn[t, i] & N.CX_FLAG_TERMINATED), (i, t)
+            if not (term or trunc):   # (after an episode end states[t + 1] is the first frame of the next episode)
+                want = np.stack([np.asarray(obs.layers[c]) for c in chars]).astype(np.float32)
+                assert np.array_equal(sn[t + 1, i], want), (i, t)
