@@ -10,15 +10,17 @@
 //   * W1^T is staged once; the policy input of the CTA's envs lives in shared memory for all T steps (xo[env][d], what
 //     the learner gets) and a step changes four floats of it per env (the layered board of a single-agent game is a
 //     static image plus the agent, as in k_agent_rollout_obs): nothing is re-read from HBM;
-//   * the hidden layer visits only the inputs that can be nonzero -- a layered board is one 0/1 plane per character,
-//     so one input per cell is set: the static scene's cells plus the agent's plane, 2 x cells of L x cells inputs --
-//     in ascending input order, which gives the bits of the dense loop of k_policy_sample (cx_policy.cuh); the
-//     sampled actions are therefore bit-identical to the two-kernel rollout;
-//   * the uniform numbers of the next 64 steps come from all eight warps at once (Philox does not depend on the state);
-//   * per step: hidden layer on all eight warps, then warp 0, lane = env, sums the logits, samples, steps its env with
-//     the (action, cell) table look-up of k_agent_rollout, writes action / reward / flags, pokes the new agent
-//     position into xo and hands it (32 x n_in floats, contiguous in HBM) to the TMA engine: one cp.async.bulk per
-//     step, read while the next step's hidden layer runs.
+//   * the hidden layer visits only the inputs that are nonzero -- a layered board is one 0/1 plane per character, so
+//     one input per cell is set: the static scene's cells (minus the one the agent covers) plus one term of the agent's
+//     plane, `cells` + 1 of L x cells inputs -- in ascending input order, which gives the bits of the dense loop of
+//     k_policy_sample (cx_policy.cuh); the sampled actions are therefore bit-identical to the two-kernel rollout;
+//   * the uniform numbers of the next 64 steps come from all warps at once (Philox does not depend on the state);
+//   * nine warps: warps 1-8 run the hidden layer (four hidden units each, lane = env); warp 0, lane = env, is the actor:
+//     it sums the logits, samples, looks the step up in the (action, cell) table of k_agent_rollout and publishes where
+//     the agent is drawn -- that is all the next hidden layer waits for.  Everything else of the step (time limit,
+//     auto reset, statistics, the action / reward / flags / log-prob stores, the four pokes into xo and its bulk store:
+//     32 x n_in floats, contiguous in HBM, one cp.async.bulk per step) happens on warp 0 WHILE warps 1-8 already run
+//     the next hidden layer.
 #include <stdlib.h>
 
 #include "cx_agent_common.cuh"
@@ -27,6 +29,7 @@
 namespace {
 
 constexpr int POLICY_RNG_STEPS = 64;   // steps of uniform numbers generated ahead
+constexpr int ROLLOUT_THREADS = POLICY_THREADS + 32;   // warp 0: the actor; warps 1-8: the hidden layer
 
 struct PolicyRolloutParams {
   CxAgentHeader h;
@@ -48,7 +51,7 @@ struct PolicyRolloutParams {
   const uint64_t* d_step;
 };
 
-__global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const __grid_constant__ PolicyRolloutParams P) {
+__global__ void __launch_bounds__(ROLLOUT_THREADS) k_agent_policy_rollout(const __grid_constant__ PolicyRolloutParams P) {
   extern __shared__ __align__(16) uint8_t smem[];
   const CxAgentHeader& H = P.h;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -62,32 +65,33 @@ __global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const _
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_h + (POLICY_THREADS / 32) * CX_MAX_ACTIONS * POLICY_PITCH);
   uint32_t* s_list = s_bits + POLICY_RNG_STEPS * 32;
   uint32_t* s_drawn = s_list + 2 * cells;
-  __shared__ int s_n_list;
+  __shared__ int s_n_list[2];   // static entries in front of the agent's plane, all static entries
   const size_t stats_off = (reinterpret_cast<uint8_t*>(s_drawn + 32) - smem + 15) / 16 * 16;
   LaneStats& stats = reinterpret_cast<LaneStats*>(smem + stats_off)[lane];
 
-  const PolicyRegs R = policy_load_small(P.b1, P.w2, P.b2, P.n_hidden, A, warp, lane);
+  const int mw = warp > 0 ? warp - 1 : 0;   // hidden-layer warp index (warp 0 only needs b2 from the small operands)
+  const PolicyRegs R = policy_load_small(P.b1, P.w2, P.b2, P.n_hidden, A, mw, lane);
   const uint64_t step_base = (P.d_step ? *P.d_step : 0ull) + P.step0;
   const int64_t n = P.n, e0 = (int64_t)blockIdx.x * 32, env = e0 + lane;
   // ---- stage the tables and W1^T (every 16-byte load requested before the first store) ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(P.blob);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < H.blob_bytes_ext / 16; i += POLICY_THREADS) dst[i] = src[i];
+    for (int i = tid; i < H.blob_bytes_ext / 16; i += ROLLOUT_THREADS) dst[i] = src[i];
     const bool w_vec = P.n_hidden == 32 && (reinterpret_cast<uintptr_t>(P.w1t) & 15) == 0;
     if (w_vec) {
       constexpr int DEPTH = 8;
-      for (int base = tid; base < n_in * 8; base += DEPTH * POLICY_THREADS) {
+      for (int base = tid; base < n_in * 8; base += DEPTH * ROLLOUT_THREADS) {
         float4 v[DEPTH];
 #pragma unroll
         for (int u = 0; u < DEPTH; ++u)
-          if (base + u * POLICY_THREADS < n_in * 8) v[u] = __ldg(reinterpret_cast<const float4*>(P.w1t) + base + u * POLICY_THREADS);
+          if (base + u * ROLLOUT_THREADS < n_in * 8) v[u] = __ldg(reinterpret_cast<const float4*>(P.w1t) + base + u * ROLLOUT_THREADS);
 #pragma unroll
         for (int u = 0; u < DEPTH; ++u)
-          if (base + u * POLICY_THREADS < n_in * 8) reinterpret_cast<float4*>(s_w)[base + u * POLICY_THREADS] = v[u];
+          if (base + u * ROLLOUT_THREADS < n_in * 8) reinterpret_cast<float4*>(s_w)[base + u * ROLLOUT_THREADS] = v[u];
       }
     } else {
-      for (int k = tid; k < n_in * 32; k += POLICY_THREADS) {
+      for (int k = tid; k < n_in * 32; k += ROLLOUT_THREADS) {
         const int d = k >> 5, j = k & 31;
         s_w[k] = j < P.n_hidden ? __ldg(P.w1t + (size_t)d * P.n_hidden + j) : 0.0f;
       }
@@ -100,22 +104,25 @@ __global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const _
   const uint8_t* __restrict__ s_basek = smem + H.off_basek;
   const uint8_t* __restrict__ s_baselay = smem + H.off_baselay;
   const uint32_t none = cells, agent_k = H.agent_k;
-  // ---- the policy input of the static scene; the inputs that can be nonzero, ascending ----
-  for (int k = tid; k < n_in * 32; k += POLICY_THREADS) {
+  // ---- the policy input of the static scene; its nonzero inputs, ascending (none of them in the agent's plane) ----
+  for (int k = tid; k < n_in * 32; k += ROLLOUT_THREADS) {
     const int d = k >> 5, e = k & 31;
     s_o[e * n_in + d] = (float)s_baselay[d];
   }
   if (tid == 0) {
-    int m = 0;
+    int m = 0, before = 0;
     for (int d = 0; d < n_in; ++d) {
       const uint32_t k = (uint32_t)d / (uint32_t)cells, c = (uint32_t)d - k * (uint32_t)cells;
-      if (k == agent_k) s_list[m++] = (uint32_t)d | (c << 16) | 0x80000000u;
-      else if (s_baselay[d]) s_list[m++] = (uint32_t)d | (c << 16);
+      if (k != agent_k && s_baselay[d]) {
+        s_list[m++] = ((uint32_t)d * 8u) | (c << 16);          // row of W1^T as a float4 index | cell
+        if (k < agent_k) before = m;
+      }
     }
-    s_n_list = m;
+    s_n_list[0] = before;
+    s_n_list[1] = m;
   }
   __syncthreads();
-  const int n_list = s_n_list;
+  const int n_before = s_n_list[0], n_static = s_n_list[1];
   // ---- warp 0, lane = env: state, the agent in both copies, states[0] ----
   uint32_t cell = none, ts = 0, drawn = none;
   float rt = 0.0f;
@@ -153,16 +160,46 @@ __global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const _
   const uint32_t stride = H.stride, n_actions = H.n_actions;
   const uint32_t max_steps = H.max_steps > 0 ? (uint32_t)H.max_steps : 0xFFFFFFFFu;
   const uint64_t quad0 = (P.env_offset + (uint64_t)e0) >> 2;   // env_offset is a multiple of 4: the CTA's envs are 8 quads
+  // what warp 0 still owes the previous step while the hidden layer of this one runs
+  bool owed = false;
+  uint32_t o_a = 0, o_f = 0, o_show = none;
+  float o_rw = 0.0f, o_lp = 0.0f;
+  int o_t = 0;
+  auto settle = [&]() {   // warp 0: stores of step o_t, the agent's move in xo, xo -> states[o_t + 1]
+    const int64_t row = (int64_t)o_t * n + env;
+    P.actions[row] = (uint8_t)o_a;
+    __stcs(P.reward + row, o_rw);
+    P.flags[row] = (uint8_t)o_f;
+    if (P.logp) __stcs(P.logp + row, o_lp);
+    if (lane == 0) bulk_wait_read();   // the store of the previous frame has read xo (a whole step ago)
+    __syncwarp();
+    if (drawn != o_show) {
+      if (drawn != none) erase(drawn);
+      if (o_show != none) draw(o_show);
+      drawn = o_show;
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_store_s2g(P.states + ((int64_t)(o_t + 1) * n + e0) * n_in, s_o, (uint32_t)(32 * n_in * sizeof(float)), l2pol);
+      bulk_commit();
+    }
+  };
   for (int t = 0; t < P.T; ++t) {
     if ((t % POLICY_RNG_STEPS) == 0) {   // the random bits of the next POLICY_RNG_STEPS steps, four envs per Philox call
-      for (int k = tid; k < POLICY_RNG_STEPS * 8; k += POLICY_THREADS) {
+      for (int k = tid; k < POLICY_RNG_STEPS * 8; k += ROLLOUT_THREADS) {
         const int tt = k >> 3, q = k & 7;
         const CxPhilox4 p = cx_philox4(P.seed ^ 0x5A4D504C45ull, quad0 + (uint64_t)q, step_base + (uint64_t)(t + tt));
         reinterpret_cast<uint4*>(s_bits)[tt * 8 + q] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
       }
     }
-    policy_hidden_shares_layered(s_w, s_list, n_list, s_drawn[lane], s_h, A, R, warp, lane);
-    __syncthreads();
+    if (warp > 0) {
+      policy_hidden_shares_layered(s_w, s_list, n_before, n_static, agent_k * (uint32_t)cells, (uint32_t)cells,
+                                   s_drawn[lane], s_h, A, R, mw, lane);
+    } else if (owed) {
+      settle();
+    }
+    __syncthreads();   // the logit shares of step t are complete
     if (warp == 0) {
       float w[CX_MAX_ACTIONS];
       policy_logits(s_h, R, A, lane, w);
@@ -172,12 +209,14 @@ __global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const _
       const uint32_t idx = min(a, n_actions) * stride + cell;
       uint32_t e = s_tt[idx];
       float rw = s_tr[idx];
-      if (H.track && (ts & CX_OVER_BIT)) {  // auto_reset == 0 and the episode ended: frozen env
-        e = cell | (drawn << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
+      const bool frozen = H.track && (ts & CX_OVER_BIT);   // auto_reset == 0 and the episode ended
+      const uint32_t show = frozen ? s_drawn[lane] : (e >> 8) & 0xFF;
+      s_drawn[lane] = show;                                 // all the next hidden layer waits for
+      if (frozen) {
+        e = cell | (show << 8) | ((CX_FLAG_ALREADY_OVER | CX_FLAG_REWARD_NONE) << 16);
         rw = 0.0f;
       }
       uint32_t p = e & 0xFF;
-      const uint32_t show = (e >> 8) & 0xFF;
       uint32_t f = e >> 16;
       if (H.track && !(f & (CX_FLAG_BAD_ACTION | CX_FLAG_ALREADY_OVER))) {
         const uint32_t steps = min(ts + 1u, (uint32_t)CX_STEP_MAX);
@@ -196,30 +235,18 @@ __global__ void __launch_bounds__(POLICY_THREADS) k_agent_policy_rollout(const _
         }
       }
       cell = p;
-      const int64_t row = (int64_t)t * n + env;
-      P.actions[row] = (uint8_t)a;
-      __stcs(P.reward + row, rw);
-      P.flags[row] = (uint8_t)f;
-      if (P.logp) __stcs(P.logp + row, lp);
-      // ---- the next policy input: move the agent in both copies, ship the env-major one ----
-      if (lane == 0) bulk_wait_read();   // the store of the previous frame has read xo (a whole hidden layer ago)
-      __syncwarp();
-      if (drawn != show) {
-        if (drawn != none) erase(drawn);
-        if (show != none) draw(show);
-        drawn = show;
-        s_drawn[lane] = drawn;
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        bulk_store_s2g(P.states + ((int64_t)(t + 1) * n + e0) * n_in, s_o, (uint32_t)(32 * n_in * sizeof(float)), l2pol);
-        bulk_commit();
-      }
+      owed = true;
+      o_t = t;
+      o_a = a;
+      o_f = f;
+      o_show = show;
+      o_rw = rw;
+      o_lp = lp;
     }
-    __syncthreads();   // the drawn cells are up to date for the next hidden layer; the logit shares may be overwritten
+    __syncthreads();   // the drawn cells of step t are published; the logit shares may be overwritten
   }
   if (warp == 0) {
+    if (owed) settle();
     if (lane == 0) bulk_wait_read();   // shared memory must outlive the last bulk read
     __syncwarp();
     P.cell[env] = (uint8_t)cell;
@@ -303,7 +330,7 @@ int cx_launch_agent_policy_rollout(const cx_game* g, void* d_state, int64_t n, i
     cx_set_error("cx_rollout_policy: too many environments for one launch");
     return CX_ERR_INVALID_ARG;
   }
-  k_agent_policy_rollout<<<(unsigned)grid, POLICY_THREADS, smem, s>>>(P);
+  k_agent_policy_rollout<<<(unsigned)grid, ROLLOUT_THREADS, smem, s>>>(P);
   CX_CUDA_OK(cudaGetLastError());
   return CX_OK;
 }

@@ -128,29 +128,42 @@ __device__ __forceinline__ void policy_hidden_shares(const float* s_w, const flo
 }
 
 // The same hidden layer for inputs that are a layered board (campx/rendering.py:204-215: one 0/1 plane per character, so
-// exactly one input per cell is 1): only the inputs that CAN be nonzero are visited -- the static scene's set cells and
-// the agent's plane, `n_list` entries in ascending input order (list[i] = input index d | cell << 16 | is_agent << 31),
-// against n_in for the dense loop.  Lane = env: `drawn` is the cell where this env's agent is drawn (cells: nowhere); an
-// input of the static scene is 0 where the agent covers it, an input of the agent's plane 1 at `drawn`.  Skipped inputs
-// are 0 for every env and fmaf(w, 0, acc) == acc, so the result has the bits of policy_hidden_shares on the full row.
-__device__ __forceinline__ void policy_hidden_shares_layered(const float* s_w, const uint32_t* s_list, int n_list, uint32_t drawn,
-                                                             float* s_h, int A, const PolicyRegs& R, int warp, int lane) {
-  const int j0 = warp * 4;
+// exactly one input per cell is 1): only the inputs that are nonzero are visited, in ascending input order -- the static
+// scene's set cells (list[i] = row of W1^T as a float4 index d * 8 | cell << 16; the first n_before of them lie in
+// front of the agent's plane), minus the one the agent covers, plus ONE term of the agent's plane, W1^T[agent_k * cells +
+// drawn], gathered per lane.  Lane = env: `drawn` is the cell where this env's agent is drawn (>= cells: nowhere).
+// Skipped inputs are 0 and fmaf(w, 0, acc) == acc, so the result has the bits of policy_hidden_shares on the full row.
+__device__ __forceinline__ void policy_hidden_shares_layered(const float* s_w, const uint32_t* s_list, int n_before, int n_static,
+                                                             uint32_t agent_row, uint32_t cells, uint32_t drawn, float* s_h,
+                                                             int A, const PolicyRegs& R, int mw, int lane) {
+  const int j0 = mw * 4;
   float acc[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) acc[u] = __shfl_sync(0xffffffffu, R.b1r, u);
   const float4* wp = reinterpret_cast<const float4*>(s_w + j0);
+  auto statics = [&](int lo, int hi) {
 #pragma unroll 4
-  for (int i = 0; i < n_list; ++i) {
-    const uint32_t it = s_list[i], d = it & 0xFFFFu, c = (it >> 16) & 0x7FFFu;
-    const bool agent = (it >> 31) != 0;
-    const float xv = (agent == (c == drawn)) ? 1.0f : 0.0f;   // agent plane: set at drawn; static: set unless covered
-    const float4 wa = wp[d * 8];
+    for (int i = lo; i < hi; ++i) {
+      const uint32_t it = s_list[i];
+      const float xv = (it >> 16) != drawn ? 1.0f : 0.0f;     // set unless the agent covers the cell
+      const float4 wa = wp[it & 0xFFFFu];
+      acc[0] = fmaf(wa.x, xv, acc[0]);
+      acc[1] = fmaf(wa.y, xv, acc[1]);
+      acc[2] = fmaf(wa.z, xv, acc[2]);
+      acc[3] = fmaf(wa.w, xv, acc[3]);
+    }
+  };
+  statics(0, n_before);
+  {
+    const bool on = drawn < cells;
+    const float4 wa = wp[(agent_row + (on ? drawn : 0u)) * 8u];
+    const float xv = on ? 1.0f : 0.0f;
     acc[0] = fmaf(wa.x, xv, acc[0]);
     acc[1] = fmaf(wa.y, xv, acc[1]);
     acc[2] = fmaf(wa.z, xv, acc[2]);
     acc[3] = fmaf(wa.w, xv, acc[3]);
   }
+  statics(n_before, n_static);
 #pragma unroll
   for (int u = 0; u < 4; ++u) acc[u] = fmaxf(acc[u], 0.0f);                               // relu(affine1(x))
 #pragma unroll
@@ -158,7 +171,7 @@ __device__ __forceinline__ void policy_hidden_shares_layered(const float* s_w, c
     if (a < A) {                                                                          // warp-uniform
       const float c0 = __shfl_sync(0xffffffffu, R.w2r.x, a), c1 = __shfl_sync(0xffffffffu, R.w2r.y, a);
       const float c2 = __shfl_sync(0xffffffffu, R.w2r.z, a), c3 = __shfl_sync(0xffffffffu, R.w2r.w, a);
-      s_h[(warp * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane] = fmaf(c3, acc[3], fmaf(c2, acc[2], fmaf(c1, acc[1], c0 * acc[0])));
+      s_h[(mw * CX_MAX_ACTIONS + a) * POLICY_PITCH + lane] = fmaf(c3, acc[3], fmaf(c2, acc[2], fmaf(c1, acc[1], c0 * acc[0])));
     }
   }
 }
