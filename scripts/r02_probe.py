@@ -196,11 +196,12 @@ if __name__ == "__main__":
 
 def lane_knobs():
     """k_agent_rollout_lane at BASELINE config 1 (Demo 1, 65,536 envs): warps per CTA, steps per launch."""
-    for wpc in ("1",):
-        os.environ.pop("CX_AGENT_PDL", None); os.environ.pop("CX_AGENT_LANE_N", None); os.environ.pop("CX_AGENT_SMALL_N", None)
+    for wpc in (os.environ.get("LANEKNOB_MODES", "1").split(",")):
+        os.environ.pop("CX_AGENT_PDL", None); os.environ.pop("CX_AGENT_LANE_N", None); os.environ.pop("CX_AGENT_SMALL_N", None); os.environ.pop("CX_AGENT_WT", None)
+        if wpc.startswith("wt"): os.environ.update(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT=wpc[2:])
         if wpc.endswith("pdl0"): os.environ["CX_AGENT_PDL"] = "0"
         if wpc.startswith("tile64"): os.environ.update(CX_AGENT_LANE_N="0", CX_AGENT_SMALL_N="0", CX_AGENT_WT="64")
-        for n in (4096, 16384, 32768, 65536, 131072, 262144):
+        for n in [int(x) for x in os.environ.get("LANEKNOB_SIZES", "4096,16384,32768,65536,131072,262144").split(",")]:
             for T in (32, 100):
                 g = NativeGame(expected_spec("demo1", max_episode_steps=100, track_returns=True), n)
                 nb = max(2, int(400e6 // (n * T * 31)) + 1)
