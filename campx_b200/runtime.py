@@ -347,7 +347,9 @@ class NativeGame(object):
 
     @property
     def stats_tensor(self):
-        """float64[8] view of the (folded) episode statistics inside the state blob (all-reducible in place)."""
+        """float64[8] view of the (folded) episode statistics inside the state blob.  The kernels keep adding to the
+        blob, so all-reduce a CLONE over ranks (campx_b200.dist.all_reduce_stats), not the view itself -- a view that
+        holds the global sums would be summed over ranks again at the next report."""
         self.fold_stats()
         return self.state[:8 * N.CX_STATS_DOUBLES].view(torch.float64)
 
